@@ -1,0 +1,546 @@
+/*
+ * bsp_core.h -- per-thread bodies of the banded generalized eigensolver.
+ *
+ * One CUDA thread owns one eigenpair (pencil p, index e) and walks the band of
+ * H - sigma S row by row with a (B+1)x(B+1) Schur-complement window kept in
+ * registers (all indices static after unrolling by B+1).  The bodies are
+ * written as host/device functions over plain pointers so the __global__
+ * wrappers in bsp_kernels.cu stay thin, and so tests/ can replay exactly this
+ * logic on the CPU (tests/emul/; test infrastructure, never a product path).
+ *
+ * Replaces the work LAPACK DSYGV does at matrices.f90:248 of the reference
+ * (dpotrf -> dsygst -> dsytrd -> dorgtr -> dsteqr -> dtrsm, all dense O(N^3))
+ * by a band-native pipeline, O(N^2 b^2) per pencil and parallel over the N
+ * eigenpairs:
+ *   1. multisection with Sturm counts  nu(sigma) = #negative pivots of the
+ *      banded LDL^T of H - sigma S  (Sylvester inertia; S is SPD),
+ *   2. inverse iteration / Rayleigh-quotient iteration on the banded pencil,
+ *      the last steps in residual-correction form so that the un-pivoted LDL^T
+ *      only has to be a contraction, not an accurate solver,
+ *   3. S-normalisation, sign convention, transpose to column-major C.
+ *
+ * Band storage ("full-band rows"): row i of a matrix with half bandwidth B is
+ *   fb[i*FS + c] = A(i, i-B+c),  c = 0..2B,  FS = 2B+2  (0-based i).
+ * Rows n..nrows-1 are padding: diag(H)=1, everything else 0, which decouples
+ * them and keeps every count unchanged.
+ */
+#ifndef BSP_CORE_H
+#define BSP_CORE_H
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BSP_HD __host__ __device__ __forceinline__
+#else
+#define BSP_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define BSP_LDG(p) __ldg(p)
+#define BSP_RCP(x) __drcp_rn(x)
+#else
+#define BSP_LDG(p) (*(p))
+#define BSP_RCP(x) (1.0 / (x))
+#endif
+
+#define BSP_EPS 2.220446049250313e-16
+
+/* refinement status bits */
+#define BSP_ST_CONVERGED 1
+
+struct BspEigChunk {
+    /* geometry */
+    int n;        /* basis size                                   */
+    int npad;     /* n rounded up to a multiple of B+1            */
+    int nrows;    /* rows stored per band matrix = npad + B + 1   */
+    int xrows;    /* rows of X / R workspaces   = npad + B + 1    */
+    int ldw;      /* eigen-index stride (n rounded up to 32)      */
+    int npencil;  /* pencils in this chunk                        */
+    /* pencils */
+    const double *fbH; /* [npencil][nrows][FS]  H_l = H0 + c_l Q  */
+    const double *fbS; /* [ninst][nrows][FS]                      */
+    const int *inst;   /* [npencil] instance of each pencil       */
+    const int *nvec;   /* [npencil] eigenvectors wanted           */
+    double *pbound;    /* [npencil][4]  lo0, hi0, hmax, smax      */
+    /* bracket state, double buffered: index (buf*npencil + p)*ldw + e */
+    double *lo, *hi;
+    int *clo, *chi;
+    double *samp_s; /* [2][npencil][ldw] published samples        */
+    int *samp_c;
+    double *gap;    /* [npencil][ldw] lower bound of the gap      */
+    int *done;      /* [npencil][ldw]                             */
+    /* refinement state [npencil][ldw] */
+    double *sigma, *rho, *rho_prev, *scale, *res;
+    int *status;
+    /* workspaces */
+    double *L; /* [npencil][npad][B+1][ldw]  (zd, l_1..l_B)       */
+    double *X; /* [npencil][xrows][ldw]                           */
+    double *R; /* [npencil][xrows][ldw]                           */
+    int *counters; /* [0] brackets not done, [1] eigenpairs not converged */
+    /* tunables */
+    double tau;       /* bracket width / gap at hand-over         */
+    double delta_rel; /* shift offset / gap in correction steps   */
+    double conv_tol;  /* scaled residual that ends the iteration  */
+};
+
+/* ------------------------------------------------------------------------- */
+BSP_HD double bsp_hash_uniform(uint32_t a, uint32_t b, uint32_t c)
+{
+    /* stateless integer hash -> uniform in (-1, 1); start vector of the
+     * inverse iteration (dstein draws a random vector at the same point) */
+    uint32_t x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return ((double)x + 0.5) * (2.0 / 4294967296.0) - 1.0;
+}
+
+/* ------------------------------------------------------------------------- *
+ * Sturm count: number of negative pivots of LDL^T(H - sigma S) over rows
+ * 0..npad-1.  first_neg (optional) receives the first row with a pivot <= 0.
+ * ------------------------------------------------------------------------- */
+template <int B>
+BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restrict__ fbS, int npad,
+                           double sigma, double pivmin, int *first_neg)
+{
+    constexpr int K1 = B + 1;
+    constexpr int FS = 2 * B + 2;
+    double w[K1][K1];
+    int cnt = 0, first = -1;
+#pragma unroll
+    for (int r = 0; r < K1; ++r) {
+#pragma unroll
+        for (int c = 0; c < K1; ++c) {
+            if (c <= r) {
+                const int off = r * FS + (c - r + B);
+                w[r][c] = fma(-sigma, BSP_LDG(fbS + off), BSP_LDG(fbH + off));
+            } else {
+                w[r][c] = 0.0;
+            }
+        }
+    }
+    for (int j0 = 0; j0 < npad; j0 += K1) {
+#pragma unroll
+        for (int t = 0; t < K1; ++t) {
+            const int j = j0 + t;
+            double d = w[t][t];
+            if (fabs(d) < pivmin) d = -pivmin;
+            if (d < 0.0) { ++cnt; if (first < 0) first = j; }
+            const double rinv = BSP_RCP(d);
+            double col[K1], l[K1];
+#pragma unroll
+            for (int i = 1; i <= B; ++i) {
+                col[i] = w[(t + i) % K1][t];
+                l[i] = col[i] * rinv;
+            }
+#pragma unroll
+            for (int m = 1; m <= B; ++m) {
+#pragma unroll
+                for (int i = m; i <= B; ++i) {
+                    w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
+                }
+            }
+            /* row j retires; its slot takes row j+B+1 */
+            const double *hrow = fbH + (size_t)(j + K1) * FS;
+            const double *srow = fbS + (size_t)(j + K1) * FS;
+#pragma unroll
+            for (int m = 0; m <= B; ++m) {
+                w[t][(t + 1 + m) % K1] = fma(-sigma, BSP_LDG(srow + m), BSP_LDG(hrow + m));
+            }
+        }
+    }
+    if (first_neg) *first_neg = first;
+    return cnt;
+}
+
+/* ------------------------------------------------------------------------- *
+ * bounds: candidate 0..15 -> +s0*2^t, 16..31 -> -s0*2^(t-31)
+ * ------------------------------------------------------------------------- */
+template <int B>
+BSP_HD void bsp_bounds_candidate(const BspEigChunk &g, int p, int lane, double *cand_s, int *cand_c)
+{
+    constexpr int FS = 2 * B + 2;
+    const double *fbH = g.fbH + (size_t)p * g.nrows * FS;
+    const double *fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
+    double s0 = 0.0, hmax = 0.0, smax = 0.0;
+    for (int j = 0; j < g.n; ++j) {
+        const double h = fabs(fbH[(size_t)j * FS + B]);
+        const double s = fbS[(size_t)j * FS + B];
+        if (h > hmax) hmax = h;
+        if (s > smax) smax = s;
+        const double q = h / s;
+        if (q > s0) s0 = q;
+    }
+    if (!(s0 > 0.0)) s0 = 1.0;
+    double sig;
+    if (lane < 16) sig = ldexp(s0, lane);
+    else sig = -ldexp(s0, lane - 31);
+    const double pivmin = 1e-30 * (hmax + fabs(sig) * smax);
+    cand_s[p * 32 + lane] = sig;
+    cand_c[p * 32 + lane] = bsp_sturm_count<B>(fbH, fbS, g.npad, sig, pivmin, nullptr);
+    if (lane == 0) {
+        g.pbound[p * 4 + 2] = hmax;
+        g.pbound[p * 4 + 3] = smax;
+    }
+}
+
+BSP_HD void bsp_bounds_pick(const BspEigChunk &g, int p, const double *cand_s, const int *cand_c)
+{
+    /* smallest positive candidate with count n; negative candidate of smallest
+     * magnitude with count 0.  The ladders span 2^-15 .. 2^15 times max|H_jj|/S_jj. */
+    double hi0 = cand_s[p * 32 + 15], lo0 = cand_s[p * 32 + 16];
+    for (int t = 15; t >= 0; --t)
+        if (cand_c[p * 32 + t] >= g.n) hi0 = cand_s[p * 32 + t];
+    for (int t = 16; t < 32; ++t)
+        if (cand_c[p * 32 + t] == 0) lo0 = cand_s[p * 32 + t];
+    g.pbound[p * 4 + 0] = lo0;
+    g.pbound[p * 4 + 1] = hi0;
+}
+
+/* ------------------------------------------------------------------------- *
+ * one multisection round for eigen index e of pencil p.
+ * reads bracket buffer (round&1), writes buffer ((round+1)&1).
+ * ------------------------------------------------------------------------- */
+template <int B>
+BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round)
+{
+    constexpr int FS = 2 * B + 2;
+    const int n = g.n;
+    if (e >= n) return;
+    const size_t per = (size_t)g.npencil * g.ldw;
+    const size_t id = (size_t)p * g.ldw + e;
+    const size_t rd = (size_t)(round & 1) * per, wr = (size_t)((round + 1) & 1) * per;
+    double lo, hi;
+    int clo, chi;
+    if (round == 0) {
+        lo = g.pbound[p * 4 + 0]; hi = g.pbound[p * 4 + 1]; clo = 0; chi = n;
+    } else {
+        lo = g.lo[rd + id]; hi = g.hi[rd + id]; clo = g.clo[rd + id]; chi = g.chi[rd + id];
+    }
+    int was_done = (round == 0) ? 0 : g.done[id];
+    if (round > 0 && !was_done) {
+        /* tighten with the samples every eigen index of this pencil published
+         * last round: s is non-decreasing in the index, c = nu(s) monotone */
+        const double *S = g.samp_s + (size_t)((round - 1) & 1) * per + (size_t)p * g.ldw;
+        const int *Cc = g.samp_c + (size_t)((round - 1) & 1) * per + (size_t)p * g.ldw;
+        int a = -1, b = n;
+        while (b - a > 1) {
+            const int mid = (a + b) >> 1;
+            if (Cc[mid] > e) b = mid; else a = mid;
+        }
+        if (a >= 0) {
+            const double s = S[a];
+            if (s > lo && s < hi) { lo = s; clo = Cc[a]; }
+        }
+        if (b < n) {
+            const double s = S[b];
+            if (s < hi && s > lo) { hi = s; chi = Cc[b]; }
+        }
+    }
+    /* gap to the neighbours' brackets (theirs as of last round: still valid) */
+    double gl = INFINITY, gr = INFINITY;
+    if (round > 0) {
+        if (e > 0) gl = lo - g.hi[rd + id - 1];
+        if (e + 1 < n) gr = g.lo[rd + id + 1] - hi;
+    } else {
+        if (n > 1) { gl = 0.0; gr = 0.0; }
+    }
+    const double gp = fmin(gl, gr);
+    const double wdt = hi - lo;
+    const double amax = fmax(fabs(lo), fabs(hi));
+    int done = was_done;
+    if (!done) {
+        if (wdt <= 4.0 * BSP_EPS * amax + 1e-300) done = 1;
+        else if (e < g.nvec[p] && gp > 0.0 && wdt <= g.tau * gp) done = 1;
+    }
+    double s = lo;
+    int c = clo;
+    if (!done) {
+        int m = chi - clo, rk = e - clo;
+        if (m < 1) m = 1;
+        if (rk < 0) rk = 0;
+        if (rk > m - 1) rk = m - 1;
+        double frac = ((double)rk + 0.5) / (double)m;
+        if (round == 0) frac = frac * frac; /* box states: E_i ~ i^2 */
+        s = lo + wdt * frac;
+        if (!(s > lo && s < hi)) {
+            done = 1; s = lo; c = clo;
+        } else {
+            const double *fbH = g.fbH + (size_t)p * g.nrows * FS;
+            const double *fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
+            const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(s) * g.pbound[p * 4 + 3]);
+            c = bsp_sturm_count<B>(fbH, fbS, g.npad, s, pivmin, nullptr);
+            if (c <= e) { lo = s; clo = c; } else { hi = s; chi = c; }
+        }
+    }
+    g.lo[wr + id] = lo; g.hi[wr + id] = hi; g.clo[wr + id] = clo; g.chi[wr + id] = chi;
+    g.samp_s[(size_t)(round & 1) * per + id] = s;
+    g.samp_c[(size_t)(round & 1) * per + id] = c;
+    g.gap[id] = gp;
+    g.done[id] = done;
+    if (!done) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(g.counters + 0, 1);
+#else
+        g.counters[0] += 1;
+#endif
+    }
+}
+
+/* ------------------------------------------------------------------------- *
+ * hand-over: final brackets live in buffer `buf`; copy to buffer 0, set the
+ * first shift to the bracket midpoint.
+ * ------------------------------------------------------------------------- */
+BSP_HD void bsp_refine_prepare(const BspEigChunk &g, int p, int e, int buf)
+{
+    if (e >= g.n) return;
+    const size_t per = (size_t)g.npencil * g.ldw;
+    const size_t id = (size_t)p * g.ldw + e;
+    const double lo = g.lo[(size_t)buf * per + id], hi = g.hi[(size_t)buf * per + id];
+    if (buf != 0) { g.lo[id] = lo; g.hi[id] = hi; }
+    const double mid = 0.5 * (lo + hi);
+    g.sigma[id] = mid;
+    g.rho[id] = mid;
+    g.rho_prev[id] = mid;
+    g.scale[id] = 1.0;
+    g.res[id] = INFINITY;
+    g.status[id] = (e < g.nvec[p]) ? 0 : BSP_ST_CONVERGED;
+}
+
+/* ------------------------------------------------------------------------- *
+ * F pass: LDL^T of H - sigma S fused with the forward substitution of the
+ * right-hand side; stores (zd, l_1..l_B) per row.  Also refines the bracket
+ * with the inertia it gets for free.
+ *   iter == 0 : rhs = hashed uniform(-1,1)      (plain inverse iteration)
+ *   iter  > 0 : rhs = scale * R  (R written by the previous B pass)
+ * ------------------------------------------------------------------------- */
+template <int B>
+BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
+{
+    constexpr int K1 = B + 1;
+    constexpr int FS = 2 * B + 2;
+    if (e >= g.n) return;
+    const size_t id = (size_t)p * g.ldw + e;
+    if (g.status[id] & BSP_ST_CONVERGED) return;
+    const int n = g.n, npad = g.npad, ldw = g.ldw;
+    const double *__restrict__ fbH = g.fbH + (size_t)p * g.nrows * FS;
+    const double *__restrict__ fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
+    const double sigma = g.sigma[id];
+    const double sc = g.scale[id];
+    const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(sigma) * g.pbound[p * 4 + 3]);
+    const double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
+    double *__restrict__ Lp = g.L + (size_t)p * npad * K1 * ldw + e;
+
+    double w[K1][K1], y[K1];
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < K1; ++r) {
+#pragma unroll
+        for (int c = 0; c < K1; ++c) {
+            if (c <= r) {
+                const int off = r * FS + (c - r + B);
+                w[r][c] = fma(-sigma, BSP_LDG(fbS + off), BSP_LDG(fbH + off));
+            } else {
+                w[r][c] = 0.0;
+            }
+        }
+        if (r < n) y[r] = (iter == 0) ? bsp_hash_uniform((uint32_t)p, (uint32_t)e, (uint32_t)r)
+                                       : sc * Rp[(size_t)r * ldw];
+        else y[r] = 0.0;
+    }
+    for (int j0 = 0; j0 < npad; j0 += K1) {
+#pragma unroll
+        for (int t = 0; t < K1; ++t) {
+            const int j = j0 + t;
+            double d = w[t][t];
+            if (fabs(d) < pivmin) d = -pivmin;
+            if (d < 0.0) ++cnt;
+            const double rinv = BSP_RCP(d);
+            double col[K1], l[K1];
+            const double y0 = y[t];
+            double *Lrow = Lp + (size_t)j * K1 * ldw;
+            Lrow[0] = y0 * rinv;
+#pragma unroll
+            for (int i = 1; i <= B; ++i) {
+                col[i] = w[(t + i) % K1][t];
+                l[i] = col[i] * rinv;
+                Lrow[(size_t)i * ldw] = l[i];
+                y[(t + i) % K1] = fma(-l[i], y0, y[(t + i) % K1]);
+            }
+#pragma unroll
+            for (int m = 1; m <= B; ++m) {
+#pragma unroll
+                for (int i = m; i <= B; ++i) {
+                    w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
+                }
+            }
+            const int rn = j + K1;
+            const double *hrow = fbH + (size_t)rn * FS;
+            const double *srow = fbS + (size_t)rn * FS;
+#pragma unroll
+            for (int m = 0; m <= B; ++m) {
+                w[t][(t + 1 + m) % K1] = fma(-sigma, BSP_LDG(srow + m), BSP_LDG(hrow + m));
+            }
+            if (rn < n) y[t] = (iter == 0) ? bsp_hash_uniform((uint32_t)p, (uint32_t)e, (uint32_t)rn)
+                                           : sc * Rp[(size_t)rn * ldw];
+            else y[t] = 0.0;
+        }
+    }
+    /* inertia -> bracket (buffer 0) */
+    if (cnt <= e) { if (sigma > g.lo[id]) g.lo[id] = sigma; }
+    else { if (sigma < g.hi[id]) g.hi[id] = sigma; }
+}
+
+/* ------------------------------------------------------------------------- *
+ * B pass: back substitution  y = L^-T (zd);  x_new = cx*scale*x_old - y;
+ * banded matvecs s = S x_new, h = H x_new on a sliding window; Rayleigh
+ * quotient, residual, next right-hand side and next shift.
+ *   corr_now  : this iteration is in correction form (cx = 1) else plain (cx = 0)
+ *   corr_next : what to leave in R for the next F pass:
+ *               1 -> h - rho' s  (rho' = Rayleigh quotient known at pass start)
+ *               0 -> s
+ * ------------------------------------------------------------------------- */
+template <int B>
+BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now, int corr_next)
+{
+    constexpr int K1 = B + 1;
+    constexpr int FS = 2 * B + 2;
+    constexpr int W = 2 * B + 1;
+    if (e >= g.n) return;
+    const size_t id = (size_t)p * g.ldw + e;
+    if (g.status[id] & BSP_ST_CONVERGED) return;
+    const int n = g.n, npad = g.npad, ldw = g.ldw;
+    const double *__restrict__ fbH = g.fbH + (size_t)p * g.nrows * FS;
+    const double *__restrict__ fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
+    const double *__restrict__ Lp = g.L + (size_t)p * npad * K1 * ldw + e;
+    double *__restrict__ Xp = g.X + (size_t)p * g.xrows * ldw + e;
+    double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
+    const double sc = g.scale[id];
+    const double rho_p = g.rho[id]; /* rho' */
+    const double cx = corr_now ? sc : 0.0;
+
+    double yw[B > 0 ? B : 1];  /* y_{j+1..j+B} */
+    double xw[W];              /* x_new[j .. j+2B] */
+#pragma unroll
+    for (int i = 0; i < B; ++i) yw[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) xw[i] = 0.0;
+    double xSx = 0.0, xHx = 0.0, resmax = 0.0;
+
+    for (int j = npad - 1; j >= -B; --j) {
+        double xn = 0.0;
+        if (j >= 0) {
+            const double *Lrow = Lp + (size_t)j * K1 * ldw;
+            double yj = Lrow[0];
+#pragma unroll
+            for (int i = B; i >= 1; --i) yj = fma(-Lrow[(size_t)i * ldw], yw[i - 1], yj);
+#pragma unroll
+            for (int i = B - 1; i >= 1; --i) yw[i] = yw[i - 1];
+            yw[0] = yj;
+            if (j < n) {
+                const double xo = corr_now ? Xp[(size_t)j * ldw] : 0.0;
+                xn = fma(cx, xo, -yj);
+                Xp[(size_t)j * ldw] = xn;
+            }
+        }
+#pragma unroll
+        for (int c = W - 1; c >= 1; --c) xw[c] = xw[c - 1];
+        xw[0] = xn;
+        /* row i = j + B now has its whole stencil x_new[j .. j+2B] */
+        const int i = j + B;
+        if (i < n) {
+            const double *hrow = fbH + (size_t)i * FS;
+            const double *srow = fbS + (size_t)i * FS;
+            double s = 0.0, h = 0.0;
+#pragma unroll
+            for (int c = 0; c < W; ++c) {
+                s = fma(BSP_LDG(srow + c), xw[c], s);
+                h = fma(BSP_LDG(hrow + c), xw[c], h);
+            }
+            const double xi = xw[B];
+            xSx = fma(xi, s, xSx);
+            xHx = fma(xi, h, xHx);
+            const double r = fma(-rho_p, s, h);
+            resmax = fmax(resmax, fabs(r));
+            Rp[(size_t)i * ldw] = corr_next ? r : s;
+        }
+    }
+    /* bookkeeping + next shift */
+    double lo = g.lo[id], hi = g.hi[id];
+    const double good = (xSx > 0.0 && xSx < INFINITY) ? 1.0 : 0.0;
+    double rho_new = rho_p, scn = sc, res = INFINITY;
+    if (good != 0.0) {
+        rho_new = xHx / xSx;
+        scn = 1.0 / sqrt(xSx);
+        res = resmax * scn;
+    }
+    g.rho_prev[id] = rho_p;
+    g.rho[id] = rho_new;
+    g.scale[id] = scn;
+    g.res[id] = res;
+    double sig = (rho_new > lo && rho_new < hi) ? rho_new : 0.5 * (lo + hi);
+    if (corr_next) {
+        double gp = g.gap[id];
+        if (!(gp > 0.0) || !(gp < INFINITY)) gp = fmax(hi - lo, fabs(rho_new) * 1e-6 + 1e-12);
+        const double delta = g.delta_rel * gp;
+        if (fabs(sig - rho_p) < delta) sig = (rho_p + delta < hi) ? rho_p + delta : rho_p - delta;
+    }
+    g.sigma[id] = sig;
+}
+
+/* convergence bookkeeping after a B pass (separate tiny kernel so the host can
+ * read one counter): marks eigenpairs whose scaled residual is below conv_tol */
+BSP_HD void bsp_check_converged(const BspEigChunk &g, int p, int e, int allow)
+{
+    if (e >= g.n) return;
+    const size_t id = (size_t)p * g.ldw + e;
+    if (g.status[id] & BSP_ST_CONVERGED) return;
+    const double r = g.res[id], a = fmax(1.0, fabs(g.rho[id]));
+    if (allow && r <= g.conv_tol * a) {
+        g.status[id] |= BSP_ST_CONVERGED;
+    } else {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(g.counters + 1, 1);
+#else
+        g.counters[1] += 1;
+#endif
+    }
+}
+
+/* ------------------------------------------------------------------------- *
+ * finalize, per eigenpair: eigenvalue, normalisation factor with the sign
+ * convention (first coefficient with |c_i| >= 1e-6 max|c| positive).
+ * fac[id] multiplies column e of X when it is transposed into C.
+ * ------------------------------------------------------------------------- */
+BSP_HD void bsp_finalize_eigen(const BspEigChunk &g, int p, int e, double *E, double *fac, int *bad,
+                               double res_tol)
+{
+    if (e >= g.n) return;
+    const size_t id = (size_t)p * g.ldw + e;
+    if (e >= g.nvec[p]) {
+        E[(size_t)p * g.n + e] = 0.5 * (g.lo[id] + g.hi[id]);
+        fac[id] = 0.0;
+        return;
+    }
+    const double rho = g.rho[id];
+    E[(size_t)p * g.n + e] = rho;
+    const double *Xp = g.X + (size_t)p * g.xrows * g.ldw + e;
+    double amax = 0.0;
+    for (int j = 0; j < g.n; ++j) amax = fmax(amax, fabs(Xp[(size_t)j * g.ldw]));
+    double sgn = 1.0;
+    const double thr = 1e-6 * amax;
+    for (int j = 0; j < g.n; ++j) {
+        const double v = Xp[(size_t)j * g.ldw];
+        if (fabs(v) >= thr) { sgn = (v < 0.0) ? -1.0 : 1.0; break; }
+    }
+    fac[id] = sgn * g.scale[id];
+    const double r = g.res[id];
+    if (!(r <= res_tol * fmax(1.0, fabs(rho)))) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(bad + p, 1);
+#else
+        bad[p] += 1;
+#endif
+    }
+}
+
+#endif /* BSP_CORE_H */

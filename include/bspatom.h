@@ -1,0 +1,141 @@
+/*
+ * bspatom.h -- C-ABI of the B200-native replacement for BspAtom's hot path:
+ * B-spline matrix assembly (MATRIX_SVT) + generalized symmetric eigensolve
+ * H c = E S c per angular momentum l (SOLVE_SYSTEM / LAPACK DSYGV), batched,
+ * plus the dense dipole contraction of TRANS_AMP.
+ *
+ * The reference (carlosmwh1985/BspAtom) has no FFI of its own; the seam this
+ * header replaces is
+ *     CALL MATRIX_SVT                      Bsp_Atom.f90:72   (matrices.f90:1-200)
+ *     CALL SOLVE_SYSTEM                    Bsp_Atom.f90:75   (matrices.f90:204-394)
+ *     CALL DSYGV(1,'V','U',nfun,Hij,...)   matrices.f90:248
+ *     CALL DGEMV / DDOT                    PhotoIon.f90:95,103
+ * INTEGRATION.md shows the ISO_C_BINDING interface module a maintainer adds.
+ *
+ * Conventions: everything FP64; matrices column-major (Fortran order); plain
+ * pointers and sizes only; the caller owns every host buffer and the library
+ * keeps no host pointer after a call returns.  Functions return 0 on success,
+ * a negative value -i when argument i is invalid (LAPACK style), or a positive
+ * BSPATOM_E* code; they never exit()/abort() -- the Fortran caller decides to
+ * STOP (matrices.f90:250-254).  One handle drives ONE GPU; multi-GPU runs use
+ * one process (handle) per GPU and shard the (problem, l) list (no collective
+ * on the compute path).  There is NO CPU fallback: without a CUDA device every
+ * entry point fails with BSPATOM_ENODEVICE.
+ */
+#ifndef BSPATOM_H
+#define BSPATOM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSPATOM_VERSION 100
+
+/* positive error codes */
+#define BSPATOM_ENODEVICE 1001 /* no CUDA device / driver                      */
+#define BSPATOM_ECUDA 1002     /* CUDA runtime error (see bspatom_last_error)  */
+#define BSPATOM_EUNSUPPORTED 1003 /* k (bandwidth) outside the compiled range  */
+#define BSPATOM_ESTATE 1004    /* run/download called before upload            */
+#define BSPATOM_ENOMEM 1005
+
+/* potential kinds: 0..2 are the reference's KIND_POT (Modules.f90:263-295) */
+#define BSPATOM_POT_COULOMB 0     /* -Z/r                    par = {Z}                    */
+#define BSPATOM_POT_ROGERS 1      /* par = {Z, Ntot, N1,N2,N3, a1,a2,a3}                  */
+#define BSPATOM_POT_SIMONS_FUES 2 /* -Z/r, Bl(l)/r^2 via ul_extra                         */
+#define BSPATOM_POT_YUKAWA 10     /* -Z exp(-lambda r)/r     par = {Z, lambda}            */
+#define BSPATOM_POT_TIETZ 11      /* -[1+(Z-1)/(1+t r)^2]/r  par = {Z, t}                 */
+#define BSPATOM_POT_TABLE (-1)    /* V given at the quadrature points through v_tab       */
+
+typedef struct bspatom_handle_s *bspatom_handle;
+
+/*
+ * One radial problem = one (instance, l) pencil.  Mirrors the module globals
+ * MATRIX_SVT / SOLVE_SYSTEM read: nfun,k,ka,nkp,rt (Modules.f90:55-58), xg,wg
+ * (Modules.f90:29), KIND_POT,Zatom,Numn,Ntot,alphan,Bl (Modules.f90:213-236).
+ */
+typedef struct bsp_problem {
+    int k;            /* B-spline order                                           */
+    int nfun;         /* basis size N (after READ_INPUTS' remap)                  */
+    int nkp;          /* number of knots = nfun + k                               */
+    int ka;           /* Gauss-Legendre points per knot interval (<= 32)          */
+    const double *rt; /* knots rt(1:nkp) exactly as GRID computed them (host)     */
+    const double *xg; /* GL nodes on [-1,1] (ka) or NULL: library runs gauleg     */
+    const double *wg; /* GL weights (ka) or NULL                                  */
+    int pot_kind;     /* BSPATOM_POT_*                                            */
+    double pot_par[8];
+    const double *v_tab; /* BSPATOM_POT_TABLE: V(r) at point g of interval m
+                            (1-based m = 1..nkp-1) at v_tab[(m-1)*ka + g]        */
+    int l;            /* angular momentum: U_l = [l(l+1) + 2 ul_extra] / (2 r^2)  */
+    double ul_extra;  /* Bl(l) for KIND_POT=2 (matrices.f90:151), else 0          */
+    int nvec;         /* leading eigenvectors wanted, 0..nfun                     */
+} bsp_problem;
+
+/* ---- handle ------------------------------------------------------------- */
+int bspatom_create(bspatom_handle *h, int device_id);
+int bspatom_destroy(bspatom_handle h);
+const char *bspatom_last_error(bspatom_handle h);
+int bspatom_version(void);
+
+/* tunables: name in {"tau","max_rounds","max_iters","chunk","res_tol","polish"} */
+int bspatom_set_option(bspatom_handle h, const char *name, double value);
+
+/* ---- assembly: replaces MATRIX_SVT (matrices.f90:1-200) ------------------ *
+ * Outputs in LAPACK band storage (any may be NULL):
+ *   S, H0 = T+V, Q = int B_i B_j/(2 r^2), T, V, R = int B_i r B_j,
+ *   Rinv = int B_i B_j / r              : upper band, AB(k,nfun), AB(kd+1+i-j,j)=A(i,j), kd=k-1
+ *   D = int B_i B_j'  (non-symmetric)   : general band, AB(2k-1,nfun), AB(kd+1+i-j,j)=A(i,j)
+ * so that  Uij(:,:,l) = [l(l+1)+2 Bl(l)] Q  and  Hij = T + U_l + V = H0 + c_l Q.
+ * Only p->l independent fields of *p are read.                               */
+int bspatom_assemble_band(bspatom_handle h, const bsp_problem *p, double *S, double *H0, double *Q,
+                          double *T, double *V, double *R, double *Rinv, double *D);
+
+/* ---- fused batched path: replaces MATRIX_SVT + the l-loop of SOLVE_SYSTEM -- *
+ * E : sum_p nfun_p doubles, ascending per problem           (En, matrices.f90:248)
+ * C : sum_p nfun_p*nvec_p doubles; problem p's block is column-major
+ *     nfun_p x nvec_p, column j = eigenvector j, C^T S C = I  (Hij on exit of DSYGV).
+ *     Sign: the first coefficient with |c_i| >= 1e-6 max|c| is positive.
+ * info[p]: 0 ok; nfun+i: S not positive definite at pivot i; 1..nfun: that
+ *     many eigenpairs missed the residual tolerance.                         */
+int bspatom_solve_batch(bspatom_handle h, int nprob, const bsp_problem *probs, double *E, double *C,
+                        int *info);
+
+/* same thing in three stages, so that a caller (and bench.py) can keep the
+ * batch resident in HBM: upload copies knots/parameters H2D; run launches the
+ * kernels only (no host<->device traffic, returns after the stream drained);
+ * download copies E, C, info D2H.  C may be NULL to skip the eigenvectors.    */
+int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs);
+int bspatom_batch_run(bspatom_handle h);
+int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info);
+
+/* ---- LAPACK-compatible entry: one-token rename at matrices.f90:248 --------- *
+ * DSYGV semantics for itype=1, jobz='V'|'N', uplo='U'|'L'.  The pencil must be
+ * banded (bandwidth found from the zero pattern; the reference's matrices have
+ * half-bandwidth k-1, matrices.f90:71-72).  On exit A(:,j) = eigenvector j,
+ * w ascending, B = Cholesky factor (U^T U or L L^T).  Trailing hidden
+ * CHARACTER lengths passed by Fortran compilers are ignored.                 */
+void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const int *n, double *A,
+                    const int *lda, double *B, const int *ldb, double *w, double *work,
+                    const int *lwork, int *info, ...);
+
+/* ---- dense contraction: replaces DGEMV+DDOT of TRANS_AMP (PhotoIon.f90:90-105)
+ * D(nf,ni) = Cf^T * A * Ci, A given as general band AB(2*kd+1, n) (ld 2kd+1),
+ * Cf: n x nf, Ci: n x ni, D: nf x ni, all column-major.                      */
+int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf, const double *Cf,
+                   int ni, const double *Ci, double *D);
+
+/* ---- wavefunction synthesis: WRITE_WF (Bsp_Atom.f90:101-152) --------------- *
+ * psi(ip, iv) = sum_j C(j,iv) B_j(r_ip), r_ip = ra + ip (rb-ra)/npts, ip=0..npts */
+int bspatom_wavefunction(bspatom_handle h, int k, int nfun, int nkp, const double *rt, double ra,
+                         double rb, int npts, int nvec, const double *C, double *r_out,
+                         double *psi_out);
+
+/* ---- statistics of the last run (for bench.py) ----------------------------- *
+ * out[0] kernel launches, out[1] multisection rounds, out[2] refinement
+ * iterations, out[3] ms in assembly, out[4] ms eigenvalue stage, out[5] ms
+ * eigenvector stage, out[6] ms finalize, out[7] total device ms               */
+int bspatom_get_stats(bspatom_handle h, double *out, int nout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSPATOM_H */

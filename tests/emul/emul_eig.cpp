@@ -1,0 +1,132 @@
+// CPU replay of the per-thread solver bodies in bspatom_b200/csrc/bsp_core.h and
+// of the stage schedule in bsp_driver.h.  TEST INFRASTRUCTURE ONLY: it exists so
+// that `pytest -m "not gpu"` can check the solver logic (indexing, bracket
+// bookkeeping, iteration schedule) without a GPU.  It is never built into
+// libbspatom.so and nothing in the product imports it.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../bspatom_b200/csrc/bsp_core.h"
+#include "../../bspatom_b200/csrc/bsp_driver.h"
+
+template <int B>
+struct EmulExec {
+    BspEigChunk g;
+    std::vector<double> cand_s;
+    std::vector<int> cand_c;
+    void bounds() {
+        cand_s.assign(g.npencil * 32, 0.0);
+        cand_c.assign(g.npencil * 32, 0);
+        for (int p = 0; p < g.npencil; ++p)
+            for (int l = 0; l < 32; ++l) bsp_bounds_candidate<B>(g, p, l, cand_s.data(), cand_c.data());
+        for (int p = 0; p < g.npencil; ++p) bsp_bounds_pick(g, p, cand_s.data(), cand_c.data());
+    }
+    void round(int r) {
+        for (int p = 0; p < g.npencil; ++p)
+            for (int e = 0; e < g.n; ++e) bsp_multisection_round<B>(g, p, e, r);
+    }
+    void prepare(int buf) {
+        for (int p = 0; p < g.npencil; ++p)
+            for (int e = 0; e < g.n; ++e) bsp_refine_prepare(g, p, e, buf);
+    }
+    void factor(int it) {
+        for (int p = 0; p < g.npencil; ++p)
+            for (int e = 0; e < g.n; ++e) bsp_factor_forward<B>(g, p, e, it);
+    }
+    void back(int cn, int cx) {
+        for (int p = 0; p < g.npencil; ++p)
+            for (int e = 0; e < g.n; ++e) bsp_back_substitute<B>(g, p, e, cn, cx);
+    }
+    void check(int allow) {
+        for (int p = 0; p < g.npencil; ++p)
+            for (int e = 0; e < g.n; ++e) bsp_check_converged(g, p, e, allow);
+    }
+    void zero_counter(int w) { g.counters[w] = 0; }
+    int read_counter(int w) { return g.counters[w]; }
+};
+
+template <int B>
+static int run(int n, int npencil, const double *hb, const double *sb, const int *nvec_in, double tau,
+               double delta_rel, double conv_tol, int max_rounds, int min_iters, int max_iters,
+               double *E, double *C, double *stats)
+{
+    constexpr int K1 = B + 1, FS = 2 * B + 2;
+    BspEigChunk g;
+    memset(&g, 0, sizeof(g));
+    g.n = n;
+    g.npad = ((n + K1 - 1) / K1) * K1;
+    g.nrows = g.npad + B + 1;
+    g.xrows = g.npad + B + 1;
+    g.ldw = ((n + 31) / 32) * 32;
+    g.npencil = npencil;
+    const size_t per = (size_t)npencil * g.ldw;
+    std::vector<double> fbH((size_t)npencil * g.nrows * FS, 0.0), fbS((size_t)npencil * g.nrows * FS, 0.0);
+    for (int p = 0; p < npencil; ++p) {
+        const double *h = hb + (size_t)p * K1 * n, *s = sb + (size_t)p * K1 * n;
+        double *H = fbH.data() + (size_t)p * g.nrows * FS, *S = fbS.data() + (size_t)p * g.nrows * FS;
+        for (int i = 0; i < n; ++i)
+            for (int d = 0; d <= B; ++d) {
+                if (i + d < n) { H[(size_t)i * FS + B + d] = h[(size_t)d * n + i]; S[(size_t)i * FS + B + d] = s[(size_t)d * n + i]; }
+                if (i - d >= 0) { H[(size_t)i * FS + B - d] = h[(size_t)d * n + i - d]; S[(size_t)i * FS + B - d] = s[(size_t)d * n + i - d]; }
+            }
+        for (int i = n; i < g.nrows; ++i) H[(size_t)i * FS + B] = 1.0;
+    }
+    std::vector<int> inst(npencil), nvec(npencil);
+    for (int p = 0; p < npencil; ++p) { inst[p] = p; nvec[p] = nvec_in[p]; }
+    std::vector<double> pbound(npencil * 4), lo(2 * per), hi(2 * per), samp_s(2 * per), gap(per), sigma(per),
+        rho(per), rho_prev(per), scale(per), res(per);
+    std::vector<int> clo(2 * per), chi(2 * per), samp_c(2 * per), done(per), status(per), counters(4);
+    std::vector<double> L((size_t)npencil * g.npad * K1 * g.ldw), X((size_t)npencil * g.xrows * g.ldw, 0.0),
+        R((size_t)npencil * g.xrows * g.ldw, 0.0);
+    g.fbH = fbH.data(); g.fbS = fbS.data(); g.inst = inst.data(); g.nvec = nvec.data();
+    g.pbound = pbound.data(); g.lo = lo.data(); g.hi = hi.data(); g.clo = clo.data(); g.chi = chi.data();
+    g.samp_s = samp_s.data(); g.samp_c = samp_c.data(); g.gap = gap.data(); g.done = done.data();
+    g.sigma = sigma.data(); g.rho = rho.data(); g.rho_prev = rho_prev.data(); g.scale = scale.data();
+    g.res = res.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
+    g.counters = counters.data(); g.tau = tau; g.delta_rel = delta_rel; g.conv_tol = conv_tol;
+    EmulExec<B> ex; ex.g = g;
+    BspSchedule sch = {max_rounds, min_iters, max_iters, 4};
+    BspRunStats st = bsp_run_chunk(ex, sch);
+    std::vector<double> fac(per);
+    std::vector<int> bad(npencil, 0);
+    for (int p = 0; p < npencil; ++p)
+        for (int e = 0; e < n; ++e) bsp_finalize_eigen(g, p, e, E, fac.data(), bad.data(), 1e-9);
+    for (int p = 0; p < npencil; ++p)
+        for (int e = 0; e < nvec[p]; ++e)
+            for (int j = 0; j < n; ++j)
+                C[((size_t)p * n + e) * n + j] = fac[(size_t)p * g.ldw + e] * X[((size_t)p * g.xrows + j) * g.ldw + e];
+    stats[0] = st.rounds; stats[1] = st.iters; stats[2] = st.brackets_open; stats[3] = st.unconverged;
+    double rmax = 0;
+    for (int p = 0; p < npencil; ++p) for (int e = 0; e < nvec[p]; ++e) { double r = res[(size_t)p * g.ldw + e] / fmax(1.0, fabs(rho[(size_t)p * g.ldw + e])); if (!(r <= rmax)) rmax = r; }
+    stats[4] = rmax;
+    int nb = 0; for (int p = 0; p < npencil; ++p) nb += bad[p];
+    stats[5] = nb;
+    return 0;
+}
+
+extern "C" int emul_solve(int n, int B, int npencil, const double *hb, const double *sb, const int *nvec,
+                          double tau, double delta_rel, double conv_tol, int max_rounds, int min_iters,
+                          int max_iters, double *E, double *C, double *stats)
+{
+#define CASE(b) case b: return run<b>(n, npencil, hb, sb, nvec, tau, delta_rel, conv_tol, max_rounds, min_iters, max_iters, E, C, stats);
+    switch (B) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) default: return -2; }
+}
+
+template <int B> static int cnt(int n, const double *hb, const double *sb, double sigma)
+{
+    constexpr int K1 = B + 1, FS = 2 * B + 2;
+    int npad = ((n + K1 - 1) / K1) * K1, nrows = npad + B + 1;
+    std::vector<double> H((size_t)nrows * FS, 0.0), S((size_t)nrows * FS, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d <= B; ++d) {
+            if (i + d < n) { H[(size_t)i * FS + B + d] = hb[(size_t)d * n + i]; S[(size_t)i * FS + B + d] = sb[(size_t)d * n + i]; }
+            if (i - d >= 0) { H[(size_t)i * FS + B - d] = hb[(size_t)d * n + i - d]; S[(size_t)i * FS + B - d] = sb[(size_t)d * n + i - d]; }
+        }
+    for (int i = n; i < nrows; ++i) H[(size_t)i * FS + B] = 1.0;
+    return bsp_sturm_count<B>(H.data(), S.data(), npad, sigma, 1e-300, nullptr);
+}
+extern "C" int emul_count(int n, int B, const double *hb, const double *sb, double sigma)
+{
+#define CASE2(b) case b: return cnt<b>(n, hb, sb, sigma);
+    switch (B) { CASE2(1) CASE2(2) CASE2(3) CASE2(4) CASE2(5) CASE2(6) CASE2(7) CASE2(8) CASE2(9) default: return -2; }
+}
