@@ -1,0 +1,845 @@
+/*
+ * bsp_api.cu -- C-ABI of libbspatom.so (see include/bspatom.h).
+ *
+ * Host side of the B200 path: groups the caller's (instance, l) problems by
+ * (k, nfun, nkp, ka), de-duplicates instances (all l of one potential share
+ * S, H0, Q -- the reference recomputes Uij(:,:,0:lmax), matrices.f90:148-153,
+ * we keep one Q and form H_l = H0 + c_l Q on the fly), runs the assembly
+ * kernel once per instance and the banded eigensolver chunk by chunk.
+ * There is no CPU compute path in this file: without a device every entry
+ * point returns BSPATOM_ENODEVICE.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bspatom.h"
+#include "bsp_assembly.cuh"
+#include "bsp_core.h"
+#include "bsp_driver.h"
+#include "bsp_gemm.cuh"
+#include "bsp_kernels.cuh"
+
+#define BSP_KMIN 3
+#define BSP_KMAX 10
+
+namespace {
+
+struct Options {
+    double tau = 0.02;
+    double delta_rel = 1e-4;
+    double conv_tol = 1e-11;
+    double res_tol = 1e-9;
+    int max_rounds = 90;
+    int min_iters = 4;
+    int max_iters = 12;
+    int first_check_round = 6;
+    int chunk = 0; /* 0 = auto */
+};
+
+struct Group {
+    int k = 0, B = 0, n = 0, nkp = 0, ka = 0, npad = 0, nrows = 0, xrows = 0, ldw = 0, FS = 0;
+    int ninst = 0, npencil = 0;
+    bool any_vtab = false;
+    std::vector<int> prob_index; /* pencil -> caller's problem index */
+    std::vector<int> inst, nvec;
+    std::vector<double> cl;
+    std::vector<long long> coff; /* offset of pencil block inside group C  */
+    long long c_elems = 0;
+    /* device */
+    double *d_rt = nullptr, *d_xgwg = nullptr, *d_vtab = nullptr;
+    BspInstParams *d_par = nullptr;
+    double *d_fbS = nullptr, *d_fbH0 = nullptr, *d_fbQ = nullptr;
+    int *d_inst = nullptr, *d_nvec = nullptr, *d_pdinfo = nullptr, *d_bad = nullptr;
+    double *d_cl = nullptr, *d_E = nullptr, *d_C = nullptr;
+    long long *d_coff = nullptr;
+    std::vector<int> pdinfo, bad;
+};
+
+struct Workspace {
+    size_t bytes = 0;
+    char *base = nullptr;
+};
+
+} // namespace
+
+struct bspatom_handle_s {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    Options opt;
+    std::vector<Group> groups;
+    int nprob = 0;
+    std::vector<long long> e_off, c_off; /* per caller problem: offsets in E and C */
+    std::vector<int> p_n, p_nvec;
+    bool uploaded = false, ran = false;
+    Workspace ws;
+    int *h_counter = nullptr; /* pinned */
+    double stats[16] = {0};
+    long long launches = 0;
+    /* per-kernel-class device timing (CUDA events on the launching stream) */
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_class; /* class of the pair starting at 2*i */
+    size_t ev_used = 0;
+    double k_ms[4] = {0, 0, 0, 0};   /* 0 round, 1 factor, 2 back, 3 assembly */
+    long long k_cnt[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            char b_[512];                                                                      \
+            snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            h->err = b_;                                                                       \
+            return BSPATOM_ECUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+template <class T>
+int dev_alloc(bspatom_handle h, T **p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CU(cudaMalloc((void **)p, count * sizeof(T)));
+    return 0;
+}
+
+void free_group(Group &g)
+{
+    cudaFree(g.d_rt); cudaFree(g.d_xgwg); cudaFree(g.d_vtab); cudaFree(g.d_par);
+    cudaFree(g.d_fbS); cudaFree(g.d_fbH0); cudaFree(g.d_fbQ);
+    cudaFree(g.d_inst); cudaFree(g.d_nvec); cudaFree(g.d_pdinfo); cudaFree(g.d_bad);
+    cudaFree(g.d_cl); cudaFree(g.d_E); cudaFree(g.d_C); cudaFree(g.d_coff);
+    g = Group();
+}
+
+void free_batch(bspatom_handle h)
+{
+    for (auto &g : h->groups) free_group(g);
+    h->groups.clear();
+    h->uploaded = h->ran = false;
+}
+
+/* Gauss-Legendre nodes/weights on [-1,1] by Newton iteration on P_n with the
+ * start values and stopping rule the host program uses (gauleg,
+ * Modules.f90:112-153: z0 = cos(pi (i-1/4)/(n+1/2)), stop at 10 eps), so that a
+ * caller who passes xg = wg = NULL gets the nodes GRID would have produced. */
+void gauss_legendre(int n, double *x, double *w)
+{
+    const double pi = acos(-1.0), tol = 10.0 * BSP_EPS;
+    /* dp deliberately outlives the loop body: for odd n the reference skips the
+     * Newton loop at the middle node (start value cos(pi/2) ~ 6e-17 is within
+     * tol of its initial zold = 0) and forms that weight with the derivative
+     * left over from the previous node.  Kept, because a host that lets the
+     * library compute the nodes must get what GRID would have handed over;
+     * callers wanting exact Gauss-Legendre weights pass xg/wg themselves. */
+    double dp = 1.0;
+    for (int i = 1; i <= (n + 1) / 2; ++i) {
+        double z = cos(pi * (i - 0.25) / (n + 0.5)), zold = 0.0;
+        while (fabs(z - zold) > tol) {
+            double pa = 1.0, pb = 0.0;
+            for (int j = 1; j <= n; ++j) {
+                const double pc = pb;
+                pb = pa;
+                pa = ((2.0 * j - 1.0) * z * pb - (j - 1.0) * pc) / j;
+            }
+            dp = n * (z * pa - pb) / (z * z - 1.0);
+            zold = z;
+            z = zold - pa / dp;
+        }
+        x[i - 1] = -z;
+        x[n - i] = z;
+        w[i - 1] = 2.0 / ((1.0 - z * z) * dp * dp);
+        w[n - i] = w[i - 1];
+    }
+}
+
+int validate_problem(const bsp_problem &p)
+{
+    if (p.k < BSP_KMIN || p.k > BSP_KMAX) return BSPATOM_EUNSUPPORTED;
+    if (p.nfun < 1) return -3;
+    if (p.nkp != p.nfun + p.k) return -3;
+    if (p.ka < 1 || p.ka > 32) return -3;
+    if (!p.rt) return -3;
+    if ((p.xg == nullptr) != (p.wg == nullptr)) return -3;
+    if (p.pot_kind == BSPATOM_POT_TABLE && !p.v_tab) return -3;
+    if (p.nvec < 0 || p.nvec > p.nfun) return -3;
+    if (p.l < 0) return -3;
+    return 0;
+}
+
+struct InstKey {
+    const bsp_problem *p;
+};
+
+bool same_instance(const bsp_problem &a, const bsp_problem &b)
+{
+    if (a.pot_kind != b.pot_kind) return false;
+    if (a.pot_kind == BSPATOM_POT_TABLE) {
+        if (a.v_tab != b.v_tab &&
+            memcmp(a.v_tab, b.v_tab, sizeof(double) * (size_t)(a.nkp - 1) * a.ka) != 0)
+            return false;
+    } else if (memcmp(a.pot_par, b.pot_par, sizeof a.pot_par) != 0) {
+        return false;
+    }
+    if (a.rt != b.rt && memcmp(a.rt, b.rt, sizeof(double) * a.nkp) != 0) return false;
+    if ((a.xg == nullptr) != (b.xg == nullptr)) return false;
+    if (a.xg && a.xg != b.xg && memcmp(a.xg, b.xg, sizeof(double) * a.ka) != 0) return false;
+    if (a.wg && a.wg != b.wg && memcmp(a.wg, b.wg, sizeof(double) * a.ka) != 0) return false;
+    return true;
+}
+
+uint64_t hash_bytes(const void *p, size_t n, uint64_t h)
+{
+    const unsigned char *c = (const unsigned char *)p;
+    for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+uint64_t instance_hash(const bsp_problem &p)
+{
+    uint64_t h = 1469598103934665603ull;
+    h = hash_bytes(&p.pot_kind, sizeof p.pot_kind, h);
+    if (p.pot_kind == BSPATOM_POT_TABLE) h = hash_bytes(p.v_tab, sizeof(double) * (size_t)(p.nkp - 1) * p.ka, h);
+    else h = hash_bytes(p.pot_par, sizeof p.pot_par, h);
+    h = hash_bytes(p.rt, sizeof(double) * p.nkp, h);
+    if (p.xg) h = hash_bytes(p.xg, sizeof(double) * p.ka, h);
+    return h;
+}
+
+/* ---- per-kernel timing ---------------------------------------------------- */
+int timed_begin(bspatom_handle h, int cls)
+{
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+            h->ev_pool.push_back(e);
+        }
+        h->ev_class.push_back(cls);
+    }
+    h->ev_class[h->ev_used / 2] = cls;
+    cudaEventRecord(h->ev_pool[h->ev_used], h->st);
+    return (int)h->ev_used;
+}
+void timed_end(bspatom_handle h, int slot)
+{
+    if (slot < 0) return;
+    cudaEventRecord(h->ev_pool[slot + 1], h->st);
+    h->ev_used = slot + 2;
+}
+/* call after the stream has been synchronised */
+void timed_collect(bspatom_handle h)
+{
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]) == cudaSuccess) {
+            h->k_ms[h->ev_class[i / 2]] += ms;
+            h->k_cnt[h->ev_class[i / 2]] += 1;
+        }
+    }
+    h->ev_used = 0;
+}
+
+/* ---- assembly launch ---------------------------------------------------- */
+template <int K>
+int launch_assembly_k(bspatom_handle h, const BspAsmArgs &a)
+{
+    constexpr int PK = K * (K + 1) / 2;
+    const int per_int = (a.want_pi ? 6 : 4) * PK + (a.want_pi ? K * K : 0);
+    const size_t smem = (size_t)(BSP_ASM_TR + K - 1) * per_int * sizeof(double);
+    dim3 grid((a.nrows + BSP_ASM_TR - 1) / BSP_ASM_TR, a.ninst);
+    if (a.ka <= 16) {
+        CU(cudaFuncSetAttribute(bsp_assemble_kernel<K, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bsp_assemble_kernel<K, 16><<<grid, BSP_ASM_THREADS, smem, h->st>>>(a);
+    } else {
+        CU(cudaFuncSetAttribute(bsp_assemble_kernel<K, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bsp_assemble_kernel<K, 32><<<grid, BSP_ASM_THREADS, smem, h->st>>>(a);
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_assembly(bspatom_handle h, int k, const BspAsmArgs &a)
+{
+    switch (k) {
+    case 3: return launch_assembly_k<3>(h, a);
+    case 4: return launch_assembly_k<4>(h, a);
+    case 5: return launch_assembly_k<5>(h, a);
+    case 6: return launch_assembly_k<6>(h, a);
+    case 7: return launch_assembly_k<7>(h, a);
+    case 8: return launch_assembly_k<8>(h, a);
+    case 9: return launch_assembly_k<9>(h, a);
+    case 10: return launch_assembly_k<10>(h, a);
+    default: return BSPATOM_EUNSUPPORTED;
+    }
+}
+
+/* ---- eigen stage executor ------------------------------------------------ */
+template <int B>
+struct GpuExec {
+    bspatom_handle h;
+    BspEigChunk g;
+    double *cand_s;
+    int *cand_c;
+    cudaError_t first_err = cudaSuccess;
+    dim3 grid() const { return dim3((g.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS, g.npencil); }
+    void note() {
+        h->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && first_err == cudaSuccess) first_err = e;
+    }
+    void bounds() {
+        bsp_bounds_kernel<B><<<g.npencil, 32, 0, h->st>>>(g, cand_s, cand_c); note();
+        bsp_bounds_pick_kernel<<<(g.npencil + 127) / 128, 128, 0, h->st>>>(g, cand_s, cand_c); note();
+    }
+    void round(int r) {
+        const int s = timed_begin(h, 0);
+        bsp_round_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, r); note();
+        timed_end(h, s);
+    }
+    void prepare(int buf) { bsp_prepare_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, buf); note(); }
+    void factor(int it) {
+        const int s = timed_begin(h, 1);
+        bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it); note();
+        timed_end(h, s);
+    }
+    void back(int cn, int cx) {
+        const int s = timed_begin(h, 2);
+        bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx); note();
+        timed_end(h, s);
+    }
+    void check(int allow) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, allow); note(); }
+    void zero_counter(int w) {
+        cudaError_t e = cudaMemsetAsync(g.counters + w, 0, sizeof(int), h->st);
+        if (e != cudaSuccess && first_err == cudaSuccess) first_err = e;
+    }
+    int read_counter(int w) {
+        cudaError_t e = cudaMemcpyAsync(h->h_counter, g.counters + w, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+        if (e != cudaSuccess) { if (first_err == cudaSuccess) first_err = e; return 0; }
+        return *h->h_counter;
+    }
+};
+
+struct ChunkTimes {
+    cudaEvent_t ev[4];
+};
+
+/* carve the chunk workspace out of one allocation */
+struct Carver {
+    char *p;
+    size_t used = 0;
+    template <class T> T *take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        T *r = (T *)(p ? p + used : nullptr);
+        used += bytes;
+        return r;
+    }
+};
+
+struct ChunkPtrs {
+    double *fbH, *pbound, *lo, *hi, *samp_s, *gap, *sigma, *rho, *rho_prev, *scale, *res, *L, *X, *R, *cand_s, *fac;
+    int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c;
+};
+
+size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
+{
+    Carver cv{base};
+    const size_t per = (size_t)np * G.ldw;
+    c.fbH = cv.take<double>((size_t)np * G.nrows * G.FS);
+    c.pbound = cv.take<double>((size_t)np * 4);
+    c.lo = cv.take<double>(2 * per); c.hi = cv.take<double>(2 * per);
+    c.clo = cv.take<int>(2 * per); c.chi = cv.take<int>(2 * per);
+    c.samp_s = cv.take<double>(2 * per); c.samp_c = cv.take<int>(2 * per);
+    c.gap = cv.take<double>(per); c.done = cv.take<int>(per);
+    c.sigma = cv.take<double>(per); c.rho = cv.take<double>(per); c.rho_prev = cv.take<double>(per);
+    c.scale = cv.take<double>(per); c.res = cv.take<double>(per); c.status = cv.take<int>(per);
+    c.fac = cv.take<double>(per);
+    c.counters = cv.take<int>(64);
+    c.cand_s = cv.take<double>((size_t)np * 32); c.cand_c = cv.take<int>((size_t)np * 32);
+    c.L = cv.take<double>((size_t)np * G.npad * (G.B + 1) * G.ldw);
+    c.X = cv.take<double>((size_t)np * G.xrows * G.ldw);
+    c.R = cv.take<double>((size_t)np * G.xrows * G.ldw);
+    return cv.used;
+}
+
+template <int B>
+int run_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, BspRunStats &st, ChunkTimes &tm)
+{
+    const size_t per_mat = (size_t)G.nrows * G.FS;
+    {
+        dim3 grid((unsigned)((per_mat + 255) / 256), np);
+        bsp_combine_kernel<<<grid, 256, 0, h->st>>>(c.fbH, G.d_fbH0, G.d_fbQ, G.d_inst + p0, G.d_cl + p0, per_mat);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    BspEigChunk g;
+    memset(&g, 0, sizeof g);
+    g.n = G.n; g.npad = G.npad; g.nrows = G.nrows; g.xrows = G.xrows; g.ldw = G.ldw; g.npencil = np;
+    g.fbH = c.fbH; g.fbS = G.d_fbS; g.inst = G.d_inst + p0; g.nvec = G.d_nvec + p0;
+    g.pbound = c.pbound; g.lo = c.lo; g.hi = c.hi; g.clo = c.clo; g.chi = c.chi;
+    g.samp_s = c.samp_s; g.samp_c = c.samp_c; g.gap = c.gap; g.done = c.done;
+    g.sigma = c.sigma; g.rho = c.rho; g.rho_prev = c.rho_prev; g.scale = c.scale; g.res = c.res;
+    g.status = c.status; g.L = c.L; g.X = c.X; g.R = c.R; g.counters = c.counters;
+    g.tau = h->opt.tau; g.delta_rel = h->opt.delta_rel; g.conv_tol = h->opt.conv_tol;
+
+    /* the driver runs bounds+rounds, then the refinement; we want a time stamp
+     * between the two, so wrap the executor */
+    struct Timed : GpuExec<B> {
+        ChunkTimes *tm;
+        void prepare(int buf) {
+            cudaEventRecord(tm->ev[1], this->h->st);
+            GpuExec<B>::prepare(buf);
+        }
+    } ex;
+    ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.tm = &tm;
+    CU(cudaEventRecord(tm.ev[0], h->st));
+    BspSchedule sch = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters, h->opt.first_check_round};
+    st = bsp_run_chunk(ex, sch);
+    if (ex.first_err != cudaSuccess) {
+        h->err = std::string("eigen stage: ") + cudaGetErrorString(ex.first_err);
+        return BSPATOM_ECUDA;
+    }
+    CU(cudaEventRecord(tm.ev[2], h->st));
+    {
+        dim3 grid((G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS, np);
+        bsp_finalize_kernel<<<grid, BSP_EIG_THREADS, 0, h->st>>>(g, G.d_E + (size_t)p0 * G.n, c.fac, G.d_bad + p0, h->opt.res_tol);
+        h->launches++;
+        CU(cudaGetLastError());
+        int maxnv = 0;
+        for (int p = 0; p < np; ++p) maxnv = std::max(maxnv, G.nvec[p0 + p]);
+        if (maxnv > 0) {
+            dim3 tg((maxnv + 31) / 32, (G.n + 31) / 32, np), tb(32, 8);
+            bsp_transpose_kernel<<<tg, tb, 0, h->st>>>(g, c.fac, G.d_C, G.d_coff + p0);
+            h->launches++;
+            CU(cudaGetLastError());
+        }
+    }
+    CU(cudaEventRecord(tm.ev[3], h->st));
+    return 0;
+}
+
+int run_chunk(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, BspRunStats &st, ChunkTimes &tm)
+{
+    switch (G.B) {
+    case 2: return run_chunk_b<2>(h, G, p0, np, c, st, tm);
+    case 3: return run_chunk_b<3>(h, G, p0, np, c, st, tm);
+    case 4: return run_chunk_b<4>(h, G, p0, np, c, st, tm);
+    case 5: return run_chunk_b<5>(h, G, p0, np, c, st, tm);
+    case 6: return run_chunk_b<6>(h, G, p0, np, c, st, tm);
+    case 7: return run_chunk_b<7>(h, G, p0, np, c, st, tm);
+    case 8: return run_chunk_b<8>(h, G, p0, np, c, st, tm);
+    case 9: return run_chunk_b<9>(h, G, p0, np, c, st, tm);
+    default: return BSPATOM_EUNSUPPORTED;
+    }
+}
+
+int ensure_workspace(bspatom_handle h, size_t bytes)
+{
+    if (h->ws.bytes >= bytes) return 0;
+    if (h->ws.base) cudaFree(h->ws.base);
+    h->ws.base = nullptr;
+    h->ws.bytes = 0;
+    CU(cudaMalloc((void **)&h->ws.base, bytes));
+    h->ws.bytes = bytes;
+    return 0;
+}
+
+int upload_group_instances(bspatom_handle h, Group &G, const std::vector<const bsp_problem *> &insts)
+{
+    const int ni = (int)insts.size();
+    std::vector<double> rt((size_t)ni * G.nkp), xgwg((size_t)ni * 64, 0.0);
+    std::vector<BspInstParams> par(ni);
+    std::vector<double> vtab;
+    G.any_vtab = false;
+    for (int i = 0; i < ni; ++i)
+        if (insts[i]->pot_kind == BSPATOM_POT_TABLE) G.any_vtab = true;
+    const size_t vt = (size_t)(G.nkp - 1) * G.ka;
+    if (G.any_vtab) vtab.assign((size_t)ni * vt, 0.0);
+    for (int i = 0; i < ni; ++i) {
+        const bsp_problem &p = *insts[i];
+        memcpy(&rt[(size_t)i * G.nkp], p.rt, sizeof(double) * G.nkp);
+        if (p.xg) {
+            memcpy(&xgwg[(size_t)i * 64], p.xg, sizeof(double) * G.ka);
+            memcpy(&xgwg[(size_t)i * 64 + 32], p.wg, sizeof(double) * G.ka);
+        } else {
+            gauss_legendre(G.ka, &xgwg[(size_t)i * 64], &xgwg[(size_t)i * 64 + 32]);
+        }
+        par[i].pot_kind = p.pot_kind;
+        par[i].has_vtab = (p.pot_kind == BSPATOM_POT_TABLE);
+        memcpy(par[i].par, p.pot_par, sizeof p.pot_par);
+        if (par[i].has_vtab) memcpy(&vtab[(size_t)i * vt], p.v_tab, sizeof(double) * vt);
+    }
+    int rc;
+    if ((rc = dev_alloc(h, &G.d_rt, rt.size()))) return rc;
+    if ((rc = dev_alloc(h, &G.d_xgwg, xgwg.size()))) return rc;
+    if ((rc = dev_alloc(h, &G.d_par, par.size()))) return rc;
+    CU(cudaMemcpyAsync(G.d_rt, rt.data(), rt.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(G.d_xgwg, xgwg.data(), xgwg.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(G.d_par, par.data(), par.size() * sizeof(BspInstParams), cudaMemcpyHostToDevice, h->st));
+    if (G.any_vtab) {
+        if ((rc = dev_alloc(h, &G.d_vtab, vtab.size()))) return rc;
+        CU(cudaMemcpyAsync(G.d_vtab, vtab.data(), vtab.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    }
+    CU(cudaStreamSynchronize(h->st)); /* staging vectors die here */
+    return 0;
+}
+
+int check_device(bspatom_handle h)
+{
+    if (!h) return -1;
+    CU(cudaSetDevice(h->dev));
+    return 0;
+}
+
+} // namespace
+
+/* ========================================================================= */
+extern "C" {
+
+int bspatom_version(void) { return BSPATOM_VERSION; }
+
+int bspatom_create(bspatom_handle *out, int device_id)
+{
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return BSPATOM_ENODEVICE;
+    if (device_id < 0 || device_id >= ndev) return -2;
+    bspatom_handle h = new bspatom_handle_s();
+    h->dev = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void **)&h->h_counter, 64) != cudaSuccess) {
+        delete h;
+        return BSPATOM_ECUDA;
+    }
+    *out = h;
+    return 0;
+}
+
+int bspatom_destroy(bspatom_handle h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->dev);
+    free_batch(h);
+    if (h->ws.base) cudaFree(h->ws.base);
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    if (h->h_counter) cudaFreeHost(h->h_counter);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return 0;
+}
+
+const char *bspatom_last_error(bspatom_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int bspatom_set_option(bspatom_handle h, const char *name, double v)
+{
+    if (!h) return -1;
+    if (!name) return -2;
+    std::string s(name);
+    if (s == "tau") h->opt.tau = v;
+    else if (s == "delta_rel") h->opt.delta_rel = v;
+    else if (s == "conv_tol") h->opt.conv_tol = v;
+    else if (s == "res_tol") h->opt.res_tol = v;
+    else if (s == "max_rounds") h->opt.max_rounds = (int)v;
+    else if (s == "min_iters") h->opt.min_iters = std::max(3, (int)v);
+    else if (s == "max_iters") h->opt.max_iters = std::max(3, (int)v);
+    else if (s == "first_check_round") h->opt.first_check_round = std::max(1, (int)v);
+    else if (s == "chunk") h->opt.chunk = (int)v;
+    else return -2;
+    return 0;
+}
+
+int bspatom_get_stats(bspatom_handle h, double *out, int nout)
+{
+    if (!h) return -1;
+    if (!out) return -2;
+    for (int i = 0; i < nout && i < 16; ++i) out[i] = h->stats[i];
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (nprob < 0) return -2;
+    if (nprob > 0 && !probs) return -3;
+    free_batch(h);
+    h->nprob = nprob;
+    h->e_off.assign(nprob + 1, 0);
+    h->c_off.assign(nprob + 1, 0);
+    h->p_n.assign(nprob, 0);
+    h->p_nvec.assign(nprob, 0);
+    for (int i = 0; i < nprob; ++i) {
+        rc = validate_problem(probs[i]);
+        if (rc) { h->err = "invalid bsp_problem at index " + std::to_string(i); return rc; }
+        h->p_n[i] = probs[i].nfun;
+        h->p_nvec[i] = probs[i].nvec;
+        h->e_off[i + 1] = h->e_off[i] + probs[i].nfun;
+        h->c_off[i + 1] = h->c_off[i] + (long long)probs[i].nfun * probs[i].nvec;
+    }
+    /* group by shape */
+    std::map<std::vector<int>, int> gid;
+    std::vector<std::vector<const bsp_problem *>> ginsts;
+    std::vector<std::multimap<uint64_t, int>> ghash;
+    for (int i = 0; i < nprob; ++i) {
+        const bsp_problem &p = probs[i];
+        std::vector<int> key = {p.k, p.nfun, p.nkp, p.ka};
+        auto it = gid.find(key);
+        int gi;
+        if (it == gid.end()) {
+            gi = (int)h->groups.size();
+            gid[key] = gi;
+            h->groups.emplace_back();
+            ginsts.emplace_back();
+            ghash.emplace_back();
+            Group &G = h->groups.back();
+            G.k = p.k; G.B = p.k - 1; G.n = p.nfun; G.nkp = p.nkp; G.ka = p.ka;
+            G.FS = 2 * G.B + 2;
+            G.npad = ((G.n + G.B) / (G.B + 1)) * (G.B + 1);
+            G.nrows = G.npad + G.B + 1;
+            G.xrows = G.npad + G.B + 1;
+            G.ldw = ((G.n + 31) / 32) * 32;
+        } else {
+            gi = it->second;
+        }
+        Group &G = h->groups[gi];
+        const uint64_t hv = instance_hash(p);
+        int inst = -1;
+        auto range = ghash[gi].equal_range(hv);
+        for (auto r = range.first; r != range.second; ++r)
+            if (same_instance(*ginsts[gi][r->second], p)) { inst = r->second; break; }
+        if (inst < 0) {
+            inst = (int)ginsts[gi].size();
+            ginsts[gi].push_back(&p);
+            ghash[gi].insert({hv, inst});
+        }
+        G.prob_index.push_back(i);
+        G.inst.push_back(inst);
+        G.nvec.push_back(p.nvec);
+        G.cl.push_back((double)p.l * (double)(p.l + 1) + 2.0 * p.ul_extra);
+        G.coff.push_back(G.c_elems);
+        G.c_elems += (long long)p.nfun * p.nvec;
+    }
+    for (size_t gi = 0; gi < h->groups.size(); ++gi) {
+        Group &G = h->groups[gi];
+        G.ninst = (int)ginsts[gi].size();
+        G.npencil = (int)G.prob_index.size();
+        if ((rc = upload_group_instances(h, G, ginsts[gi]))) return rc;
+        const size_t per_mat = (size_t)G.nrows * G.FS;
+        if ((rc = dev_alloc(h, &G.d_fbS, per_mat * G.ninst))) return rc;
+        if ((rc = dev_alloc(h, &G.d_fbH0, per_mat * G.ninst))) return rc;
+        if ((rc = dev_alloc(h, &G.d_fbQ, per_mat * G.ninst))) return rc;
+        if ((rc = dev_alloc(h, &G.d_inst, G.npencil))) return rc;
+        if ((rc = dev_alloc(h, &G.d_nvec, G.npencil))) return rc;
+        if ((rc = dev_alloc(h, &G.d_cl, G.npencil))) return rc;
+        if ((rc = dev_alloc(h, &G.d_coff, G.npencil))) return rc;
+        if ((rc = dev_alloc(h, &G.d_pdinfo, G.ninst))) return rc;
+        if ((rc = dev_alloc(h, &G.d_bad, G.npencil))) return rc;
+        if ((rc = dev_alloc(h, &G.d_E, (size_t)G.npencil * G.n))) return rc;
+        if ((rc = dev_alloc(h, &G.d_C, (size_t)G.c_elems))) return rc;
+        CU(cudaMemcpyAsync(G.d_inst, G.inst.data(), sizeof(int) * G.npencil, cudaMemcpyHostToDevice, h->st));
+        CU(cudaMemcpyAsync(G.d_nvec, G.nvec.data(), sizeof(int) * G.npencil, cudaMemcpyHostToDevice, h->st));
+        CU(cudaMemcpyAsync(G.d_cl, G.cl.data(), sizeof(double) * G.npencil, cudaMemcpyHostToDevice, h->st));
+        CU(cudaMemcpyAsync(G.d_coff, G.coff.data(), sizeof(long long) * G.npencil, cudaMemcpyHostToDevice, h->st));
+        CU(cudaStreamSynchronize(h->st));
+    }
+    h->uploaded = true;
+    return 0;
+}
+
+int bspatom_batch_run(bspatom_handle h)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!h->uploaded) { h->err = "batch_run before batch_upload"; return BSPATOM_ESTATE; }
+    const long long launches0 = h->launches;
+    for (int i = 0; i < 4; ++i) { h->k_ms[i] = 0; h->k_cnt[i] = 0; }
+    h->ev_used = 0;
+    double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0;
+    int rounds = 0, iters = 0;
+    cudaEvent_t e0, e1, e2;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
+    ChunkTimes tm;
+    for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tm.ev[i]));
+    CU(cudaEventRecord(e0, h->st));
+    for (auto &G : h->groups) {
+        /* ---- assembly, once per instance ---- */
+        CU(cudaEventRecord(e1, h->st));
+        BspAsmArgs a;
+        memset(&a, 0, sizeof a);
+        a.n = G.n; a.nkp = G.nkp; a.ka = G.ka; a.nrows = G.nrows; a.ninst = G.ninst; a.want_pi = 0;
+        a.rt = G.d_rt; a.xgwg = G.d_xgwg; a.par = G.d_par; a.vtab = G.d_vtab;
+        a.fb[BSP_MAT_S] = G.d_fbS; a.fb[BSP_MAT_H0] = G.d_fbH0; a.fb[BSP_MAT_Q] = G.d_fbQ;
+        {
+            const int s = timed_begin(h, 3);
+            rc = launch_assembly(h, G.k, a);
+            timed_end(h, s);
+            if (rc) return rc;
+        }
+        bsp_pdcheck_kernel<<<(G.ninst + 31) / 32, 32, 0, h->st>>>(G.d_fbS, G.n, G.nrows, G.B, G.ninst, G.d_pdinfo, nullptr);
+        h->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(G.d_bad, 0, sizeof(int) * G.npencil, h->st));
+        CU(cudaEventRecord(e2, h->st));
+        /* ---- eigen stages, chunk by chunk ---- */
+        ChunkPtrs c;
+        const size_t per_pencil = carve_chunk(G, 1, nullptr, c);
+        int chunk = h->opt.chunk;
+        if (chunk <= 0) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            const size_t budget = std::min<size_t>((free_b + h->ws.bytes) / 2, (size_t)48 << 30);
+            chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil, 296));
+        }
+        chunk = std::min(chunk, G.npencil);
+        const size_t need = carve_chunk(G, chunk, nullptr, c);
+        if ((rc = ensure_workspace(h, need))) return rc;
+        carve_chunk(G, chunk, h->ws.base, c);
+        float ms = 0;
+        for (int p0 = 0; p0 < G.npencil; p0 += chunk) {
+            const int np = std::min(chunk, G.npencil - p0);
+            BspRunStats st;
+            if ((rc = run_chunk(h, G, p0, np, c, st, tm))) return rc;
+            CU(cudaStreamSynchronize(h->st));
+            timed_collect(h);
+            rounds = std::max(rounds, st.rounds);
+            iters = std::max(iters, st.iters);
+            CU(cudaEventElapsedTime(&ms, tm.ev[0], tm.ev[1])); t_val += ms;
+            CU(cudaEventElapsedTime(&ms, tm.ev[1], tm.ev[2])); t_vec += ms;
+            CU(cudaEventElapsedTime(&ms, tm.ev[2], tm.ev[3])); t_fin += ms;
+        }
+        CU(cudaEventElapsedTime(&ms, e1, e2)); t_asm += ms;
+    }
+    CU(cudaEventRecord(e1, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    float total = 0;
+    CU(cudaEventElapsedTime(&total, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
+    h->stats[0] = (double)(h->launches - launches0);
+    h->stats[1] = rounds; h->stats[2] = iters;
+    h->stats[3] = t_asm; h->stats[4] = t_val; h->stats[5] = t_vec; h->stats[6] = t_fin; h->stats[7] = total;
+    for (int i = 0; i < 4; ++i) { h->stats[8 + i] = h->k_ms[i]; h->stats[12 + i] = (double)h->k_cnt[i]; }
+    h->ran = true;
+    return 0;
+}
+
+int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!h->ran) { h->err = "batch_download before batch_run"; return BSPATOM_ESTATE; }
+    for (auto &G : h->groups) {
+        G.pdinfo.resize(G.ninst);
+        G.bad.resize(G.npencil);
+        CU(cudaMemcpyAsync(G.pdinfo.data(), G.d_pdinfo, sizeof(int) * G.ninst, cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(G.bad.data(), G.d_bad, sizeof(int) * G.npencil, cudaMemcpyDeviceToHost, h->st));
+        /* pencils of a group are usually contiguous in the caller's order: merge runs */
+        int p = 0;
+        while (p < G.npencil) {
+            int q = p;
+            while (q + 1 < G.npencil && G.prob_index[q + 1] == G.prob_index[q] + 1) ++q;
+            const int i0 = G.prob_index[p];
+            const int cnt = q - p + 1;
+            if (E) CU(cudaMemcpyAsync(E + h->e_off[i0], G.d_E + (size_t)p * G.n, sizeof(double) * (size_t)cnt * G.n,
+                                      cudaMemcpyDeviceToHost, h->st));
+            if (C) {
+                const long long nel = (q + 1 < G.npencil ? G.coff[q + 1] : G.c_elems) - G.coff[p];
+                if (nel > 0) CU(cudaMemcpyAsync(C + h->c_off[i0], G.d_C + G.coff[p], sizeof(double) * (size_t)nel,
+                                                cudaMemcpyDeviceToHost, h->st));
+            }
+            p = q + 1;
+        }
+    }
+    CU(cudaStreamSynchronize(h->st));
+    if (info) {
+        for (auto &G : h->groups)
+            for (int p = 0; p < G.npencil; ++p) {
+                const int pd = G.pdinfo[G.inst[p]];
+                info[G.prob_index[p]] = pd ? G.n + pd : G.bad[p];
+            }
+    }
+    return 0;
+}
+
+int bspatom_solve_batch(bspatom_handle h, int nprob, const bsp_problem *probs, double *E, double *C, int *info)
+{
+    int rc = bspatom_batch_upload(h, nprob, probs);
+    if (rc) return rc;
+    if ((rc = bspatom_batch_run(h))) return rc;
+    return bspatom_batch_download(h, E, C, info);
+}
+
+/* ------------------------------------------------------------------------- */
+int bspatom_assemble_band(bspatom_handle h, const bsp_problem *p, double *S, double *H0, double *Q, double *T,
+                          double *V, double *R, double *Rinv, double *D)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!p) return -2;
+    bsp_problem q = *p;
+    q.l = 0; q.nvec = 0;
+    if ((rc = validate_problem(q))) return rc;
+    Group G;
+    G.k = q.k; G.B = q.k - 1; G.n = q.nfun; G.nkp = q.nkp; G.ka = q.ka; G.FS = 2 * G.B + 2;
+    G.npad = ((G.n + G.B) / (G.B + 1)) * (G.B + 1);
+    G.nrows = G.npad + G.B + 1;
+    std::vector<const bsp_problem *> insts = {&q};
+    if ((rc = upload_group_instances(h, G, insts))) { free_group(G); return rc; }
+    const size_t per_mat = (size_t)G.nrows * G.FS;
+    double *d_all = nullptr;
+    if ((rc = dev_alloc(h, &d_all, per_mat * BSP_NMAT))) { free_group(G); return rc; }
+    BspAsmArgs a;
+    memset(&a, 0, sizeof a);
+    a.n = G.n; a.nkp = G.nkp; a.ka = G.ka; a.nrows = G.nrows; a.ninst = 1; a.want_pi = 1;
+    a.rt = G.d_rt; a.xgwg = G.d_xgwg; a.par = G.d_par; a.vtab = G.d_vtab;
+    for (int m = 0; m < BSP_NMAT; ++m) a.fb[m] = d_all + per_mat * m;
+    rc = launch_assembly(h, G.k, a);
+    std::vector<double> host(per_mat * BSP_NMAT);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(host.data(), d_all, host.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = BSPATOM_ECUDA; }
+    }
+    cudaFree(d_all);
+    free_group(G);
+    if (rc) return rc;
+    const int n = q.nfun, kd = q.k - 1, FS = 2 * kd + 2;
+    double *sym[7] = {S, H0, Q, T, V, R, Rinv};
+    for (int m = 0; m < 7; ++m) {
+        if (!sym[m]) continue;
+        const double *fb = host.data() + per_mat * m;
+        for (int j = 0; j < n; ++j)
+            for (int r = 0; r <= kd; ++r) {
+                const int i = j - kd + r; /* AB(kd+1+i-j, j) 1-based -> row r = kd+i-j */
+                sym[m][(size_t)j * (kd + 1) + r] = (i >= 0) ? fb[(size_t)i * FS + (j - i + kd)] : 0.0;
+            }
+    }
+    if (D) {
+        const double *fb = host.data() + per_mat * BSP_MAT_D;
+        const int ld = 2 * kd + 1;
+        for (int j = 0; j < n; ++j)
+            for (int r = 0; r < ld; ++r) {
+                const int i = j - kd + r;
+                D[(size_t)j * ld + r] = (i >= 0 && i < n) ? fb[(size_t)i * FS + (j - i + kd)] : 0.0;
+            }
+    }
+    return 0;
+}
+
+} /* extern "C" */
+
+#include "bsp_api_extra.cuh"

@@ -1,0 +1,287 @@
+/*
+ * bsp_api_extra.cuh -- included at the end of bsp_api.cu: the LAPACK-shaped
+ * entry (Level 0), the dense dipole contraction and wavefunction synthesis.
+ */
+#ifndef BSP_API_EXTRA_CUH
+#define BSP_API_EXTRA_CUH
+
+namespace {
+
+/* psi(ip, iv) = sum_j C(j,iv) B_j(r_ip)      WRITE_WF, Bsp_Atom.f90:118-146 */
+template <int K>
+__global__ void bsp_wavefunction_kernel(int nfun, int nkp, const double *__restrict__ rt, double ra, double rb,
+                                        int npts, int nvec, const double *__restrict__ C,
+                                        double *__restrict__ r_out, double *__restrict__ psi)
+{
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip > npts) return;
+    const double dr = (rb - ra) / (double)npts;            /* :120 */
+    const double r = ra + (double)ip * dr;                 /* :127 */
+    if (blockIdx.y == 0) r_out[ip] = r;
+    /* interv (interv.f90:86-116) for non-decreasing knots: largest left with
+     * rt(left) <= r < rt(left+1); r == rt(nkp) walks down to the last interval
+     * of positive width; outside the knots the reference returns left = 1 */
+    int left;
+    const double tlast = rt[nkp - 1];
+    if (r > tlast || r < rt[0]) {
+        left = 1;
+    } else if (r == tlast) {
+        left = nkp;
+        while (left > 1 && !(rt[left - 1] < tlast)) --left;
+    } else {
+        int a = 1, b = nkp; /* rt(a) <= r < rt(b) */
+        while (b - a > 1) {
+            const int m = (a + b) >> 1;
+            if (rt[m - 1] <= r) a = m; else b = m;
+        }
+        left = a;
+    }
+    double bsp[K], dbsp[K];
+    bool ok = rt[min(left, nkp - 1)] > rt[left - 1];       /* bsplvb.f90:30 */
+    if (ok) bsp_deboor<K>(rt, nkp, nfun, left, r, bsp, dbsp);
+    for (int iv = blockIdx.y; iv < nvec; iv += gridDim.y) {
+        double s = 0.0;
+        if (ok) {
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                const int j = left - K + 1 + a;            /* :133-141 */
+                if (j >= 1 && j <= nfun) s += C[(size_t)iv * nfun + j - 1] * bsp[a];
+            }
+        }
+        psi[(size_t)iv * (npts + 1) + ip] = s;
+    }
+}
+
+template <int K>
+void launch_wavefunction(bspatom_handle h, int nfun, int nkp, const double *rt, double ra, double rb, int npts,
+                         int nvec, const double *C, double *r_out, double *psi)
+{
+    dim3 grid((npts + 1 + 127) / 128, std::min(nvec, 64));
+    bsp_wavefunction_kernel<K><<<grid, 128, 0, h->st>>>(nfun, nkp, rt, ra, rb, npts, nvec, C, r_out, psi);
+    h->launches++;
+}
+
+bspatom_handle g_level0 = nullptr;
+
+} // namespace
+
+extern "C" {
+
+int bspatom_wavefunction(bspatom_handle h, int k, int nfun, int nkp, const double *rt, double ra, double rb,
+                         int npts, int nvec, const double *C, double *r_out, double *psi_out)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (k < BSP_KMIN || k > BSP_KMAX) return BSPATOM_EUNSUPPORTED;
+    if (nfun < 1 || nkp != nfun + k || !rt || npts < 1 || nvec < 1 || !C || !r_out || !psi_out) return -2;
+    double *d_rt = nullptr, *d_C = nullptr, *d_r = nullptr, *d_psi = nullptr;
+    if ((rc = dev_alloc(h, &d_rt, (size_t)nkp))) return rc;
+    if ((rc = dev_alloc(h, &d_C, (size_t)nfun * nvec))) return rc;
+    if ((rc = dev_alloc(h, &d_r, (size_t)npts + 1))) return rc;
+    if ((rc = dev_alloc(h, &d_psi, (size_t)(npts + 1) * nvec))) return rc;
+    CU(cudaMemcpyAsync(d_rt, rt, sizeof(double) * nkp, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(d_C, C, sizeof(double) * (size_t)nfun * nvec, cudaMemcpyHostToDevice, h->st));
+    switch (k) {
+    case 3: launch_wavefunction<3>(h, nfun, nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 4: launch_wavefunction<4>(h, nfun, nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 5: launch_wavefunction<5>(h, nfun, nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 6: launch_wavefunction<6>(h, nfun, nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 7: launch_wavefunction<7>(h, nfun, nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 8: launch_wavefunction<8>(h, nfun, nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 9: launch_wavefunction<9>(h, nfun, nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    default: launch_wavefunction<10>(h, nfun, nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(r_out, d_r, sizeof(double) * ((size_t)npts + 1), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(psi_out, d_psi, sizeof(double) * (size_t)(npts + 1) * nvec, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    cudaFree(d_rt); cudaFree(d_C); cudaFree(d_r); cudaFree(d_psi);
+    return 0;
+}
+
+int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf, const double *Cf, int ni,
+                   const double *Ci, double *D)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (n < 1) return -2;
+    if (kd < 0 || kd >= n) return -3;
+    if (!A_band) return -4;
+    if (nf < 1) return -5;
+    if (!Cf) return -6;
+    if (ni < 1) return -7;
+    if (!Ci) return -8;
+    if (!D) return -9;
+    const int ld = 2 * kd + 1;
+    double *d_A = nullptr, *d_Cf = nullptr, *d_Ci = nullptr, *d_Y = nullptr, *d_D = nullptr;
+    if ((rc = dev_alloc(h, &d_A, (size_t)ld * n))) return rc;
+    if ((rc = dev_alloc(h, &d_Ci, (size_t)n * ni))) return rc;
+    if ((rc = dev_alloc(h, &d_Y, (size_t)n * ni))) return rc;
+    if ((rc = dev_alloc(h, &d_D, (size_t)nf * ni))) return rc;
+    const bool same = (Cf == Ci && nf == ni);
+    if (same) d_Cf = d_Ci;
+    else if ((rc = dev_alloc(h, &d_Cf, (size_t)n * nf))) return rc;
+    CU(cudaMemcpyAsync(d_A, A_band, sizeof(double) * (size_t)ld * n, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(d_Ci, Ci, sizeof(double) * (size_t)n * ni, cudaMemcpyHostToDevice, h->st));
+    if (!same) CU(cudaMemcpyAsync(d_Cf, Cf, sizeof(double) * (size_t)n * nf, cudaMemcpyHostToDevice, h->st));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, h->st));
+    bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, ni), 128, 0, h->st>>>(n, kd, d_A, ni, d_Ci, d_Y);
+    h->launches++;
+    CU(cudaGetLastError());
+    bsp_dgemm_tn_kernel<<<dim3((nf + BSP_GT_M - 1) / BSP_GT_M, (ni + BSP_GT_N - 1) / BSP_GT_N), 128, 0, h->st>>>(
+        nf, ni, n, d_Cf, n, d_Y, n, d_D, nf);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e1, h->st));
+    CU(cudaMemcpyAsync(D, d_D, sizeof(double) * (size_t)nf * ni, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    h->stats[0] = 2; h->stats[7] = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_A); cudaFree(d_Ci); cudaFree(d_Y); cudaFree(d_D);
+    if (!same) cudaFree(d_Cf);
+    return 0;
+}
+
+/*
+ * DSYGV-shaped entry.  Accepts the dense pencil exactly as matrices.f90:244-248
+ * hands it to LAPACK, finds the half bandwidth from the zero pattern and runs
+ * the banded device pipeline on it.  info: 0 ok; -i argument i illegal (also -5
+ * when the pencil is not banded within the compiled range, half bandwidth <= 9);
+ * 1..n eigenpairs missed the tolerance; n+i S not positive definite at minor i;
+ * -100 - code for device errors.
+ */
+void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const int *n_, double *A, const int *lda_,
+                    double *Bmat, const int *ldb_, double *w, double *work, const int *lwork, int *info, ...)
+{
+    (void)work; (void)lwork;
+    if (!info) return;
+    *info = 0;
+    const int n = n_ ? *n_ : -1, lda = lda_ ? *lda_ : 0, ldb = ldb_ ? *ldb_ : 0;
+    const bool wantz = jobz && (*jobz == 'V' || *jobz == 'v');
+    const bool upper = uplo && (*uplo == 'U' || *uplo == 'u');
+    if (!itype || *itype != 1) { *info = -1; return; }
+    if (!jobz || !(wantz || *jobz == 'N' || *jobz == 'n')) { *info = -2; return; }
+    if (!uplo || !(upper || *uplo == 'L' || *uplo == 'l')) { *info = -3; return; }
+    if (n < 0) { *info = -4; return; }
+    if (!A || lda < std::max(1, n)) { *info = -6; return; }
+    if (!Bmat || ldb < std::max(1, n)) { *info = -8; return; }
+    if (!w) { *info = -9; return; }
+    if (n == 0) return;
+    if (!g_level0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { *info = -100 - BSPATOM_ENODEVICE; return; }
+        int rc = bspatom_create(&g_level0, dev);
+        if (rc) { *info = -100 - rc; return; }
+    }
+    bspatom_handle h = g_level0;
+    auto a = [&](const double *M, int ld, int i, int j) -> double {   /* symmetric read of the stored triangle */
+        if (upper) return (i <= j) ? M[(size_t)j * ld + i] : M[(size_t)i * ld + j];
+        return (i >= j) ? M[(size_t)j * ld + i] : M[(size_t)i * ld + j];
+    };
+    int kd = 0;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i <= j; ++i) {
+            const double va = upper ? A[(size_t)j * lda + i] : A[(size_t)i * lda + j];
+            const double vb = upper ? Bmat[(size_t)j * ldb + i] : Bmat[(size_t)i * ldb + j];
+            if ((va != 0.0 || vb != 0.0) && j - i > kd) kd = j - i;
+        }
+    if (kd > BSP_KMAX - 1) { *info = -5; h->err = "bspatom_dsygv_: pencil half bandwidth exceeds 9"; return; }
+    const int B = std::max(kd, BSP_KMIN - 1);
+    Group G;
+    G.k = B + 1; G.B = B; G.n = n; G.nkp = n + G.k; G.ka = 1; G.FS = 2 * B + 2;
+    G.npad = ((n + B) / (B + 1)) * (B + 1);
+    G.nrows = G.npad + B + 1; G.xrows = G.nrows; G.ldw = ((n + 31) / 32) * 32;
+    G.ninst = 1; G.npencil = 1;
+    G.prob_index = {0}; G.inst = {0}; G.nvec = {wantz ? n : 0}; G.cl = {0.0}; G.coff = {0};
+    G.c_elems = wantz ? (long long)n * n : 0;
+    const size_t per_mat = (size_t)G.nrows * G.FS;
+    std::vector<double> fbH(per_mat, 0.0), fbS(per_mat, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c <= 2 * B; ++c) {
+            const int j = i - B + c;
+            if (j < 0 || j >= n || abs(i - j) > kd) continue;
+            fbH[(size_t)i * G.FS + c] = a(A, lda, i, j);
+            fbS[(size_t)i * G.FS + c] = a(Bmat, ldb, i, j);
+        }
+    for (int i = n; i < G.nrows; ++i) fbH[(size_t)i * G.FS + B] = 1.0;
+    auto fail = [&](int rc) { free_batch(h); *info = -100 - rc; };
+    if (cudaSetDevice(h->dev) != cudaSuccess) { *info = -100 - BSPATOM_ECUDA; return; }
+    free_batch(h);
+    int rc = 0;
+    double *d_L = nullptr;
+    do {
+        if ((rc = dev_alloc(h, &G.d_fbS, per_mat))) break;
+        if ((rc = dev_alloc(h, &G.d_fbH0, per_mat))) break;
+        if ((rc = dev_alloc(h, &G.d_fbQ, per_mat))) break;
+        if ((rc = dev_alloc(h, &G.d_inst, 1))) break;
+        if ((rc = dev_alloc(h, &G.d_nvec, 1))) break;
+        if ((rc = dev_alloc(h, &G.d_cl, 1))) break;
+        if ((rc = dev_alloc(h, &G.d_coff, 1))) break;
+        if ((rc = dev_alloc(h, &G.d_pdinfo, 1))) break;
+        if ((rc = dev_alloc(h, &G.d_bad, 1))) break;
+        if ((rc = dev_alloc(h, &G.d_E, (size_t)n))) break;
+        if ((rc = dev_alloc(h, &G.d_C, (size_t)G.c_elems))) break;
+        if ((rc = dev_alloc(h, &d_L, (size_t)n * (B + 1)))) break;
+    } while (0);
+    if (rc) { free_group(G); cudaFree(d_L); *info = -100 - rc; return; }
+    cudaMemcpyAsync(G.d_fbS, fbS.data(), per_mat * sizeof(double), cudaMemcpyHostToDevice, h->st);
+    cudaMemcpyAsync(G.d_fbH0, fbH.data(), per_mat * sizeof(double), cudaMemcpyHostToDevice, h->st);
+    cudaMemsetAsync(G.d_fbQ, 0, per_mat * sizeof(double), h->st);
+    cudaMemcpyAsync(G.d_inst, G.inst.data(), sizeof(int), cudaMemcpyHostToDevice, h->st);
+    cudaMemcpyAsync(G.d_nvec, G.nvec.data(), sizeof(int), cudaMemcpyHostToDevice, h->st);
+    cudaMemcpyAsync(G.d_cl, G.cl.data(), sizeof(double), cudaMemcpyHostToDevice, h->st);
+    cudaMemcpyAsync(G.d_coff, G.coff.data(), sizeof(long long), cudaMemcpyHostToDevice, h->st);
+    cudaMemsetAsync(G.d_bad, 0, sizeof(int), h->st);
+    bsp_pdcheck_kernel<<<1, 32, 0, h->st>>>(G.d_fbS, n, G.nrows, B, 1, G.d_pdinfo, d_L);
+    h->launches++;
+    int pd = 0;
+    cudaMemcpyAsync(&pd, G.d_pdinfo, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    if (cudaStreamSynchronize(h->st) != cudaSuccess) { free_group(G); cudaFree(d_L); *info = -100 - BSPATOM_ECUDA; return; }
+    if (pd) { free_group(G); cudaFree(d_L); *info = n + pd; return; }
+    /* run the eigen stages on this explicit pencil */
+    h->groups.clear();
+    h->groups.push_back(G);
+    Group &GG = h->groups.back();
+    ChunkPtrs c;
+    const size_t need = carve_chunk(GG, 1, nullptr, c);
+    ChunkTimes tm;
+    BspRunStats st;
+    bool ev_ok = true;
+    for (int i = 0; i < 4; ++i) ev_ok = ev_ok && (cudaEventCreate(&tm.ev[i]) == cudaSuccess);
+    rc = ev_ok ? ensure_workspace(h, need) : BSPATOM_ECUDA;
+    if (!rc) {
+        carve_chunk(GG, 1, h->ws.base, c);
+        rc = run_chunk(h, GG, 0, 1, c, st, tm);
+    }
+    std::vector<double> Lb((size_t)n * (B + 1)), Cout(wantz ? (size_t)n * n : 0);
+    int bad = 0;
+    if (!rc) {
+        cudaMemcpyAsync(w, GG.d_E, sizeof(double) * n, cudaMemcpyDeviceToHost, h->st);
+        cudaMemcpyAsync(Lb.data(), d_L, sizeof(double) * Lb.size(), cudaMemcpyDeviceToHost, h->st);
+        cudaMemcpyAsync(&bad, GG.d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+        if (wantz) cudaMemcpyAsync(Cout.data(), GG.d_C, sizeof(double) * Cout.size(), cudaMemcpyDeviceToHost, h->st);
+        if (cudaStreamSynchronize(h->st) != cudaSuccess) rc = BSPATOM_ECUDA;
+    }
+    if (ev_ok) for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
+    cudaFree(d_L);
+    if (rc) { fail(rc); return; }
+    free_batch(h);
+    /* eigenvectors overwrite A; the Cholesky factor overwrites the stored triangle of B */
+    if (wantz)
+        for (int j = 0; j < n; ++j) memcpy(A + (size_t)j * lda, Cout.data() + (size_t)j * n, sizeof(double) * n);
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i <= B && j + i < n; ++i) {
+            const double v = Lb[(size_t)j * (B + 1) + i]; /* L(j+i, j) */
+            if (upper) Bmat[(size_t)(j + i) * ldb + j] = v;   /* U(j, j+i) */
+            else Bmat[(size_t)j * ldb + (j + i)] = v;
+        }
+    *info = bad;
+}
+
+} /* extern "C" */
+
+#endif

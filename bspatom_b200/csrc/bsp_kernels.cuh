@@ -1,0 +1,135 @@
+/*
+ * bsp_kernels.cuh -- __global__ wrappers around the per-thread bodies of
+ * bsp_core.h plus the small data-movement kernels (band combine, transpose).
+ * Thread mapping everywhere: blockIdx.y = pencil, blockIdx.x*blockDim.x +
+ * threadIdx.x = eigen index e, so a warp streams 32 consecutive e of one
+ * pencil: every workspace access X/R/L[row][e] is a fully coalesced 256 B
+ * line and every band-row read is a warp-uniform broadcast that stays in L1.
+ */
+#ifndef BSP_KERNELS_CUH
+#define BSP_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include "bsp_core.h"
+
+#define BSP_EIG_THREADS 128
+
+template <int B>
+__global__ void __launch_bounds__(32) bsp_bounds_kernel(BspEigChunk g, double *cand_s, int *cand_c)
+{
+    bsp_bounds_candidate<B>(g, blockIdx.x, threadIdx.x, cand_s, cand_c);
+}
+
+__global__ void bsp_bounds_pick_kernel(BspEigChunk g, const double *cand_s, const int *cand_c)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < g.npencil) bsp_bounds_pick(g, p, cand_s, cand_c);
+}
+
+template <int B>
+__global__ void __launch_bounds__(BSP_EIG_THREADS) bsp_round_kernel(BspEigChunk g, int round)
+{
+    bsp_multisection_round<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, round);
+}
+
+__global__ void bsp_prepare_kernel(BspEigChunk g, int buf)
+{
+    bsp_refine_prepare(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, buf);
+}
+
+template <int B>
+__global__ void __launch_bounds__(BSP_EIG_THREADS) bsp_factor_kernel(BspEigChunk g, int iter)
+{
+    bsp_factor_forward<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter);
+}
+
+template <int B>
+__global__ void __launch_bounds__(BSP_EIG_THREADS) bsp_back_kernel(BspEigChunk g, int corr_now, int corr_next)
+{
+    bsp_back_substitute<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, corr_now, corr_next);
+}
+
+__global__ void bsp_check_kernel(BspEigChunk g, int allow)
+{
+    bsp_check_converged(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, allow);
+}
+
+__global__ void bsp_finalize_kernel(BspEigChunk g, double *E, double *fac, int *bad, double res_tol)
+{
+    bsp_finalize_eigen(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, E, fac, bad, res_tol);
+}
+
+/* C[p] (n x nvec_p, column-major, column e = eigenvector e) = fac[e] * X[p][row][e]
+ * 32x32 shared-memory transpose; coff[p] = offset of pencil p's block in C. */
+__global__ void bsp_transpose_kernel(BspEigChunk g, const double *fac, double *C, const long long *coff)
+{
+    __shared__ double tile[32][33];
+    const int p = blockIdx.z;
+    const int nv = g.nvec[p];
+    const int e0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    if (e0 >= nv) return;
+    const double *X = g.X + (size_t)p * g.xrows * g.ldw;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int r = r0 + rr, e = e0 + threadIdx.x;
+        double v = 0.0;
+        if (r < g.n && e < nv) v = X[(size_t)r * g.ldw + e] * fac[(size_t)p * g.ldw + e];
+        tile[rr][threadIdx.x] = v;
+    }
+    __syncthreads();
+    double *Cp = C + coff[p];
+    for (int ee = threadIdx.y; ee < 32; ee += blockDim.y) {
+        const int e = e0 + ee, r = r0 + threadIdx.x;
+        if (e < nv && r < g.n) Cp[(size_t)e * g.n + r] = tile[threadIdx.x][ee];
+    }
+}
+
+/* fbH[p] = fbH0[inst] + cl[p] * fbQ[inst]   (Hij = Tij + Uij(:,:,l) + Vij, matrices.f90:244) */
+__global__ void bsp_combine_kernel(double *fbH, const double *fbH0, const double *fbQ, const int *inst,
+                                   const double *cl, size_t per_mat)
+{
+    const int p = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_mat) return;
+    const size_t src = (size_t)inst[p] * per_mat + i;
+    fbH[(size_t)p * per_mat + i] = fma(cl[p], fbQ[src], fbH0[src]);
+}
+
+/* S positive definite?  one thread per instance: banded Cholesky pivots.
+ * pd_info[inst] = 0 or the 1-based index of the first non-positive pivot
+ * (LAPACK dpotrf numbering; DSYGV reports N + that, matrices.f90:250). */
+__global__ void bsp_pdcheck_kernel(const double *fbS, int n, int nrows, int B, int ninst, int *pd_info,
+                                   double *Lout /* NULL or [ninst][n][B+1]: L(j+i,j) */)
+{
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= ninst) return;
+    const int FS = 2 * B + 2;
+    const double *S = fbS + (size_t)inst * nrows * FS;
+    /* window of the last B columns of L (scaled), generic B <= 15 */
+    double w[16][16];
+    for (int a = 0; a < 16; ++a) for (int b = 0; b < 16; ++b) w[a][b] = 0.0;
+    int info = 0;
+    for (int j = 0; j < n && !info; ++j) {
+        /* column j of the Schur complement: a(j+i,j) - sum_{c<j} l(j+i,c) l(j,c) d(c) */
+        double col[16];
+        for (int i = 0; i <= B; ++i) {
+            double v = (j + i < n) ? S[(size_t)(j + i) * FS + (B - i)] : 0.0;
+            /* previous columns c = j-1 .. j-B are kept in w[(c)%16][*] as l(c+t,c)*sqrt(d) */
+            for (int t = 1; t <= B - i; ++t) {
+                const int c = j - t;
+                if (c < 0) break;
+                v -= w[c & 15][t + i] * w[c & 15][t];
+            }
+            col[i] = v;
+        }
+        if (!(col[0] > 0.0)) { info = j + 1; break; }
+        const double d = sqrt(col[0]);
+        w[j & 15][0] = d;
+        for (int i = 1; i <= B; ++i) w[j & 15][i] = col[i] / d;
+        for (int i = B + 1; i < 16; ++i) w[j & 15][i] = 0.0;
+        if (Lout)
+            for (int i = 0; i <= B; ++i) Lout[((size_t)inst * n + j) * (B + 1) + i] = w[j & 15][i];
+    }
+    pd_info[inst] = info;
+}
+
+#endif

@@ -1,0 +1,432 @@
+"""Host side of the B200 path, mirroring the reference driver's interface.
+
+The reference is a Fortran program whose hot path is two argument-less subroutines that talk
+through module globals (``CALL MATRIX_SVT`` Bsp_Atom.f90:72, ``CALL SOLVE_SYSTEM`` Bsp_Atom.f90:75).
+No Fortran compiler exists in this image, so -- as the task prescribes for a compiled reference
+whose toolchain is absent -- the host above the C-ABI is written here, keeping the reference's
+names and meaning: ``BspAtom`` holds what MOD_GRID / MOD_BSPLINES / MOD_PHOTOION hold
+(Modules.f90:21-58,207-236) and offers READ_INPUTS, GRID, MATRIX_SVT, SOLVE_SYSTEM, WRITE_WF,
+TRANS_AMP.  The Fortran binding a maintainer would add instead is in INTEGRATION.md.
+
+Everything numeric below the knot vector runs on the GPU through libbspatom.so; this module only
+parses input, builds knots (GRID stays on the host in the reference too) and moves buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import re
+from dataclasses import dataclass, field
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import BspAtomError, BspProblem
+
+POT_COULOMB, POT_ROGERS, POT_SIMONS_FUES, POT_YUKAWA, POT_TIETZ, POT_TABLE = 0, 1, 2, 10, 11, -1
+
+# Simons-Fues Bl(0:3) for Rb, ReadInputs.f90:136-139
+_BL_RB = (0.72657, 0.47095, -0.55508, -0.04008)
+
+
+# --------------------------------------------------------------------------------------
+# input: three namelists on stdin (ReadInputs.f90:15-21)
+# --------------------------------------------------------------------------------------
+_NML_DEFAULTS = {
+    "VARS_BSP": dict(KIND_GRID=0, ra=0.0, rb=0.0, rmax=0.0, k=0, ka=0, nfun=0, KIND_BC1=0, KIND_BC2=0, nfib=1),
+    "VARS_TISE": dict(KIND_POT=0, n0_ini=1, l_ini=0, m_ini=0, l_fin=0, lmax=0, Emax_fin=-1.0, Zatom=1.0,
+                      KIND_EGR=0, KIND_NLM=0),
+    "VARS_FIELD": dict(KIND_PI=0),
+}
+
+
+def _fortran_value(tok: str):
+    t = tok.strip().rstrip(",")
+    if re.fullmatch(r"[+-]?\d+", t):
+        return int(t)
+    return float(t.replace("D", "E").replace("d", "e"))
+
+
+def parse_namelists(text: str) -> dict:
+    """Parse the bsp_0.inp format: '!' comment lines, ``&GROUP name=value ... &end`` blocks."""
+    lines = [ln for ln in text.splitlines() if not ln.lstrip().startswith("!")]
+    body = " ".join(lines)
+    out = {g: dict(d) for g, d in _NML_DEFAULTS.items()}
+    for m in re.finditer(r"&(\w+)(.*?)(?:&end|/)", body, flags=re.S | re.I):
+        group = m.group(1).upper()
+        vals = out.setdefault(group, {})
+        known = {k.lower(): k for k in vals}
+        for kv in re.finditer(r"(\w+)\s*=\s*([^\s,=]+)", m.group(2)):
+            name = known.get(kv.group(1).lower(), kv.group(1))
+            vals[name] = _fortran_value(kv.group(2))
+    return out
+
+
+def _nint(x: float) -> int:
+    """Fortran NINT: round half away from zero."""
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+@dataclass
+class Problem:
+    """One radial problem instance: knots + potential (what MATRIX_SVT reads from the modules)."""
+
+    k: int
+    nfun: int
+    nkp: int
+    ka: int
+    rt: np.ndarray
+    xg: Optional[np.ndarray] = None
+    wg: Optional[np.ndarray] = None
+    pot_kind: int = POT_COULOMB
+    pot_par: Sequence[float] = (1.0,)
+    v_tab: Optional[np.ndarray] = None
+    bl: Optional[Sequence[float]] = None  # Bl(0:lmax) for KIND_POT=2
+
+
+class BspInputs:
+    """What READ_INPUTS + GRID leave in MOD_GRID / MOD_BSPLINES / MOD_PHOTOION: pure host logic,
+    no GPU needed (the reference keeps these on the host as well)."""
+
+    def __init__(self):
+        self.KIND_GRID = 0
+        self.KIND_BC1 = self.KIND_BC2 = 0
+        self.KIND_POT = 0
+        self.KIND_PI = 0
+        self.ra = self.rb = self.rmax = 0.0
+        self.k = self.ka = self.nfun = self.nkp = self.nointv = 0
+        self.nbc1 = self.nbc2 = self.nintv_exp = self.nintv_lin = 0
+        self.lmax = self.l_ini = self.l_fin = 0
+        self.n0_ini = 1
+        self.Zatom = 1.0
+        self.Emax_fin = -1.0
+        self.pot_par = np.zeros(8)
+        self.Bl = None
+        self.rt = None
+
+    @classmethod
+    def from_values(cls, kind_grid=0, k=7, ka=0, nfun=100, ra=0.0, rb=500.0, rmax=0.0, kind_bc1=0, kind_bc2=0,
+                    zatom=1.0, kind_pot=0, lmax=0):
+        a = cls()
+        a.KIND_GRID, a.k, a.ka, a.nfun = kind_grid, k, ka, nfun
+        a.KIND_BC1, a.KIND_BC2 = kind_bc1, kind_bc2
+        a.ra, a.rb, a.rmax = ra, rb, rmax
+        a.Zatom, a.KIND_POT, a.lmax = zatom, kind_pot, lmax
+        a.set_sizes()
+        a.set_potential()
+        a.GRID()
+        return a
+
+    # ---- READ_INPUTS (ReadInputs.f90:1-145) ---------------------------------------------
+    def READ_INPUTS(self, text: str):
+        nml = parse_namelists(text)
+        b, t, f = nml["VARS_BSP"], nml["VARS_TISE"], nml["VARS_FIELD"]
+        self.KIND_GRID, self.ra, self.rb, self.rmax = int(b["KIND_GRID"]), float(b["ra"]), float(b["rb"]), float(b["rmax"])
+        self.k, self.ka, self.nfun = int(b["k"]), int(b["ka"]), int(b["nfun"])
+        self.KIND_BC1, self.KIND_BC2 = int(b["KIND_BC1"]), int(b["KIND_BC2"])
+        self.set_sizes()
+        self.KIND_POT = int(t["KIND_POT"])
+        self.n0_ini, self.l_ini, self.l_fin = int(t["n0_ini"]), int(t["l_ini"]), int(t["l_fin"])
+        self.lmax = int(t["lmax"])
+        self.Emax_fin, self.Zatom = float(t["Emax_fin"]), float(t["Zatom"])
+        if self.l_fin > self.lmax:                       # ReadInputs.f90:87
+            self.lmax = self.l_fin
+        self.KIND_PI = int(f.get("KIND_PI", 0))
+        self.set_potential()
+        return self
+
+    def set_sizes(self):
+        """derived sizes, ReadInputs.f90:39-69"""
+        k = self.k
+        if self.ka == 0:
+            self.ka = k + 3
+        self.nbc1 = k if self.KIND_BC1 != 0 else k - 1
+        self.nbc2 = k if self.KIND_BC2 != 0 else k - 1
+        self.nkp = self.nfun + k
+        self.nointv = self.nkp - self.nbc1 - self.nbc2 + 1
+        self.gsize = self.rb - self.ra
+        if self.KIND_GRID == 2:
+            dx = self.gsize / self.nointv
+            imax = _nint((self.rmax - self.ra) / dx)
+            self.nintv_exp = 3 * imax
+            self.nintv_lin = self.nointv - imax
+            self.nointv = self.nintv_exp + self.nintv_lin
+            self.nkp = self.nointv + self.nbc1 + self.nbc2 - 1
+            self.nfun = self.nkp - k
+
+    def set_potential(self):
+        """potential tables, ReadInputs.f90:95-141"""
+        par = np.zeros(8)
+        par[0] = self.Zatom
+        self.Bl = None
+        if self.KIND_POT == POT_ROGERS:
+            numn = (2, 8, 8)
+            aj = ((0.8855, 0.2549, -0.0901, 0.0), (0.3386, 1.1323, -0.4904, 0.0), (0.1437, 0.9129, -0.6940, 0.2503))
+            ntot = 0
+            for i in range(3):
+                ntot += numn[i]
+                xn = float(self.Zatom - ntot)
+                if xn == 0.0:
+                    xn = 1.0
+                suman = 0.0
+                for j in range(4):
+                    suman = suman + aj[i][j] / (xn ** j)
+                par[5 + i] = (xn + 1.0) * suman
+                par[2 + i] = numn[i]
+            par[1] = ntot
+        elif self.KIND_POT == POT_SIMONS_FUES:
+            bl = np.zeros(max(self.lmax, 3) + 1)
+            bl[:4] = _BL_RB
+            self.Bl = bl
+        self.pot_par = par
+
+    # ---- GRID (grid.f90:1-63): knots stay a host computation ---------------------------
+    def GRID(self):
+        nkp, nbc1, nbc2, ra, rb = self.nkp, self.nbc1, self.nbc2, self.ra, self.rb
+        rt = np.zeros(nkp)
+        rt[:nbc1] = ra
+        rt[nkp - nbc2:] = rb
+        if self.KIND_GRID == 0:
+            for i in range(nbc1 + 1, nkp - nbc2 + 1):
+                rt[i - 1] = ra + float(i - nbc1) * self.gsize / float(self.nointv)
+        elif self.KIND_GRID == 1:
+            delta = 0.01
+            hin = math.log(self.gsize / delta) / float(self.nointv - 1)
+            rt[nbc1] = delta
+            j = 1
+            for i in range(nbc1 + 2, nkp - nbc2 + 1):
+                rt[i - 1] = rt[nbc1] * math.exp(hin * j)
+                j += 1
+        elif self.KIND_GRID == 2:
+            delta = 0.01
+            hin = math.log((self.rmax - ra) / delta) / float(self.nintv_exp - 1)
+            rt[nbc1] = delta
+            j = 1
+            for i in range(2, self.nintv_exp + 1):
+                rt[i + nbc1 - 1] = delta * math.exp(hin * j)
+                j += 1
+            dr = (rb - self.rmax) / float(self.nintv_lin)
+            for i in range(self.nintv_exp + 1, self.nointv + 1):
+                rt[i + nbc1 - 1] = self.rmax + float(i - self.nintv_exp) * dr
+        else:
+            raise ValueError("KIND_GRID must be 0, 1 or 2")
+        self.rt = rt
+        return rt
+
+    def problem(self) -> Problem:
+        if self.rt is None:
+            self.GRID()
+        return Problem(k=self.k, nfun=self.nfun, nkp=self.nkp, ka=self.ka, rt=self.rt, pot_kind=self.KIND_POT,
+                       pot_par=tuple(self.pot_par), bl=self.Bl)
+
+
+class BspAtom(BspInputs):
+    """State + entry points of the reference driver for the hot path (PROGRAM BSP_ATOM_PI)."""
+
+    def __init__(self, device: int = 0):
+        super().__init__()
+        self.lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self.lib.bspatom_create(C.byref(self._h), int(device))
+        _lib.check(self.lib, None, rc, "bspatom_create")
+        self.device = device
+        self.Enl = None   # (nfun, lmax+1)  eigenvalues per l   (Enl, matrices.f90:294)
+        self.cinl = None  # list over l of (nfun, nvec) eigenvector blocks (cinl, matrices.f90:369)
+        self.info = None
+
+    def adopt(self, inp: "BspInputs"):
+        """take over sizes / knots / potential from a BspInputs"""
+        for k_, v in vars(inp).items():
+            setattr(self, k_, v)
+        return self
+
+    # ---- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.bspatom_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: float):
+        _lib.check(self.lib, self._h, self.lib.bspatom_set_option(self._h, name.encode(), float(value)),
+                   "bspatom_set_option")
+
+    def stats(self) -> dict:
+        out = (C.c_double * 16)()
+        self.lib.bspatom_get_stats(self._h, out, 16)
+        keys = ["launches", "rounds", "iters", "ms_assembly", "ms_eigenvalues", "ms_eigenvectors", "ms_finalize",
+                "ms_total", "ms_k_round", "ms_k_factor", "ms_k_back", "ms_k_assembly",
+                "n_k_round", "n_k_factor", "n_k_back", "n_k_assembly"]
+        return dict(zip(keys, list(out)))
+
+    # ---- MATRIX_SVT (matrices.f90:1-200) ------------------------------------------------
+    def MATRIX_SVT(self, prob: Optional[Problem] = None) -> dict:
+        """Banded S, H0=T+V, Q, T, V, R, Rinv (upper band, (k, nfun) Fortran order) and D
+        (general band (2k-1, nfun)).  Uij(:,:,l) = [l(l+1)+2Bl(l)] Q."""
+        prob = prob or self.problem()
+        keep: list = []
+        cp = _to_c_problem(prob, 0, 0, keep)
+        k, n = prob.k, prob.nfun
+        names = ["S", "H0", "Q", "T", "V", "R", "Rinv"]
+        out = {nm: np.zeros((k, n), order="F") for nm in names}
+        out["D"] = np.zeros((2 * k - 1, n), order="F")
+        ptrs = [out[nm].ctypes.data_as(C.c_void_p) for nm in names + ["D"]]
+        rc = self.lib.bspatom_assemble_band(self._h, C.byref(cp), *ptrs)
+        _lib.check(self.lib, self._h, rc, "bspatom_assemble_band")
+        self.band = out
+        return out
+
+    # ---- SOLVE_SYSTEM core (matrices.f90:242-265) --------------------------------------
+    def SOLVE_SYSTEM(self, nvec: Optional[int] = None):
+        """Loop l = 0..lmax of the reference, as ONE batched call.  Fills Enl, cinl, info.
+        Raises like the reference STOPs (matrices.f90:250-254) when info != 0."""
+        prob = self.problem()
+        ls = list(range(self.lmax + 1))
+        E, Cs, info = self.solve_batch([(prob, l) for l in ls], nvec=nvec)
+        self.info = info
+        bad = [(l, i) for l, i in zip(ls, info) if i != 0]
+        if bad:
+            raise BspAtomError("ERROR DIAGONALIZING THE MATRIX! info=%d  l = %d" % (bad[0][1], bad[0][0]))
+        self.Enl = np.stack(E, axis=1)
+        self.cinl = Cs
+        return self.Enl, self.cinl
+
+    def solve_batch(self, items: Iterable, nvec: Optional[int] = None, want_vectors: bool = True,
+                    out_E: Optional[np.ndarray] = None, out_C: Optional[np.ndarray] = None):
+        """items: iterable of (Problem, l).  Returns (list of E arrays, list of C arrays, info)."""
+        items = list(items)
+        arr, keep = build_problem_array(items, nvec)
+        n_e = sum(p.nfun for p, _ in items)
+        n_c = sum(int(arr[i].nfun) * int(arr[i].nvec) for i in range(len(items)))
+        E = out_E if out_E is not None else np.empty(n_e)
+        Cbuf = (out_C if out_C is not None else np.empty(n_c)) if want_vectors else None
+        info = np.zeros(len(items), dtype=np.int32)
+        rc = self.lib.bspatom_solve_batch(self._h, len(items), arr, E.ctypes.data_as(C.c_void_p),
+                                          Cbuf.ctypes.data_as(C.c_void_p) if Cbuf is not None else None,
+                                          info.ctypes.data_as(C.c_void_p))
+        _lib.check(self.lib, self._h, rc, "bspatom_solve_batch")
+        Es, Cs, eo, co = [], [], 0, 0
+        for i, (p, _) in enumerate(items):
+            nv = int(arr[i].nvec)
+            Es.append(E[eo:eo + p.nfun])
+            eo += p.nfun
+            if Cbuf is not None:
+                Cs.append(Cbuf[co:co + p.nfun * nv].reshape((p.nfun, nv), order="F"))
+                co += p.nfun * nv
+        return Es, Cs, info
+
+    # staged variant: keeps the batch resident in HBM (bench.py times batch_run alone)
+    def batch_upload(self, items: Iterable, nvec: Optional[int] = None):
+        items = list(items)
+        arr, keep = build_problem_array(items, nvec)
+        rc = self.lib.bspatom_batch_upload(self._h, len(items), arr)
+        _lib.check(self.lib, self._h, rc, "bspatom_batch_upload")
+        self._resident = (items, [int(arr[i].nvec) for i in range(len(items))])
+
+    def batch_run(self):
+        _lib.check(self.lib, self._h, self.lib.bspatom_batch_run(self._h), "bspatom_batch_run")
+
+    def batch_download(self, E: np.ndarray, Cbuf: Optional[np.ndarray], info: np.ndarray):
+        rc = self.lib.bspatom_batch_download(self._h, E.ctypes.data_as(C.c_void_p),
+                                             Cbuf.ctypes.data_as(C.c_void_p) if Cbuf is not None else None,
+                                             info.ctypes.data_as(C.c_void_p))
+        _lib.check(self.lib, self._h, rc, "bspatom_batch_download")
+
+    # ---- WRITE_WF (Bsp_Atom.f90:101-152) ------------------------------------------------
+    def WRITE_WF(self, ci: np.ndarray, npts: int = 10000):
+        ci = np.asarray(ci, dtype=np.float64)
+        if ci.ndim == 1:
+            ci = ci[:, None]
+        ci = np.asfortranarray(ci)
+        if ci.shape[0] != self.nfun:
+            raise ValueError("ci must have nfun rows")
+        nvec = ci.shape[1]
+        r = np.empty(npts + 1)
+        psi = np.empty((npts + 1, nvec), order="F")
+        rt = np.ascontiguousarray(self.rt)
+        rc = self.lib.bspatom_wavefunction(self._h, self.k, self.nfun, self.nkp, rt.ctypes.data_as(C.c_void_p),
+                                           self.ra, self.rb, npts, nvec, ci.ctypes.data_as(C.c_void_p),
+                                           r.ctypes.data_as(C.c_void_p), psi.ctypes.data_as(C.c_void_p))
+        _lib.check(self.lib, self._h, rc, "bspatom_wavefunction")
+        return r, psi
+
+    # ---- TRANS_AMP contraction (PhotoIon.f90:90-105) ------------------------------------
+    def dipole(self, A_band: np.ndarray, Cf: np.ndarray, Ci: np.ndarray) -> np.ndarray:
+        """D = Cf^T A Ci with A in general band storage (2kd+1, n)."""
+        A_band = np.asfortranarray(A_band, dtype=np.float64)
+        Cf = np.asfortranarray(Cf, dtype=np.float64)
+        Ci = np.asfortranarray(Ci, dtype=np.float64)
+        n = Cf.shape[0]
+        kd = (A_band.shape[0] - 1) // 2
+        D = np.empty((Cf.shape[1], Ci.shape[1]), order="F")
+        rc = self.lib.bspatom_dipole(self._h, n, kd, A_band.ctypes.data_as(C.c_void_p), Cf.shape[1],
+                                     Cf.ctypes.data_as(C.c_void_p), Ci.shape[1], Ci.ctypes.data_as(C.c_void_p),
+                                     D.ctypes.data_as(C.c_void_p))
+        _lib.check(self.lib, self._h, rc, "bspatom_dipole")
+        return D
+
+
+def _to_c_problem(p: Problem, l: int, nvec: int, keep: list) -> BspProblem:
+    cp = BspProblem()
+    cp.k, cp.nfun, cp.nkp, cp.ka = int(p.k), int(p.nfun), int(p.nkp), int(p.ka)
+    rt = np.ascontiguousarray(p.rt, dtype=np.float64)
+    keep.append(rt)
+    cp.rt = rt.ctypes.data_as(C.POINTER(C.c_double))
+    if p.xg is not None:
+        xg = np.ascontiguousarray(p.xg, dtype=np.float64)
+        wg = np.ascontiguousarray(p.wg, dtype=np.float64)
+        keep += [xg, wg]
+        cp.xg = xg.ctypes.data_as(C.POINTER(C.c_double))
+        cp.wg = wg.ctypes.data_as(C.POINTER(C.c_double))
+    cp.pot_kind = int(p.pot_kind)
+    par = list(p.pot_par) + [0.0] * 8
+    for i in range(8):
+        cp.pot_par[i] = float(par[i])
+    if p.v_tab is not None:
+        vt = np.ascontiguousarray(p.v_tab, dtype=np.float64)
+        keep.append(vt)
+        cp.v_tab = vt.ctypes.data_as(C.POINTER(C.c_double))
+    cp.l = int(l)
+    cp.ul_extra = float(p.bl[l]) if (p.bl is not None and p.pot_kind == POT_SIMONS_FUES) else 0.0
+    cp.nvec = int(nvec)
+    return cp
+
+
+def build_problem_array(items: List, nvec: Optional[int]):
+    keep: list = []
+    arr = (BspProblem * len(items))()
+    cache = {}
+    for i, (p, l) in enumerate(items):
+        nv = p.nfun if nvec is None else min(int(nvec), p.nfun)
+        key = id(p)
+        if key not in cache:
+            cache[key] = _to_c_problem(p, 0, 0, keep)
+        base = cache[key]
+        C.memmove(C.byref(arr[i]), C.byref(base), C.sizeof(BspProblem))
+        arr[i].l = int(l)
+        arr[i].ul_extra = float(p.bl[l]) if (p.bl is not None and p.pot_kind == POT_SIMONS_FUES) else 0.0
+        arr[i].nvec = nv
+    arr._keep = keep
+    return arr, keep
+
+
+def dsygv(H: np.ndarray, S: np.ndarray, jobz: str = "V", uplo: str = "U"):
+    """LAPACK-shaped entry ``bspatom_dsygv_`` (the one-token rename of matrices.f90:248)."""
+    lib = _lib.load()
+    n = H.shape[0]
+    A = np.asfortranarray(H, dtype=np.float64).copy(order="F")
+    Bm = np.asfortranarray(S, dtype=np.float64).copy(order="F")
+    w = np.zeros(n)
+    work = np.zeros(max(1, 4 * n))
+    ci = lambda v: C.byref(C.c_int(v))
+    info = C.c_int(0)
+    lib.bspatom_dsygv_(ci(1), jobz.encode(), uplo.encode(), ci(n), A.ctypes.data_as(C.c_void_p), ci(n),
+                       Bm.ctypes.data_as(C.c_void_p), ci(n), w.ctypes.data_as(C.c_void_p),
+                       work.ctypes.data_as(C.c_void_p), ci(4 * n), C.byref(info))
+    return w, A, Bm, info.value

@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing: one process per GPU, static partition of the (instance, l) work list, no
+collective on the compute path, ONE gather of eigenpairs at the end.
+
+In the reference the l-loop bodies are independent (they share only the read-only Sij, Tij, Vij,
+matrices.f90:242-248), so the work list shards with no exchange step; S/H0/Q are cheap enough to be
+re-assembled on every rank that needs them."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+
+def shard_items(nitems: int, rank: int, world: int) -> List[int]:
+    """item i -> rank (i mod world): every item costs the same for equal (N, k)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside world")
+    return list(range(rank, nitems, world))
+
+
+def gather_eigenpairs(E_local: np.ndarray, idx_local: Sequence[int], nitems: int, nfun: int,
+                      C_local: Optional[np.ndarray] = None, nvec: int = 0, dst: int = 0, device=None):
+    """Collect the per-rank results on rank ``dst`` for the host writers (Enl.dat,
+    Eigenvec_All.dat, WRITE_WF: matrices.f90:261-265,366-378).
+
+    E_local: (len(idx_local), nfun); C_local: (len(idx_local), nfun*nvec) or None.
+    Uses the default torch.distributed group: NCCL (tensors staged on ``device``) when the
+    backend is nccl, gloo on CPU otherwise.  Returns (E, C) on dst, (None, None) elsewhere.
+    Equal-count all_gather with padding: at most one padded item per rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        E = np.asarray(E_local).reshape(len(idx_local), nfun)
+        Cm = None if C_local is None else np.asarray(C_local).reshape(len(idx_local), nfun * nvec)
+        Eo = np.empty((nitems, nfun)); Eo[list(idx_local)] = E
+        Co = None
+        if Cm is not None:
+            Co = np.empty((nitems, nfun * nvec)); Co[list(idx_local)] = Cm
+        return Eo, Co
+    world, rank = dist.get_world_size(), dist.get_rank()
+    backend = dist.get_backend()
+    dev = device if backend == "nccl" else torch.device("cpu")
+    per = (nitems + world - 1) // world
+    width = nfun + (nfun * nvec if C_local is not None else 0)
+    buf = torch.zeros((per, width), dtype=torch.float64, device=dev)
+    nloc = len(idx_local)
+    if nloc:
+        buf[:nloc, :nfun] = torch.from_numpy(np.ascontiguousarray(E_local).reshape(nloc, nfun)).to(dev)
+        if C_local is not None:
+            buf[:nloc, nfun:] = torch.from_numpy(np.ascontiguousarray(C_local).reshape(nloc, nfun * nvec)).to(dev)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    if rank != dst:
+        return None, None
+    E = np.empty((nitems, nfun))
+    Cm = np.empty((nitems, nfun * nvec)) if C_local is not None else None
+    for r in range(world):
+        ids = shard_items(nitems, r, world)
+        blk = out[r][: len(ids)].cpu().numpy()
+        E[ids] = blk[:, :nfun]
+        if Cm is not None:
+            Cm[ids] = blk[:, nfun:]
+    return E, Cm

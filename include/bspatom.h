@@ -132,7 +132,9 @@ int bspatom_wavefunction(bspatom_handle h, int k, int nfun, int nkp, const doubl
 /* ---- statistics of the last run (for bench.py) ----------------------------- *
  * out[0] kernel launches, out[1] multisection rounds, out[2] refinement
  * iterations, out[3] ms in assembly, out[4] ms eigenvalue stage, out[5] ms
- * eigenvector stage, out[6] ms finalize, out[7] total device ms               */
+ * eigenvector stage, out[6] ms finalize, out[7] total device ms,
+ * out[8..11] summed device ms of the multisection / factor / back-substitution /
+ * assembly kernels (CUDA events around each launch), out[12..15] their launch counts */
 int bspatom_get_stats(bspatom_handle h, double *out, int nout);
 
 #ifdef __cplusplus

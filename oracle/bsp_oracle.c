@@ -66,9 +66,14 @@ void bsp_gauleg(double x1, double x2, double *x, double *w, int n)
     int m = (n + 1) / 2;
     double xm = 0.5 * (x2 + x1);
     double xl = 0.5 * (x2 - x1);
+    /* pp is a routine-level variable in the reference: for odd n the middle
+     * start value cos(pi/2) ~ 6e-17 already satisfies |z - z1| <= EPS1 with
+     * z1 = 0, the Newton loop is skipped (:136) and w(middle) is formed with
+     * the pp left over from the previous node (reference quirk, kept) */
+    double pp = 0.0;
     for (int i = 1; i <= m; ++i) {
         double z = cos(PI * (i - .25) / (n + .5)); /* :134 */
-        double z1 = 0.0, pp = 0.0;
+        double z1 = 0.0;
         while (fabs(z - z1) > EPS1) {              /* :136 */
             double p1 = 1.0, p2 = 0.0, p3;
             for (int j = 1; j <= n; ++j) {

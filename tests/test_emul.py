@@ -1,0 +1,112 @@
+"""CPU replay of the solver's per-thread bodies (bspatom_b200/csrc/bsp_core.h) and stage schedule
+(bsp_driver.h) through tests/emul/emul_eig.cpp -- checks the solver LOGIC against the oracle
+without a GPU.  The parity tests proper are the -m gpu ones; nothing here is a product path."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "emul_eig.cpp")
+SO = os.path.join(HERE, "emul", "libemul_eig.so")
+CORE = [os.path.join(HERE, "..", "bspatom_b200", "csrc", f) for f in ("bsp_core.h", "bsp_driver.h")]
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    newest = max(os.path.getmtime(p) for p in [SRC] + CORE)
+    if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-o", SO, SRC])
+    lib = C.CDLL(SO)
+    lib.emul_solve.argtypes = [C.c_int] * 3 + [dp, dp, ip] + [C.c_double] * 3 + [C.c_int] * 3 + [dp] * 3
+    lib.emul_count.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double]
+    return lib
+
+
+def lower_band(A, b):
+    n = A.shape[0]
+    ab = np.zeros((b + 1, n))
+    for d in range(b + 1):
+        ab[d, :n - d] = np.diagonal(A, -d)
+    return np.ascontiguousarray(ab)
+
+
+def solve(emul, H, S, b, nvec=None, tau=0.02):
+    n = H.shape[0]
+    hb, sb = lower_band(H, b), lower_band(S, b)
+    nv = np.array([n if nvec is None else nvec], dtype=np.int32)
+    E = np.zeros(n)
+    Cm = np.zeros((n, n))
+    st = np.zeros(8)
+    rc = emul.emul_solve(n, b, 1, hb.ctypes.data_as(dp), sb.ctypes.data_as(dp), nv.ctypes.data_as(ip), tau, 1e-4,
+                         1e-11, 90, 4, 12, E.ctypes.data_as(dp), Cm.ctypes.data_as(dp), st.ctypes.data_as(dp))
+    assert rc == 0
+    return E, Cm.T[:, :nv[0]].copy(), st
+
+
+def test_sturm_count_is_inertia(emul, oracle):
+    b = oracle.make_basis(kind_grid=0, k=5, nfun=40, rb=30.0)
+    m = oracle.matrix_svt(b, lmax=1)
+    H = oracle.hamiltonian(m["T"], m["U"][:, :, 1], m["V"])
+    w, _, _ = oracle.dsygv(H, m["S"])
+    hb, sb = lower_band(H, 4), lower_band(m["S"], 4)
+    for j in (0, 1, 7, 20, 39):
+        for sig, expect in ((w[j] - 1e-6 * (1 + abs(w[j])), j), (w[j] + 1e-6 * (1 + abs(w[j])), j + 1)):
+            assert emul.emul_count(40, 4, hb.ctypes.data_as(dp), sb.ctypes.data_as(dp), sig) == expect
+
+
+def test_shipped_input_against_golden_truth(emul, oracle):
+    """cfg1: the solver's eigenvalues vs the 40-digit spectrum -- expected CLOSER than dsygv."""
+    gold = json.load(open(os.path.join(HERE, "golden", "shipped_truth.json")))
+    b = oracle.shipped_basis()
+    m = oracle.matrix_svt(b, lmax=2)
+    for l in range(3):
+        H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+        truth = np.array([float(s) for s in gold["levels"][str(l)]])
+        E, Cm, st = solve(emul, H, m["S"], b.k - 1)
+        assert st[2] == 0 and st[3] == 0 and st[5] == 0          # brackets closed, all converged
+        rel = np.abs(E - truth) / np.maximum(np.abs(truth), 1e-2)
+        assert rel.max() < 5e-13, rel.max()
+        w, v, _ = oracle.dsygv(H, m["S"])
+        rel_ref = np.abs(w - truth) / np.maximum(np.abs(truth), 1e-2)
+        assert rel.max() <= rel_ref.max()
+        # eigenvectors: S-orthonormal, tiny scaled residual, equal to LAPACK's up to sign
+        G = Cm.T @ m["S"] @ Cm
+        assert np.abs(G - np.eye(b.nfun)).max() < 1e-10
+        R = H @ Cm - (m["S"] @ Cm) * E
+        assert (np.abs(R).max(0) / np.maximum(1, np.abs(E))).max() < 1e-12
+        ov = np.abs(np.sum(Cm * (m["S"] @ v), axis=0))
+        assert ov.min() > 1 - 1e-8
+        # sign convention: first significant coefficient positive
+        for j in range(b.nfun):
+            c = Cm[:, j]
+            first = np.nonzero(np.abs(c) >= 1e-6 * np.abs(c).max())[0][0]
+            assert c[first] > 0
+
+
+@pytest.mark.parametrize("k,nfun,grid", [(3, 30, 0), (5, 64, 1), (8, 90, 0), (10, 50, 0)])
+def test_orders_and_sizes(emul, oracle, k, nfun, grid):
+    b = oracle.make_basis(kind_grid=grid, k=k, nfun=nfun, rb=40.0)
+    m = oracle.matrix_svt(b, lmax=2, par=oracle.pot_params(0, 2.0))
+    H = oracle.hamiltonian(m["T"], m["U"][:, :, 2], m["V"])
+    E, Cm, st = solve(emul, H, m["S"], k - 1)
+    w, v, _ = oracle.dsygv(H, m["S"])
+    tol = np.maximum(np.maximum(1e-12 * np.abs(w), 1e-10), 64 * 2.2e-16 * np.abs(w).max())
+    assert np.all(np.abs(E - w) <= tol)
+    assert st[3] == 0
+
+
+def test_partial_vectors_still_give_all_eigenvalues(emul, oracle):
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=60, rb=50.0)
+    m = oracle.matrix_svt(b, lmax=0)
+    H = oracle.hamiltonian(m["T"], m["U"][:, :, 0], m["V"])
+    E, Cm, st = solve(emul, H, m["S"], 6, nvec=5)
+    w, v, _ = oracle.dsygv(H, m["S"])
+    assert np.all(np.abs(E - w) <= np.maximum(1e-12 * np.abs(w), 1e-10))
+    assert Cm.shape[1] == 5 and np.abs(np.abs(np.sum(Cm * (m["S"] @ v[:, :5]), 0)) - 1).max() < 1e-9

@@ -1,0 +1,136 @@
+"""GPU: banded assembly through the C-ABI (bspatom_assemble_band) against the oracle's MATRIX_SVT
+restatement on identical knots / nodes.  Bar (north_star): 1e-13 entrywise relative."""
+import os
+
+import numpy as np
+import pytest
+
+import bspatom_b200 as bsp
+from cases import band_to_dense_general, band_to_dense_sym, host_basis, rel_entry_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-13
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def oracle_mats(oracle, a, lmax=1, kind_pot=0, par=None):
+    b = oracle.make_basis(kind_grid=a.KIND_GRID, k=a.k, ka=a.ka, nfun=a._nfun0, ra=a.ra, rb=a.rb, rmax=a.rmax)
+    assert np.array_equal(b.rt, a.rt)
+    return b, oracle.matrix_svt(b, lmax=lmax, kind_pot=kind_pot, par=par)
+
+
+def make(kind_grid=0, k=7, nfun=100, rb=500.0, rmax=0.0, ka=0, **kw):
+    a = host_basis(kind_grid=kind_grid, k=k, nfun=nfun, rb=rb, rmax=rmax, ka=ka, **kw)
+    a._nfun0 = nfun
+    return a
+
+
+def compare_all(atom, oracle, a, kind_pot=0, par=None, tol=TOL, with_nodes=True):
+    b, m = oracle_mats(oracle, a, lmax=1, kind_pot=kind_pot, par=par)
+    p = a.problem()
+    if par is not None:
+        p.pot_par = tuple(par)
+    p.pot_kind = kind_pot
+    if with_nodes:
+        p.xg, p.wg = b.xg, b.wg
+    band = atom.MATRIX_SVT(p)
+    n = a.nfun
+    ref = dict(S=m["S"], T=m["T"], V=m["V"], R=m["R"], Rinv=m["Ri"], Q=m["U"][:, :, 1] / 2.0)
+    worst = {}
+    for nm, r in ref.items():
+        got = band_to_dense_sym(band[nm], n)
+        # the reference's upper triangle is what DSYGV 'U' reads (matrices.f90:248)
+        err = rel_entry_err(np.triu(got), np.triu(r))
+        worst[nm] = err
+        assert err <= tol, (nm, err)
+    # H0 = T + V is this library's own combination (the reference adds T + U_l + V at matrices.f90:244);
+    # T > 0 and V < 0 cancel, so the bar is relative to |T| + |V| entrywise
+    got = np.triu(band_to_dense_sym(band["H0"], n))
+    mag = np.triu(np.abs(m["T"]) + np.abs(m["V"]))
+    mask = mag > 0
+    err = np.max(np.abs(got - np.triu(m["T"] + m["V"]))[mask] / mag[mask])
+    assert err <= tol, ("H0", err)
+    gotD = band_to_dense_general(band["D"], n)
+    err = rel_entry_err(gotD, m["D"])
+    worst["D"] = err
+    assert err <= 50 * tol, ("D", err)   # B_i B_j' has genuine sign cancellation inside an interval
+    return worst
+
+
+def test_shipped_input_cfg1(atom, oracle):
+    compare_all(atom, oracle, make(kind_grid=2, nfun=100, rmax=60.0))
+
+
+def test_shipped_input_against_committed_fixture(atom):
+    """same comparison against tests/golden/shipped_band.npz (no oracle involved)."""
+    z = np.load(os.path.join(GOLD, "shipped_band.npz"))
+    a = make(kind_grid=2, nfun=100, rmax=60.0)
+    p = a.problem()
+    p.xg, p.wg = z["xg"], z["wg"]
+    band = atom.MATRIX_SVT(p)
+    for nm, key in (("S", "S"), ("T", "T"), ("V", "V"), ("Q", "Q"), ("R", "R"), ("Rinv", "Ri")):
+        assert rel_entry_err(band[nm], z[key]) <= TOL, nm
+    assert rel_entry_err(band["D"], z["D"]) <= 50 * TOL
+
+
+def test_library_nodes_equal_host_nodes(atom, oracle):
+    """xg = wg = NULL: the library runs its own gauleg and must land on the same matrices."""
+    compare_all(atom, oracle, make(kind_grid=0, nfun=150, rb=100.0), with_nodes=False, tol=2e-13)
+
+
+@pytest.mark.parametrize("kw", [dict(kind_grid=0, nfun=1000), dict(kind_grid=2, nfun=782, rmax=70.0),
+                                dict(kind_grid=1, nfun=400), dict(kind_grid=0, nfun=500)])
+def test_baseline_grids_k7(atom, oracle, kw):
+    compare_all(atom, oracle, make(**kw))
+
+
+@pytest.mark.parametrize("k,nfun", [(3, 40), (4, 41), (5, 64), (6, 33), (8, 200), (9, 77), (10, 60)])
+def test_other_orders(atom, oracle, k, nfun):
+    # odd ka (k even) exercises the reference's middle-weight quirk through the oracle's nodes
+    compare_all(atom, oracle, make(kind_grid=0, k=k, nfun=nfun, rb=60.0))
+
+
+def test_knot_end_quirk_B1(atom, oracle):
+    """nfun0=808 -> N=1000 with a non-monotone knot pair rb+1ulp, rb; nfun0=408 -> an ulp-wide extra
+    interval.  The GPU treats such intervals as empty; the reference's contribution is O(1e-14)."""
+    compare_all(atom, oracle, make(kind_grid=2, nfun=808, rmax=60.0), tol=1e-12)
+    compare_all(atom, oracle, make(kind_grid=2, nfun=408, rmax=60.0), tol=1e-12)
+
+
+def test_potentials(atom, oracle):
+    a = make(kind_grid=1, nfun=120, rb=80.0, kind_pot=1, zatom=20.0)
+    compare_all(atom, oracle, a, kind_pot=1, par=oracle.pot_params(1, 20.0), tol=5e-13)   # exp(): libm vs CUDA
+    a = make(kind_grid=0, nfun=120, rb=80.0)
+    compare_all(atom, oracle, a, kind_pot=10, par=oracle.pot_params(10, 3.0, (0.25,)), tol=5e-13)
+    compare_all(atom, oracle, a, kind_pot=11, par=oracle.pot_params(11, 7.0, (1.3,)))
+    compare_all(atom, oracle, a, kind_pot=2, par=oracle.pot_params(2, 1.0))
+
+
+def test_tabulated_potential(atom, oracle):
+    """BSPATOM_POT_TABLE: the host evaluates SELPOT itself and hands V at the quadrature points."""
+    a = make(kind_grid=0, nfun=80, rb=40.0)
+    b, m = oracle_mats(oracle, a, lmax=0, kind_pot=11, par=oracle.pot_params(11, 5.0, (0.9,)))
+    par = oracle.pot_params(11, 5.0, (0.9,))
+    vt = np.zeros((a.nkp - 1, a.ka))
+    for mm in range(1, a.nkp):
+        f1 = (a.rt[mm] + a.rt[mm - 1]) / 2.0
+        f2 = (a.rt[mm] - a.rt[mm - 1]) / 2.0
+        for g in range(a.ka):
+            r = f1 + b.xg[g] * f2
+            vt[mm - 1, g] = oracle.selpot(11, par, r if r != 0 else np.finfo(float).eps)
+    p = a.problem()
+    p.pot_kind, p.v_tab, p.xg, p.wg = bsp.POT_TABLE, vt, b.xg, b.wg
+    band = atom.MATRIX_SVT(p)
+    assert rel_entry_err(np.triu(band_to_dense_sym(band["V"], a.nfun)), np.triu(m["V"])) <= TOL
+
+
+def test_invalid_arguments(atom):
+    a = make(kind_grid=0, nfun=50, rb=20.0)
+    p = a.problem()
+    p.k = 2
+    with pytest.raises(bsp.BspAtomError, match="compiled range"):
+        atom.MATRIX_SVT(p)
+    p = a.problem()
+    p.nkp += 1
+    with pytest.raises(bsp.BspAtomError):
+        atom.MATRIX_SVT(p)

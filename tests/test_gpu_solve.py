@@ -1,0 +1,219 @@
+"""GPU: the batched generalized eigensolve through the C-ABI against the oracle (assembly
+restatement + LAPACK dsygv with the reference's arguments, matrices.f90:244-248), the 40-digit
+golden spectrum, and size-independent properties at BASELINE sizes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import bspatom_b200 as bsp
+from cases import cfg3_problems, check_eigenpairs, eig_tolerance, host_basis
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def oracle_pencil(oracle, a, nfun0, l, kind_pot=0, par=None):
+    b = oracle.make_basis(kind_grid=a.KIND_GRID, k=a.k, ka=a.ka, nfun=nfun0, ra=a.ra, rb=a.rb, rmax=a.rmax)
+    m = oracle.matrix_svt(b, lmax=l, kind_pot=kind_pot, par=par)
+    H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+    return b, H, m["S"]
+
+
+def vectors_match_up_to_sign(Cg, Cr, S, E, tol=1e-6):
+    """|<c_gpu, S c_ref>| = 1 up to the eigenvector condition eps*|E_max|/gap of the REFERENCE
+    (dsygv is only backward stable in the norm of the pencil)."""
+    ov = np.abs(np.sum(Cg * (S @ Cr), axis=0))
+    gap = np.minimum(np.diff(E, prepend=-np.inf), np.diff(E, append=np.inf))
+    bound = np.minimum(1.0, (64 * 2.2e-16 * np.abs(E).max() / gap) ** 2 + tol)
+    assert np.all(1.0 - ov <= bound), float(np.max((1.0 - ov) / bound))
+
+
+def test_cfg1_shipped_input_all_l(atom, oracle):
+    gold = json.load(open(os.path.join(HERE, "golden", "shipped_truth.json")))
+    atom.READ_INPUTS(open(os.path.join(HERE, "golden", "cfg1_shipped.inp")).read())
+    atom.GRID()
+    Enl, cinl = atom.SOLVE_SYSTEM()
+    assert Enl.shape == (124, 3) and list(atom.info) == [0, 0, 0]
+    b = oracle.shipped_basis()
+    m = oracle.matrix_svt(b, lmax=2)
+    for l in range(3):
+        H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+        w, v, _ = oracle.dsygv(H, m["S"])
+        truth = np.array([float(s) for s in gold["levels"][str(l)]])
+        E = Enl[:, l]
+        assert np.all(np.abs(E - w) <= eig_tolerance(w)), np.max(np.abs(E - w) / eig_tolerance(w))
+        rel = np.abs(E - truth) / np.maximum(np.abs(truth), 1e-2)
+        assert rel.max() < 1e-12
+        # hydrogen: level i of l is n = i + l + 1
+        for i in range(3):
+            n = i + l + 1
+            assert abs(E[i] + 0.5 / n ** 2) < 1e-6 / n ** 2
+        check_eigenpairs(E, cinl[l], H, m["S"], res_tol=1e-11, orth_tol=1e-9)
+        vectors_match_up_to_sign(cinl[l], v, m["S"], w)
+
+
+@pytest.mark.parametrize("l", [0, 1, 17, 50])
+def test_cfg2_linear_grid_strict_tolerance(atom, oracle, l):
+    """cfg2-lin: KIND_GRID=0, N=1000, k=7: well scaled, so the strict 1e-12 / 1e-10 bar applies
+    (plus dsygv's own eps*|E_max| floor at high l)."""
+    a = host_basis(kind_grid=0, k=7, nfun=1000, rb=500.0)
+    b, H, S = oracle_pencil(oracle, a, 1000, l)
+    w, v, info = oracle.dsygv(H, S)
+    Es, Cs, inf = atom.solve_batch([(a.problem(), l)])
+    assert inf[0] == 0
+    tol = eig_tolerance(w, c_eps=32.0)
+    assert np.all(np.abs(Es[0] - w) <= tol), np.max(np.abs(Es[0] - w) / tol)
+    check_eigenpairs(Es[0], Cs[0], H, S, res_tol=1e-11, orth_tol=1e-9)
+    vectors_match_up_to_sign(Cs[0], v, S, w)
+
+
+@pytest.mark.parametrize("l", [0, 50])
+def test_cfg2_explin_grid(atom, oracle, l):
+    """cfg2-explin: |E_max| ~ 3e7..4e9, dsygv is only eps*|E_max| accurate; compare within that floor
+    and check the residual (scaled by |E|) and S-orthonormality, which do not depend on the reference."""
+    a = host_basis(kind_grid=2, k=7, nfun=782, rb=500.0, rmax=70.0)
+    assert a.nfun == 1000
+    b, H, S = oracle_pencil(oracle, a, 782, l)
+    w, v, info = oracle.dsygv(H, S)
+    Es, Cs, inf = atom.solve_batch([(a.problem(), l)])
+    assert inf[0] == 0
+    tol = eig_tolerance(w)
+    assert np.all(np.abs(Es[0] - w) <= tol), np.max(np.abs(Es[0] - w) / tol)
+    check_eigenpairs(Es[0], Cs[0], H, S, res_tol=1e-11, orth_tol=1e-9)
+
+
+def test_cfg2_batch_equals_single_and_partition_is_bit_identical(atom):
+    """work list (l = 0..15) solved as one batch, as two interleaved shards (rank r of 2 takes items
+    r, r+2, ...: bspatom_b200.parallel.shard_items) and one by one: results must be bit-identical
+    (a simulated partition on one device)."""
+    from bspatom_b200.parallel import shard_items
+
+    a = host_basis(kind_grid=0, k=7, nfun=300, rb=150.0)
+    p = a.problem()
+    items = [(p, l) for l in range(16)]
+    Es, Cs, info = atom.solve_batch(items)
+    assert not info.any()
+    for r in range(2):
+        ids = shard_items(len(items), r, 2)
+        Er, Cr, _ = atom.solve_batch([items[i] for i in ids])
+        for j, i in enumerate(ids):
+            assert np.array_equal(Er[j], Es[i]) and np.array_equal(Cr[j], Cs[i])
+    E1, C1, _ = atom.solve_batch([items[5]])
+    assert np.array_equal(E1[0], Es[5]) and np.array_equal(C1[0], Cs[5])
+
+
+def test_cfg3_screened_potentials_sample(atom, oracle):
+    """cfg3: Yukawa / Tietz sweep, N=500; 24 of the 4096 problems against the oracle, 256 through
+    properties only."""
+    a, items = cfg3_problems(256)
+    Es, Cs, info = atom.solve_batch(items)
+    assert not info.any()
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=500, rb=500.0)
+    for i in list(range(0, 256, 11))[:24]:
+        p, l = items[i]
+        par = np.zeros(8)
+        par[:2] = p.pot_par
+        m = oracle.matrix_svt(b, lmax=l, kind_pot=p.pot_kind, par=par)
+        H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+        w, v, _ = oracle.dsygv(H, m["S"])
+        tol = eig_tolerance(w, c_eps=32.0)
+        assert np.all(np.abs(Es[i] - w) <= tol), (i, np.max(np.abs(Es[i] - w) / tol))
+        check_eigenpairs(Es[i], Cs[i], H, m["S"], res_tol=1e-11, orth_tol=1e-9)
+    for i in range(256):
+        assert np.all(np.diff(Es[i]) > 0)
+
+
+def test_cfg4_large_box_k8(atom, oracle):
+    """cfg4 shape at reduced N (k=8, ka=11 -> the odd-ka quirk nodes travel from the host side);
+    the full N=4000 case is covered by properties in test_full_size_properties."""
+    a = host_basis(kind_grid=0, k=8, nfun=600, rb=300.0)
+    b, H, S = oracle_pencil(oracle, a, 600, 3)
+    w, v, _ = oracle.dsygv(H, S)
+    p = a.problem()
+    p.xg, p.wg = b.xg, b.wg
+    Es, Cs, inf = atom.solve_batch([(p, 3)])
+    assert inf[0] == 0
+    tol = eig_tolerance(w, c_eps=32.0)
+    assert np.all(np.abs(Es[0] - w) <= tol)
+    check_eigenpairs(Es[0], Cs[0], H, S, res_tol=1e-11, orth_tol=1e-9)
+
+
+def test_full_size_properties_n4000(atom):
+    """BASELINE cfg4 at full size: N=4000, k=8, Rmax=2000, one l: no dense oracle (minutes per l on
+    the CPU) -- ascending spectrum, hydrogen levels, and residual / orthonormality checked on the
+    device-independent banded operators built by the library itself."""
+    a = host_basis(kind_grid=0, k=8, nfun=4000, rb=2000.0, ka=12)
+    p = a.problem()
+    Es, Cs, inf = atom.solve_batch([(p, 1)], nvec=64)
+    assert inf[0] == 0
+    E, Cm = Es[0], Cs[0]
+    assert np.all(np.diff(E) > 0)
+    for i in range(4):
+        n = i + 2
+        assert abs(E[i] + 0.5 / n ** 2) < 1e-7
+    band = atom.MATRIX_SVT(p)
+    from cases import band_to_dense_sym
+
+    S = band_to_dense_sym(band["S"], 4000)
+    H = band_to_dense_sym(band["H0"], 4000) + 2.0 * band_to_dense_sym(band["Q"], 4000)
+    SC = S @ Cm
+    assert np.abs(Cm.T @ SC - np.eye(64)).max() < 1e-9
+    R = H @ Cm - SC * E[:64]
+    assert (np.abs(R).max(0) / np.maximum(1, np.abs(E[:64]))).max() < 1e-11
+
+
+def test_nvec_subset_and_values_only(atom, oracle):
+    a = host_basis(kind_grid=0, k=7, nfun=200, rb=100.0)
+    b, H, S = oracle_pencil(oracle, a, 200, 2)
+    w, v, _ = oracle.dsygv(H, S)
+    Es, Cs, inf = atom.solve_batch([(a.problem(), 2)], nvec=10)
+    assert Cs[0].shape == (200, 10)
+    assert np.all(np.abs(Es[0] - w) <= eig_tolerance(w, c_eps=32.0))
+    Ev, Cv, inf = atom.solve_batch([(a.problem(), 2)], nvec=0, want_vectors=False)
+    assert np.all(np.abs(Ev[0] - w) <= eig_tolerance(w, c_eps=32.0))
+
+
+def test_mixed_shapes_in_one_batch(atom, oracle):
+    a1 = host_basis(kind_grid=0, k=7, nfun=120, rb=60.0)
+    a2 = host_basis(kind_grid=1, k=5, nfun=90, rb=60.0)
+    items = [(a1.problem(), 0), (a2.problem(), 1), (a1.problem(), 2), (a2.problem(), 0)]
+    Es, Cs, inf = atom.solve_batch(items)
+    assert not inf.any()
+    for (a, n0), (p, l), E in zip([(a1, 120), (a2, 90), (a1, 120), (a2, 90)], items, Es):
+        b, H, S = oracle_pencil(oracle, a, n0, l)
+        w, _, _ = oracle.dsygv(H, S)
+        assert np.all(np.abs(E - w) <= eig_tolerance(w))
+
+
+def test_simons_fues_ul_extra(atom, oracle):
+    a = host_basis(kind_grid=0, k=7, nfun=150, rb=80.0, kind_pot=2, lmax=3)
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=150, rb=80.0)
+    m = oracle.matrix_svt(b, lmax=3, kind_pot=2, par=oracle.pot_params(2, 1.0))
+    Es, Cs, inf = atom.solve_batch([(a.problem(), l) for l in range(4)])
+    for l in range(4):
+        H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+        w, _, _ = oracle.dsygv(H, m["S"])
+        assert np.all(np.abs(Es[l] - w) <= eig_tolerance(w))
+
+
+def test_dsygv_entry_is_a_drop_in(atom, oracle):
+    """Level 0: same arguments as matrices.f90:248, dense in / dense out."""
+    b = oracle.shipped_basis()
+    m = oracle.matrix_svt(b, lmax=1)
+    H = oracle.hamiltonian(m["T"], m["U"][:, :, 1], m["V"])
+    w, v, _ = oracle.dsygv(H, m["S"])
+    wg, A, Bf, info = bsp.dsygv(H, m["S"])
+    assert info == 0
+    assert np.all(np.abs(wg - w) <= eig_tolerance(w))
+    check_eigenpairs(wg, A, H, m["S"], res_tol=1e-11, orth_tol=1e-9)
+    U = np.triu(Bf)
+    assert np.allclose(U.T @ U, m["S"], rtol=0, atol=1e-14)       # B <- Cholesky factor
+    # not positive definite -> info = n + i like LAPACK
+    Sbad = m["S"].copy()
+    Sbad[10, 10] = -1.0
+    _, _, _, info = bsp.dsygv(H, Sbad)
+    assert info == b.nfun + 11
+    _, _, _, info = bsp.dsygv(np.ones((40, 40)), np.eye(40))
+    assert info == -5                                              # not banded

@@ -1,0 +1,164 @@
+"""CPU: the oracle against its pins (analytic hydrogen, 40-digit golden spectrum, LAPACK dsygv,
+structural invariants).  The reference ships no tests or golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+def test_sizes_shipped_input(oracle):
+    # worked example of SURVEY.md App. A.1: nfun 100 -> 124, nkp 131, 36 exp + 84 lin intervals
+    s = oracle.sizes(2, 7, 0, 100, 0, 0, 0.0, 500.0, 60.0)
+    assert s == dict(ka=10, nbc1=6, nbc2=6, nkp=131, nointv=120, nfun=124, nintv_exp=36, nintv_lin=84)
+
+
+def test_gauleg_is_gauss_legendre(oracle):
+    for n in (4, 10, 12, 16):
+        x, w = oracle.gauleg(n)
+        xr, wr = np.polynomial.legendre.leggauss(n)
+        assert np.allclose(x, xr, rtol=0, atol=4e-16)
+        assert np.allclose(w, wr, rtol=2e-13, atol=0)
+
+
+def test_gauleg_odd_n_quirk(oracle):
+    """Reference quirk (Modules.f90:134-147): for odd n the middle start value cos(pi/2) ~ 6e-17 is
+    already within EPS1 of z1 = 0, the Newton loop is skipped and the middle weight is built from the
+    previous node's derivative.  The default ka = k+3 is odd for even k (k=8 -> ka=11)."""
+    for n in (9, 11):
+        x, w = oracle.gauleg(n)
+        xr, wr = np.polynomial.legendre.leggauss(n)
+        mid = n // 2
+        assert np.allclose(np.delete(w, mid), np.delete(wr, mid), rtol=2e-13)
+        assert abs(x[mid]) < 1e-16
+        assert np.isclose(w[mid], w[mid - 1] * (1.0 - x[mid - 1] ** 2), rtol=1e-14)   # pp of node mid-1
+        assert abs(w.sum() - 2.0) > 1e-2
+
+
+def test_interv_semantics(oracle):
+    b = oracle.shipped_basis()
+    # interior point, left-continuity, end points (interv.f90:86-116)
+    assert oracle.interv(b.rt, 0.0) == (b.nbc1, 0)
+    assert oracle.interv(b.rt, b.rt[40]) == (41, 0)
+    assert oracle.interv(b.rt, 500.0) == (b.nkp - b.nbc2, 0)
+    assert oracle.interv(b.rt, 500.1) == (1, 1)
+    assert oracle.interv(b.rt, -0.1) == (1, -1)
+
+
+def test_bsplines_partition_of_unity_and_derivative(oracle):
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=60, rb=30.0)
+    for r in (3.7, 11.123, 20.9):   # interior: all k splines at r belong to the basis
+        left, bsp, dbsp = oracle.bspall(b, r)
+        assert abs(bsp.sum() - 1.0) < 1e-14
+        h = 1e-6
+        _, bp, _ = oracle.bspall(b, r + h)
+        _, bm, _ = oracle.bspall(b, r - h)
+        assert np.allclose(dbsp, (bp - bm) / (2 * h), atol=1e-7)
+
+
+def test_structure_of_assembled_matrices(oracle):
+    b = oracle.shipped_basis()
+    m = oracle.matrix_svt(b, lmax=2)
+    n, k = b.nfun, b.k
+    for nm in ("S", "T", "V", "R", "Ri"):
+        A = m[nm]
+        if nm in ("S", "T"):
+            assert np.array_equal(A, A.T), nm                  # products commute term by term (App. B-8)
+        else:                                                  # (fbra*V)*fket vs (fket*V)*fbra: rounding only;
+            assert np.allclose(A, A.T, rtol=1e-14, atol=0), nm # DSYGV 'U' reads the upper triangle
+        i, j = np.nonzero(A)
+        assert np.max(np.abs(i - j)) == k - 1                   # half bandwidth exactly k-1
+    assert np.linalg.eigvalsh(m["S"]).min() > 0
+    # U_l = l(l+1) U_unit: the reference accumulates lmax+1 redundant copies (matrices.f90:148-153)
+    assert np.allclose(m["U"][:, :, 2], 3.0 * m["U"][:, :, 1], rtol=1e-14, atol=0)
+    assert not np.any(m["U"][:, :, 0])
+    # D is the non-symmetric one: D + D^T = boundary term = 0 for functions vanishing at both ends
+    assert np.abs(m["D"] + m["D"].T).max() < 1e-12
+
+
+def test_fast_interval_search_equals_literal(oracle):
+    b = oracle.make_basis(kind_grid=1, k=5, nfun=40, rb=50.0)
+    a = oracle.matrix_svt(b, lmax=1, fast=True)
+    c = oracle.matrix_svt(b, lmax=1, fast=False)
+    for nm in a:
+        assert np.array_equal(a[nm], c[nm]), nm
+
+
+def test_hydrogen_known_answer(oracle):
+    """analytic pin: level i of angular momentum l is n = i + l, E = -Z^2/(2 n^2)
+    (the reference prints i+l itself, matrices.f90:263)."""
+    gold = json.load(open(os.path.join(GOLD, "hydrogen.json")))["levels"]
+    b = oracle.shipped_basis()
+    m = oracle.matrix_svt(b, lmax=2)
+    for l in range(3):
+        w, v = oracle.solve_system(m, l)
+        for i in range(4):
+            n = i + 1 + l
+            assert abs(w[i] - gold[str(n)]) < 1e-6 * abs(gold[str(n)]), (l, i)   # basis-limited
+    Z = 3.0
+    m = oracle.matrix_svt(oracle.make_basis(kind_grid=1, k=7, nfun=120, rb=80.0), lmax=0, par=oracle.pot_params(0, Z))
+    w, _ = oracle.solve_system(m, 0)
+    assert abs(w[0] + Z * Z / 2) < 1e-8
+
+
+def test_golden_spectrum_shipped_input(oracle):
+    """40-digit pin (tests/golden/make_golden.py): dsygv must sit inside its own backward-error
+    floor c*eps*|E_max| of the truth, the low levels much closer."""
+    gold = json.load(open(os.path.join(GOLD, "shipped_truth.json")))
+    b = oracle.shipped_basis()
+    assert gold["nfun"] == b.nfun
+    m = oracle.matrix_svt(b, lmax=2)
+    eps = np.finfo(float).eps
+    for l in range(3):
+        truth = np.array([float(s) for s in gold["levels"][str(l)]])
+        w, v = oracle.solve_system(m, l)
+        assert np.max(np.abs(w - truth)) < 64 * eps * truth[-1]
+        H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+        assert np.abs(v.T @ m["S"] @ v - np.eye(b.nfun)).max() < 1e-12     # C^T S C = I (ITYPE=1)
+
+
+def test_golden_band_fixture(oracle):
+    z = np.load(os.path.join(GOLD, "shipped_band.npz"))
+    b = oracle.shipped_basis()
+    assert np.array_equal(z["rt"], b.rt)
+    m = oracle.matrix_svt(b, lmax=1)
+    kd = b.k - 1
+    for nm in ("S", "T", "V", "R", "Ri"):
+        assert np.array_equal(oracle.dense_to_band_upper(m[nm], kd), z[nm]), nm
+    assert np.array_equal(oracle.dense_to_band_upper(m["U"][:, :, 1] / 2.0, kd), z["Q"])
+
+
+def test_rogers_and_simons_fues_potentials(oracle):
+    par = oracle.pot_params(1, zatom=20.0)            # Ca+: Z=20, Ntot=18
+    assert par[1] == 18
+    r = 0.7
+    v = oracle.selpot(1, par, r)
+    expect = -(20.0 - 18 + sum(par[2 + i] * np.exp(-par[5 + i] * r) for i in range(3))) / r
+    assert abs(v - expect) < 1e-15 * abs(expect)
+    assert oracle.selpot(2, oracle.pot_params(2, 1.0), 2.0) == -0.5
+    b = oracle.make_basis(kind_grid=0, k=5, nfun=30, rb=20.0)
+    m = oracle.matrix_svt(b, lmax=3, kind_pot=2, par=oracle.pot_params(2, 1.0))
+    bl = oracle.simons_fues_bl(3)
+    m0 = oracle.matrix_svt(b, lmax=3, kind_pot=0, par=oracle.pot_params(0, 1.0))
+    # U_l(SF) = [l(l+1) + 2 Bl(l)] Q with Q = U_1(Coulomb)/2 ... (matrices.f90:149-152)
+    Q = m0["U"][:, :, 1] / 2.0
+    for l in range(4):
+        assert np.allclose(m["U"][:, :, l], (l * (l + 1) + 2 * bl[l]) * Q, rtol=1e-13, atol=1e-18)
+
+
+def test_write_wf_and_dipole_restatements(oracle):
+    b = oracle.shipped_basis()
+    m = oracle.matrix_svt(b, lmax=1)
+    w0, v0 = oracle.solve_system(m, 0)
+    r, psi = oracle.write_wf(b, v0[:, 0], npts=2000)
+    # 1s radial function u(r) = 2 r exp(-r) (up to sign), WRITE_WF grid r_i = i*(rb-ra)/npts
+    s = np.sign(psi[5])
+    assert np.max(np.abs(s * psi - 2 * r * np.exp(-r))) < 2e-5
+    w1, v1 = oracle.solve_system(m, 1)
+    out = oracle.dipole_dots(m["R"], v0[:, 0], v1[:, :5])
+    assert np.allclose(out, v1[:, :5].T @ (m["R"] @ v0[:, 0]), rtol=1e-12, atol=1e-14)
+    # <2p|r|1s> = 128 sqrt(6)/243 = 1.2902663...
+    assert abs(abs(out[0]) - 128 * np.sqrt(6) / 243) < 1e-6
