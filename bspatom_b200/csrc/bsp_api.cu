@@ -299,7 +299,7 @@ struct GpuExec {
         if (e != cudaSuccess && first_err == cudaSuccess) first_err = e;
     }
     void bounds() {
-        bsp_bounds_kernel<B><<<g.npencil, 32, 0, h->st>>>(g, cand_s, cand_c); note();
+        bsp_bounds_kernel<B><<<g.npencil, BSP_NCAND, 0, h->st>>>(g, cand_s, cand_c); note();
         bsp_bounds_pick_kernel<<<(g.npencil + 127) / 128, 128, 0, h->st>>>(g, cand_s, cand_c); note();
     }
     void round(int r) {
@@ -366,7 +366,7 @@ size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
     c.scale = cv.take<double>(per); c.res = cv.take<double>(per); c.status = cv.take<int>(per);
     c.fac = cv.take<double>(per);
     c.counters = cv.take<int>(64);
-    c.cand_s = cv.take<double>((size_t)np * 32); c.cand_c = cv.take<int>((size_t)np * 32);
+    c.cand_s = cv.take<double>((size_t)np * BSP_NCAND); c.cand_c = cv.take<int>((size_t)np * BSP_NCAND);
     c.L = cv.take<double>((size_t)np * G.npad * (G.B + 1) * G.ldw);
     c.X = cv.take<double>((size_t)np * G.xrows * G.ldw);
     c.R = cv.take<double>((size_t)np * G.xrows * G.ldw);
@@ -701,10 +701,14 @@ int bspatom_batch_run(bspatom_handle h)
         if (chunk <= 0) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
-            const size_t budget = std::min<size_t>((free_b + h->ws.bytes) / 2, (size_t)48 << 30);
-            chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil, 296));
+            const size_t budget = std::min<size_t>((free_b + h->ws.bytes) / 2, (size_t)64 << 30);
+            chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil, 1024));
         }
         chunk = std::min(chunk, G.npencil);
+        {   /* equal chunks: no under-filled tail launch */
+            const int nchunks = (G.npencil + chunk - 1) / chunk;
+            chunk = (G.npencil + nchunks - 1) / nchunks;
+        }
         const size_t need = carve_chunk(G, chunk, nullptr, c);
         if ((rc = ensure_workspace(h, need))) return rc;
         carve_chunk(G, chunk, h->ws.base, c);

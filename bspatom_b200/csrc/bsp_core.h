@@ -153,8 +153,12 @@ BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restr
 }
 
 /* ------------------------------------------------------------------------- *
- * bounds: candidate 0..15 -> +s0*2^t, 16..31 -> -s0*2^(t-31)
+ * bounds: 64 candidates per pencil around s0 = max_j |H_jj| / S_jj:
+ *   t = 0..31  : +s0 * 2^(t-8)      (2^-8 .. 2^23)
+ *   t = 32..63 : -s0 * 2^(t-32-16)  (2^-16 .. 2^15)
+ * pbound[4p..4p+3] = lo0, hi0, hmax, smax ; lo0 > hi0 flags "not bracketed".
  * ------------------------------------------------------------------------- */
+#define BSP_NCAND 64
 template <int B>
 BSP_HD void bsp_bounds_candidate(const BspEigChunk &g, int p, int lane, double *cand_s, int *cand_c)
 {
@@ -170,13 +174,13 @@ BSP_HD void bsp_bounds_candidate(const BspEigChunk &g, int p, int lane, double *
         const double q = h / s;
         if (q > s0) s0 = q;
     }
-    if (!(s0 > 0.0)) s0 = 1.0;
+    if (!(s0 > 0.0) || !(s0 < INFINITY)) s0 = 1.0;
     double sig;
-    if (lane < 16) sig = ldexp(s0, lane);
-    else sig = -ldexp(s0, lane - 31);
+    if (lane < 32) sig = ldexp(s0, lane - 8);
+    else sig = -ldexp(s0, lane - 32 - 16);
     const double pivmin = 1e-30 * (hmax + fabs(sig) * smax);
-    cand_s[p * 32 + lane] = sig;
-    cand_c[p * 32 + lane] = bsp_sturm_count<B>(fbH, fbS, g.npad, sig, pivmin, nullptr);
+    cand_s[p * BSP_NCAND + lane] = sig;
+    cand_c[p * BSP_NCAND + lane] = bsp_sturm_count<B>(fbH, fbS, g.npad, sig, pivmin, nullptr);
     if (lane == 0) {
         g.pbound[p * 4 + 2] = hmax;
         g.pbound[p * 4 + 3] = smax;
@@ -185,13 +189,14 @@ BSP_HD void bsp_bounds_candidate(const BspEigChunk &g, int p, int lane, double *
 
 BSP_HD void bsp_bounds_pick(const BspEigChunk &g, int p, const double *cand_s, const int *cand_c)
 {
-    /* smallest positive candidate with count n; negative candidate of smallest
-     * magnitude with count 0.  The ladders span 2^-15 .. 2^15 times max|H_jj|/S_jj. */
-    double hi0 = cand_s[p * 32 + 15], lo0 = cand_s[p * 32 + 16];
-    for (int t = 15; t >= 0; --t)
-        if (cand_c[p * 32 + t] >= g.n) hi0 = cand_s[p * 32 + t];
-    for (int t = 16; t < 32; ++t)
-        if (cand_c[p * 32 + t] == 0) lo0 = cand_s[p * 32 + t];
+    /* hi0: smallest positive candidate with nu = n; lo0: negative candidate of
+     * smallest magnitude with nu = 0.  If a ladder never brackets the spectrum
+     * lo0 > hi0 is stored and every eigenpair of the pencil is reported bad. */
+    double hi0 = -1.0, lo0 = 1.0;
+    for (int t = 31; t >= 0; --t)
+        if (cand_c[p * BSP_NCAND + t] >= g.n) hi0 = cand_s[p * BSP_NCAND + t];
+    for (int t = 63; t >= 32; --t)
+        if (cand_c[p * BSP_NCAND + t] == 0) lo0 = cand_s[p * BSP_NCAND + t];
     g.pbound[p * 4 + 0] = lo0;
     g.pbound[p * 4 + 1] = hi0;
 }
@@ -213,6 +218,7 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
     int clo, chi;
     if (round == 0) {
         lo = g.pbound[p * 4 + 0]; hi = g.pbound[p * 4 + 1]; clo = 0; chi = n;
+        if (lo > hi) { const double t_ = lo; lo = hi; hi = t_; } /* unbracketed: flagged in finalize */
     } else {
         lo = g.lo[rd + id]; hi = g.hi[rd + id]; clo = g.clo[rd + id]; chi = g.chi[rd + id];
     }
@@ -343,7 +349,7 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
                 w[r][c] = 0.0;
             }
         }
-        if (r < n) y[r] = (iter == 0) ? bsp_hash_uniform((uint32_t)p, (uint32_t)e, (uint32_t)r)
+        if (r < n) y[r] = (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)r)
                                        : sc * Rp[(size_t)r * ldw];
         else y[r] = 0.0;
     }
@@ -380,7 +386,7 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
             for (int m = 0; m <= B; ++m) {
                 w[t][(t + 1 + m) % K1] = fma(-sigma, BSP_LDG(srow + m), BSP_LDG(hrow + m));
             }
-            if (rn < n) y[t] = (iter == 0) ? bsp_hash_uniform((uint32_t)p, (uint32_t)e, (uint32_t)rn)
+            if (rn < n) y[t] = (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)rn)
                                            : sc * Rp[(size_t)rn * ldw];
             else y[t] = 0.0;
         }
@@ -534,7 +540,8 @@ BSP_HD void bsp_finalize_eigen(const BspEigChunk &g, int p, int e, double *E, do
     }
     fac[id] = sgn * g.scale[id];
     const double r = g.res[id];
-    if (!(r <= res_tol * fmax(1.0, fabs(rho)))) {
+    const bool unbracketed = g.pbound[p * 4 + 0] > g.pbound[p * 4 + 1];
+    if (unbracketed || !(r <= res_tol * fmax(1.0, fabs(rho)))) {
 #if defined(__CUDA_ARCH__)
         atomicAdd(bad + p, 1);
 #else

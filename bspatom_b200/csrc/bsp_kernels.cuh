@@ -15,7 +15,7 @@
 #define BSP_EIG_THREADS 128
 
 template <int B>
-__global__ void __launch_bounds__(32) bsp_bounds_kernel(BspEigChunk g, double *cand_s, int *cand_c)
+__global__ void __launch_bounds__(BSP_NCAND) bsp_bounds_kernel(BspEigChunk g, double *cand_s, int *cand_c)
 {
     bsp_bounds_candidate<B>(g, blockIdx.x, threadIdx.x, cand_s, cand_c);
 }

@@ -15,10 +15,10 @@ struct EmulExec {
     std::vector<double> cand_s;
     std::vector<int> cand_c;
     void bounds() {
-        cand_s.assign(g.npencil * 32, 0.0);
-        cand_c.assign(g.npencil * 32, 0);
+        cand_s.assign(g.npencil * BSP_NCAND, 0.0);
+        cand_c.assign(g.npencil * BSP_NCAND, 0);
         for (int p = 0; p < g.npencil; ++p)
-            for (int l = 0; l < 32; ++l) bsp_bounds_candidate<B>(g, p, l, cand_s.data(), cand_c.data());
+            for (int l = 0; l < BSP_NCAND; ++l) bsp_bounds_candidate<B>(g, p, l, cand_s.data(), cand_c.data());
         for (int p = 0; p < g.npencil; ++p) bsp_bounds_pick(g, p, cand_s.data(), cand_c.data());
     }
     void round(int r) {

@@ -35,7 +35,9 @@ def compare_all(atom, oracle, a, kind_pot=0, par=None, tol=TOL, with_nodes=True)
         p.xg, p.wg = b.xg, b.wg
     band = atom.MATRIX_SVT(p)
     n = a.nfun
-    ref = dict(S=m["S"], T=m["T"], V=m["V"], R=m["R"], Rinv=m["Ri"], Q=m["U"][:, :, 1] / 2.0)
+    # U_1 = [1*2 + 2 Bl(1)] Q  (matrices.f90:149-152); Bl = 0 unless KIND_POT = 2
+    c1 = 2.0 + (2.0 * oracle.simons_fues_bl(1)[1] if kind_pot == 2 else 0.0)
+    ref = dict(S=m["S"], T=m["T"], V=m["V"], R=m["R"], Rinv=m["Ri"], Q=m["U"][:, :, 1] / c1)
     worst = {}
     for nm, r in ref.items():
         got = band_to_dense_sym(band[nm], n)
@@ -50,10 +52,14 @@ def compare_all(atom, oracle, a, kind_pot=0, par=None, tol=TOL, with_nodes=True)
     mask = mag > 0
     err = np.max(np.abs(got - np.triu(m["T"] + m["V"]))[mask] / mag[mask])
     assert err <= tol, ("H0", err)
+    # D = int B_i B_j' has exact analytic zeros (D_ii = [B_i^2/2] = 0) and sign cancellation inside each
+    # interval, so the oracle's own entries carry absolute noise ~eps*|row|: the bar is relative to the
+    # largest entry of the row
     gotD = band_to_dense_general(band["D"], n)
-    err = rel_entry_err(gotD, m["D"])
+    rowmax = np.abs(m["D"]).max(axis=1, keepdims=True)
+    err = float(np.max(np.abs(gotD - m["D"]) / rowmax))
     worst["D"] = err
-    assert err <= 50 * tol, ("D", err)   # B_i B_j' has genuine sign cancellation inside an interval
+    assert err <= tol, ("D", err)
     return worst
 
 
@@ -70,7 +76,7 @@ def test_shipped_input_against_committed_fixture(atom):
     band = atom.MATRIX_SVT(p)
     for nm, key in (("S", "S"), ("T", "T"), ("V", "V"), ("Q", "Q"), ("R", "R"), ("Rinv", "Ri")):
         assert rel_entry_err(band[nm], z[key]) <= TOL, nm
-    assert rel_entry_err(band["D"], z["D"]) <= 50 * TOL
+    assert np.max(np.abs(band["D"] - z["D"])) <= TOL * np.abs(z["D"]).max()
 
 
 def test_library_nodes_equal_host_nodes(atom, oracle):
@@ -93,8 +99,8 @@ def test_other_orders(atom, oracle, k, nfun):
 def test_knot_end_quirk_B1(atom, oracle):
     """nfun0=808 -> N=1000 with a non-monotone knot pair rb+1ulp, rb; nfun0=408 -> an ulp-wide extra
     interval.  The GPU treats such intervals as empty; the reference's contribution is O(1e-14)."""
-    compare_all(atom, oracle, make(kind_grid=2, nfun=808, rmax=60.0), tol=1e-12)
-    compare_all(atom, oracle, make(kind_grid=2, nfun=408, rmax=60.0), tol=1e-12)
+    compare_all(atom, oracle, make(kind_grid=2, nfun=808, rmax=60.0), tol=5e-12)
+    compare_all(atom, oracle, make(kind_grid=2, nfun=408, rmax=60.0), tol=5e-12)
 
 
 def test_potentials(atom, oracle):
