@@ -219,6 +219,8 @@ def main():
     dev_ms, launches = 0.0, 0
     kms = np.zeros(4)
     kcnt = np.zeros(4)
+    stage_ms = np.zeros(4)
+    gaps = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         atom.batch_run()
@@ -227,6 +229,8 @@ def main():
         launches += int(st["launches"])
         kms += [st["ms_k_round"], st["ms_k_factor"], st["ms_k_back"], st["ms_k_assembly"]]
         kcnt += [st["n_k_round"], st["n_k_factor"], st["n_k_back"], st["n_k_assembly"]]
+        stage_ms += [st["ms_assembly"], st["ms_eigenvalues"], st["ms_eigenvectors"], st["ms_finalize"]]
+        gaps.append((st["ms_total"], st["ms_gap_before_chunk"], st["ms_gap_after_last_chunk"]))
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     sampler.stop_flag = True
@@ -269,7 +273,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": total_solves / float(tt[0]), "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
-               "bad_info": int(np.count_nonzero(inf))}
+               "bad_info": int(np.count_nonzero(inf)),
+               "wall_ms_last_step": {k_: atom.stats()[k_] for k_ in ("wall_ms_upload", "wall_ms_run", "wall_ms_download", "wall_ms_copy_tail", "ms_total")}}
         del C_host
 
     # ---------------- CPU baseline + accuracy, rank 0 only ----------------
@@ -354,9 +359,10 @@ def main():
             "cpu_baseline": cpu_baseline,
             "accuracy": acc,
             "kernel_ms_per_step": {n_: float(m_) / args.steps for n_, m_ in zip(names, kms)},
-            "stage_ms_last_step": {k_: last_stats[k_] for k_ in ("ms_assembly", "ms_eigenvalues", "ms_eigenvectors",
-                                                               "ms_finalize", "ms_total")},
+            "stage_ms_per_step": dict(zip(("assembly", "eigenvalues", "eigenvectors", "finalize"),
+                                          (stage_ms / args.steps).tolist())),
             "rounds": int(last_stats["rounds"]), "iters": int(last_stats["iters"]),
+            "per_step_total_gap_pre_post_ms": gaps,
             "wall_ms_per_step": wall_ms_max / args.steps,
         }
         print(json.dumps(line))

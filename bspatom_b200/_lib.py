@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbspatom.so")
+LIB_PATH = os.environ.get("BSPATOM_LIB") or os.path.join(_HERE, "libbspatom.so")  # override: A/B builds only
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -17,6 +17,7 @@ ENODEVICE, ECUDA, EUNSUPPORTED, ESTATE, ENOMEM = 1001, 1002, 1003, 1004, 1005
 
 EXPORTS = [
     "bspatom_create", "bspatom_destroy", "bspatom_last_error", "bspatom_version", "bspatom_set_option",
+    "bspatom_alloc_host", "bspatom_free_host",
     "bspatom_assemble_band", "bspatom_solve_batch", "bspatom_batch_upload", "bspatom_batch_run",
     "bspatom_batch_download", "bspatom_dsygv_", "bspatom_dipole", "bspatom_wavefunction", "bspatom_get_stats",
 ]
@@ -57,6 +58,10 @@ def load():
     L.bspatom_last_error.restype = C.c_char_p
     L.bspatom_version.restype = C.c_int
     L.bspatom_set_option.argtypes = [H, C.c_char_p, C.c_double]
+    L.bspatom_alloc_host.argtypes = [C.c_size_t]
+    L.bspatom_alloc_host.restype = C.c_void_p
+    L.bspatom_free_host.argtypes = [C.c_void_p]
+    L.bspatom_free_host.restype = None
     L.bspatom_assemble_band.argtypes = [H, C.POINTER(BspProblem)] + [C.c_void_p] * 8
     L.bspatom_solve_batch.argtypes = [H, C.c_int, C.POINTER(BspProblem), C.c_void_p, C.c_void_p, C.c_void_p]
     L.bspatom_batch_upload.argtypes = [H, C.c_int, C.POINTER(BspProblem)]

@@ -12,8 +12,10 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -31,12 +33,12 @@
 namespace {
 
 struct Options {
-    double tau = 0.02;
+    double tau = 1e-3;
     double delta_rel = 1e-4;
     double conv_tol = 1e-11;
     double res_tol = 1e-9;
     int max_rounds = 90;
-    int min_iters = 4;
+    int min_iters = 3;
     int max_iters = 12;
     int first_check_round = 6;
     int chunk = 0; /* 0 = auto */
@@ -46,6 +48,7 @@ struct Group {
     int k = 0, B = 0, n = 0, nkp = 0, ka = 0, npad = 0, nrows = 0, xrows = 0, ldw = 0, FS = 0;
     int ninst = 0, npencil = 0;
     bool any_vtab = false;
+    int chunk_cached = 0; /* pencils per chunk decided on the first run */
     std::vector<int> prob_index; /* pencil -> caller's problem index */
     std::vector<int> inst, nvec;
     std::vector<double> cl;
@@ -71,6 +74,8 @@ struct Workspace {
 struct bspatom_handle_s {
     int dev = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st_copy = nullptr; /* D2H of finished chunks overlaps the next chunk's kernels */
+    std::vector<cudaEvent_t> chunk_done;
     std::string err;
     Options opt;
     std::vector<Group> groups;
@@ -79,8 +84,13 @@ struct bspatom_handle_s {
     std::vector<int> p_n, p_nvec;
     bool uploaded = false, ran = false;
     Workspace ws;
-    int *h_counter = nullptr; /* pinned */
-    double stats[16] = {0};
+    /* freed device buffers by byte size: a sweep re-submits batches of identical shape, and
+     * cudaMalloc/cudaFree of the multi-GB result buffers costs tens of ms per call */
+    std::multimap<size_t, void *> pool;
+    size_t pool_bytes = 0;
+    int *h_counter = nullptr;     /* pinned + mapped */
+    int *h_counter_dev = nullptr; /* device view of h_counter */
+    double stats[24] = {0};
     long long launches = 0;
     /* per-kernel-class device timing (CUDA events on the launching stream) */
     std::vector<cudaEvent_t> ev_pool;
@@ -103,27 +113,71 @@ namespace {
         }                                                                                      \
     } while (0)
 
+void pool_flush(bspatom_handle h)
+{
+    for (auto &kv : h->pool) cudaFree(kv.second);
+    h->pool.clear();
+    h->pool_bytes = 0;
+}
+
+size_t pool_round(size_t bytes) { return (bytes + 511) & ~(size_t)511; }
+
 template <class T>
 int dev_alloc(bspatom_handle h, T **p, size_t count)
 {
     *p = nullptr;
     if (count == 0) count = 1;
-    CU(cudaMalloc((void **)p, count * sizeof(T)));
+    const size_t bytes = pool_round(count * sizeof(T));
+    auto it = h->pool.find(bytes);
+    if (it != h->pool.end()) {
+        *p = (T *)it->second;
+        h->pool_bytes -= bytes;
+        h->pool.erase(it);
+        return 0;
+    }
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e != cudaSuccess) {          /* give the pooled memory back and retry once */
+        cudaGetLastError();
+        pool_flush(h);
+        CU(cudaMalloc((void **)p, bytes));
+    }
     return 0;
 }
 
-void free_group(Group &g)
+template <class T>
+void dev_free(bspatom_handle h, T *p, size_t count)
 {
-    cudaFree(g.d_rt); cudaFree(g.d_xgwg); cudaFree(g.d_vtab); cudaFree(g.d_par);
-    cudaFree(g.d_fbS); cudaFree(g.d_fbH0); cudaFree(g.d_fbQ);
-    cudaFree(g.d_inst); cudaFree(g.d_nvec); cudaFree(g.d_pdinfo); cudaFree(g.d_bad);
-    cudaFree(g.d_cl); cudaFree(g.d_E); cudaFree(g.d_C); cudaFree(g.d_coff);
+    if (!p) return;
+    if (count == 0) count = 1;
+    const size_t bytes = pool_round(count * sizeof(T));
+    h->pool.insert({bytes, (void *)p});
+    h->pool_bytes += bytes;
+}
+
+void free_group(bspatom_handle h, Group &g)
+{
+    const size_t per_mat = (size_t)g.nrows * g.FS;
+    dev_free(h, g.d_rt, (size_t)g.ninst * g.nkp);
+    dev_free(h, g.d_xgwg, (size_t)g.ninst * 64);
+    dev_free(h, g.d_vtab, (size_t)g.ninst * (size_t)(g.nkp - 1) * g.ka);
+    dev_free(h, g.d_par, (size_t)g.ninst);
+    dev_free(h, g.d_fbS, per_mat * g.ninst);
+    dev_free(h, g.d_fbH0, per_mat * g.ninst);
+    dev_free(h, g.d_fbQ, per_mat * g.ninst);
+    dev_free(h, g.d_inst, (size_t)g.npencil);
+    dev_free(h, g.d_nvec, (size_t)g.npencil);
+    dev_free(h, g.d_pdinfo, (size_t)g.ninst);
+    dev_free(h, g.d_bad, (size_t)g.npencil);
+    dev_free(h, g.d_cl, (size_t)g.npencil);
+    dev_free(h, g.d_E, (size_t)g.npencil * g.n);
+    dev_free(h, g.d_C, (size_t)g.c_elems);
+    dev_free(h, g.d_coff, (size_t)g.npencil);
     g = Group();
 }
 
 void free_batch(bspatom_handle h)
 {
-    for (auto &g : h->groups) free_group(g);
+    for (auto &g : h->groups) free_group(h, g);
     h->groups.clear();
     h->uploaded = h->ran = false;
 }
@@ -320,11 +374,15 @@ struct GpuExec {
     }
     void check(int allow) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, allow); note(); }
     void zero_counter(int w) {
-        cudaError_t e = cudaMemsetAsync(g.counters + w, 0, sizeof(int), h->st);
-        if (e != cudaSuccess && first_err == cudaSuccess) first_err = e;
+        /* a kernel, not cudaMemsetAsync: nothing on the compute stream may queue on a copy engine
+         * that is busy streaming results to the host */
+        bsp_zero_counter_kernel<<<1, 1, 0, h->st>>>(g.counters + w);
+        note();
     }
     int read_counter(int w) {
-        cudaError_t e = cudaMemcpyAsync(h->h_counter, g.counters + w, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+        bsp_publish_counter_kernel<<<1, 1, 0, h->st>>>(g.counters + w, h->h_counter_dev);
+        h->launches++;
+        cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
         if (e != cudaSuccess) { if (first_err == cudaSuccess) first_err = e; return 0; }
         return *h->h_counter;
@@ -450,7 +508,11 @@ int ensure_workspace(bspatom_handle h, size_t bytes)
     if (h->ws.base) cudaFree(h->ws.base);
     h->ws.base = nullptr;
     h->ws.bytes = 0;
-    CU(cudaMalloc((void **)&h->ws.base, bytes));
+    if (cudaMalloc((void **)&h->ws.base, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        pool_flush(h);
+        CU(cudaMalloc((void **)&h->ws.base, bytes));
+    }
     h->ws.bytes = bytes;
     return 0;
 }
@@ -509,6 +571,18 @@ extern "C" {
 
 int bspatom_version(void) { return BSPATOM_VERSION; }
 
+void *bspatom_alloc_host(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void bspatom_free_host(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 int bspatom_create(bspatom_handle *out, int device_id)
 {
     if (!out) return -1;
@@ -520,7 +594,9 @@ int bspatom_create(bspatom_handle *out, int device_id)
     bspatom_handle h = new bspatom_handle_s();
     h->dev = device_id;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void **)&h->h_counter, 64) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->h_counter, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&h->h_counter_dev, h->h_counter, 0) != cudaSuccess) {
         delete h;
         return BSPATOM_ECUDA;
     }
@@ -533,9 +609,12 @@ int bspatom_destroy(bspatom_handle h)
     if (!h) return 0;
     cudaSetDevice(h->dev);
     free_batch(h);
+    pool_flush(h);
     if (h->ws.base) cudaFree(h->ws.base);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_counter) cudaFreeHost(h->h_counter);
+    for (auto e : h->chunk_done) cudaEventDestroy(e);
+    if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return 0;
@@ -565,7 +644,7 @@ int bspatom_get_stats(bspatom_handle h, double *out, int nout)
 {
     if (!h) return -1;
     if (!out) return -2;
-    for (int i = 0; i < nout && i < 16; ++i) out[i] = h->stats[i];
+    for (int i = 0; i < nout && i < 24; ++i) out[i] = h->stats[i];
     return 0;
 }
 
@@ -609,7 +688,7 @@ int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs)
             G.k = p.k; G.B = p.k - 1; G.n = p.nfun; G.nkp = p.nkp; G.ka = p.ka;
             G.FS = 2 * G.B + 2;
             G.npad = ((G.n + G.B) / (G.B + 1)) * (G.B + 1);
-            G.nrows = G.npad + G.B + 1;
+            G.nrows = BSP_NROWS(G.npad, G.B);
             G.xrows = G.npad + G.B + 1;
             G.ldw = ((G.n + 31) / 32) * 32;
         } else {
@@ -660,15 +739,63 @@ int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs)
     return 0;
 }
 
-int bspatom_batch_run(bspatom_handle h)
+} /* extern "C" */
+
+namespace {
+
+bool is_pinned(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+/* enqueue on st_copy the D2H of pencils [p0, p0+np) of group G into the caller's E / C */
+int copy_chunk_out(bspatom_handle h, Group &G, int p0, int np, double *E, double *C)
+{
+    int p = p0;
+    while (p < p0 + np) {
+        int q = p;
+        while (q + 1 < p0 + np && G.prob_index[q + 1] == G.prob_index[q] + 1) ++q;
+        const int i0 = G.prob_index[p];
+        const int cnt = q - p + 1;
+        if (E) CU(cudaMemcpyAsync(E + h->e_off[i0], G.d_E + (size_t)p * G.n, sizeof(double) * (size_t)cnt * G.n,
+                                  cudaMemcpyDeviceToHost, h->st_copy));
+        if (C) {
+            const long long nel = (q + 1 < G.npencil ? G.coff[q + 1] : G.c_elems) - G.coff[p];
+            if (nel > 0) CU(cudaMemcpyAsync(C + h->c_off[i0], G.d_C + G.coff[p], sizeof(double) * (size_t)nel,
+                                            cudaMemcpyDeviceToHost, h->st_copy));
+        }
+        p = q + 1;
+    }
+    return 0;
+}
+
+int run_internal(bspatom_handle h, double *E_out, double *C_out);
+
+} // namespace
+
+extern "C" int bspatom_batch_run(bspatom_handle h)
 {
     int rc = check_device(h);
     if (rc) return rc;
+    return run_internal(h, nullptr, nullptr);
+}
+
+namespace {
+
+/* E_out / C_out: pinned host buffers (or NULL).  When given, each chunk's results are copied out on
+ * st_copy as soon as the chunk is final, overlapping the next chunk's kernels. */
+int run_internal(bspatom_handle h, double *E_out, double *C_out)
+{
+    int rc = 0;
     if (!h->uploaded) { h->err = "batch_run before batch_upload"; return BSPATOM_ESTATE; }
+    size_t chunk_no = 0;
     const long long launches0 = h->launches;
     for (int i = 0; i < 4; ++i) { h->k_ms[i] = 0; h->k_cnt[i] = 0; }
     h->ev_used = 0;
-    double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0;
+    double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0, t_gap_pre = 0, t_gap_post = 0;
     int rounds = 0, iters = 0;
     cudaEvent_t e0, e1, e2;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
@@ -698,15 +825,24 @@ int bspatom_batch_run(bspatom_handle h)
         ChunkPtrs c;
         const size_t per_pencil = carve_chunk(G, 1, nullptr, c);
         int chunk = h->opt.chunk;
+        if (chunk <= 0) chunk = G.chunk_cached;
         if (chunk <= 0) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
-            const size_t budget = std::min<size_t>((free_b + h->ws.bytes) / 2, (size_t)64 << 30);
+            const size_t budget = std::min<size_t>((free_b + h->ws.bytes + h->pool_bytes) / 2, (size_t)64 << 30);
             chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil, 1024));
+            G.chunk_cached = chunk;
         }
         chunk = std::min(chunk, G.npencil);
-        {   /* equal chunks: no under-filled tail launch */
-            const int nchunks = (G.npencil + chunk - 1) / chunk;
+        {   /* equal chunks: no under-filled tail launch.  When results stream to the host, use at
+             * least 4 chunks (if each still fills the GPU) so the D2H of one hides behind the next */
+            int nchunks = (G.npencil + chunk - 1) / chunk;
+            if ((E_out || C_out) && h->opt.chunk <= 0) {
+                const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
+                const int min_pencils = std::max(1, (148 * 4 + blocks_per_pencil - 1) / blocks_per_pencil);
+                const int want = std::min(4, std::max(1, G.npencil / min_pencils));
+                nchunks = std::max(nchunks, want);
+            }
             chunk = (G.npencil + nchunks - 1) / nchunks;
         }
         const size_t need = carve_chunk(G, chunk, nullptr, c);
@@ -716,11 +852,36 @@ int bspatom_batch_run(bspatom_handle h)
         for (int p0 = 0; p0 < G.npencil; p0 += chunk) {
             const int np = std::min(chunk, G.npencil - p0);
             BspRunStats st;
+            const bool dbg = getenv("BSPATOM_DEBUG_TIMING") != nullptr;
+            auto hnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            const double th0 = hnow();
             if ((rc = run_chunk(h, G, p0, np, c, st, tm))) return rc;
+            const double th1 = hnow();
+            if (E_out || C_out) {
+                if (chunk_no >= h->chunk_done.size()) {
+                    cudaEvent_t e;
+                    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    h->chunk_done.push_back(e);
+                }
+                CU(cudaEventRecord(h->chunk_done[chunk_no], h->st));
+                CU(cudaStreamWaitEvent(h->st_copy, h->chunk_done[chunk_no], 0));
+                if ((rc = copy_chunk_out(h, G, p0, np, E_out, C_out))) return rc;
+                ++chunk_no;
+            }
+            const double th2 = hnow();
             CU(cudaStreamSynchronize(h->st));
+            const double th3 = hnow();
             timed_collect(h);
+            if (dbg) {
+                float g0 = 0, g1 = 0;
+                cudaEventElapsedTime(&g0, e0, tm.ev[0]);
+                cudaEventElapsedTime(&g1, e0, tm.ev[3]);
+                fprintf(stderr, "[bspatom] chunk p0=%d np=%d host: run_chunk %.2f ms, enqueue copy %.2f ms, sync %.2f ms, collect %.2f ms | gpu: start %.2f end %.2f (ms since run start)\n",
+                        p0, np, th1 - th0, th2 - th1, th3 - th2, hnow() - th3, g0, g1);
+            }
             rounds = std::max(rounds, st.rounds);
             iters = std::max(iters, st.iters);
+            if (p0 == 0) { CU(cudaEventElapsedTime(&ms, e2, tm.ev[0])); t_gap_pre += ms; }
             CU(cudaEventElapsedTime(&ms, tm.ev[0], tm.ev[1])); t_val += ms;
             CU(cudaEventElapsedTime(&ms, tm.ev[1], tm.ev[2])); t_vec += ms;
             CU(cudaEventElapsedTime(&ms, tm.ev[2], tm.ev[3])); t_fin += ms;
@@ -729,8 +890,19 @@ int bspatom_batch_run(bspatom_handle h)
     }
     CU(cudaEventRecord(e1, h->st));
     CU(cudaStreamSynchronize(h->st));
+    {
+        auto t0 = std::chrono::steady_clock::now();
+        if (E_out || C_out) CU(cudaStreamSynchronize(h->st_copy));
+        h->stats[21] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     float total = 0;
     CU(cudaEventElapsedTime(&total, e0, e1));
+    {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, tm.ev[3], e1));
+        t_gap_post = ms;
+    }
+    h->stats[19] = t_gap_pre; h->stats[20] = t_gap_post;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
     h->stats[0] = (double)(h->launches - launches0);
@@ -740,6 +912,10 @@ int bspatom_batch_run(bspatom_handle h)
     h->ran = true;
     return 0;
 }
+
+} // namespace
+
+extern "C" {
 
 int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info)
 {
@@ -781,10 +957,20 @@ int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info)
 
 int bspatom_solve_batch(bspatom_handle h, int nprob, const bsp_problem *probs, double *E, double *C, int *info)
 {
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     int rc = bspatom_batch_upload(h, nprob, probs);
     if (rc) return rc;
-    if ((rc = bspatom_batch_run(h))) return rc;
-    return bspatom_batch_download(h, E, C, info);
+    const double t1 = now();
+    /* pinned (cudaHostAlloc / cudaHostRegister / bspatom_alloc_host) output buffers are filled chunk by
+     * chunk while the next chunk computes; pageable ones after the run */
+    const bool pe = is_pinned(E), pc = is_pinned(C);
+    if ((rc = run_internal(h, pe ? E : nullptr, pc ? C : nullptr))) return rc;
+    const double t2 = now();
+    rc = bspatom_batch_download(h, pe ? nullptr : E, pc ? nullptr : C, info);
+    const double t3 = now();
+    h->stats[16] = t1 - t0; h->stats[17] = t2 - t1; h->stats[18] = t3 - t2;   /* host wall ms: upload, run(+overlapped copies), download */
+    return rc;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -800,12 +986,13 @@ int bspatom_assemble_band(bspatom_handle h, const bsp_problem *p, double *S, dou
     Group G;
     G.k = q.k; G.B = q.k - 1; G.n = q.nfun; G.nkp = q.nkp; G.ka = q.ka; G.FS = 2 * G.B + 2;
     G.npad = ((G.n + G.B) / (G.B + 1)) * (G.B + 1);
-    G.nrows = G.npad + G.B + 1;
+    G.nrows = BSP_NROWS(G.npad, G.B);
     std::vector<const bsp_problem *> insts = {&q};
-    if ((rc = upload_group_instances(h, G, insts))) { free_group(G); return rc; }
+    G.ninst = 1;
+    if ((rc = upload_group_instances(h, G, insts))) { free_group(h, G); return rc; }
     const size_t per_mat = (size_t)G.nrows * G.FS;
     double *d_all = nullptr;
-    if ((rc = dev_alloc(h, &d_all, per_mat * BSP_NMAT))) { free_group(G); return rc; }
+    if ((rc = dev_alloc(h, &d_all, per_mat * BSP_NMAT))) { free_group(h, G); return rc; }
     BspAsmArgs a;
     memset(&a, 0, sizeof a);
     a.n = G.n; a.nkp = G.nkp; a.ka = G.ka; a.nrows = G.nrows; a.ninst = 1; a.want_pi = 1;
@@ -818,8 +1005,8 @@ int bspatom_assemble_band(bspatom_handle h, const bsp_problem *p, double *S, dou
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
         if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = BSPATOM_ECUDA; }
     }
-    cudaFree(d_all);
-    free_group(G);
+    dev_free(h, d_all, per_mat * BSP_NMAT);
+    free_group(h, G);
     if (rc) return rc;
     const int n = q.nfun, kd = q.k - 1, FS = 2 * kd + 2;
     double *sym[7] = {S, H0, Q, T, V, R, Rinv};

@@ -95,7 +95,8 @@ int bspatom_wavefunction(bspatom_handle h, int k, int nfun, int nkp, const doubl
     CU(cudaMemcpyAsync(r_out, d_r, sizeof(double) * ((size_t)npts + 1), cudaMemcpyDeviceToHost, h->st));
     CU(cudaMemcpyAsync(psi_out, d_psi, sizeof(double) * (size_t)(npts + 1) * nvec, cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
-    cudaFree(d_rt); cudaFree(d_C); cudaFree(d_r); cudaFree(d_psi);
+    dev_free(h, d_rt, (size_t)nkp); dev_free(h, d_C, (size_t)nfun * nvec);
+    dev_free(h, d_r, (size_t)npts + 1); dev_free(h, d_psi, (size_t)(npts + 1) * nvec);
     return 0;
 }
 
@@ -141,8 +142,9 @@ int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf
     CU(cudaEventElapsedTime(&ms, e0, e1));
     h->stats[0] = 2; h->stats[7] = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_A); cudaFree(d_Ci); cudaFree(d_Y); cudaFree(d_D);
-    if (!same) cudaFree(d_Cf);
+    dev_free(h, d_A, (size_t)ld * n); dev_free(h, d_Ci, (size_t)n * ni); dev_free(h, d_Y, (size_t)n * ni);
+    dev_free(h, d_D, (size_t)nf * ni);
+    if (!same) dev_free(h, d_Cf, (size_t)n * nf);
     return 0;
 }
 
@@ -194,7 +196,7 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
     Group G;
     G.k = B + 1; G.B = B; G.n = n; G.nkp = n + G.k; G.ka = 1; G.FS = 2 * B + 2;
     G.npad = ((n + B) / (B + 1)) * (B + 1);
-    G.nrows = G.npad + B + 1; G.xrows = G.nrows; G.ldw = ((n + 31) / 32) * 32;
+    G.nrows = BSP_NROWS(G.npad, B); G.xrows = G.npad + B + 1; G.ldw = ((n + 31) / 32) * 32;
     G.ninst = 1; G.npencil = 1;
     G.prob_index = {0}; G.inst = {0}; G.nvec = {wantz ? n : 0}; G.cl = {0.0}; G.coff = {0};
     G.c_elems = wantz ? (long long)n * n : 0;
@@ -227,7 +229,7 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
         if ((rc = dev_alloc(h, &G.d_C, (size_t)G.c_elems))) break;
         if ((rc = dev_alloc(h, &d_L, (size_t)n * (B + 1)))) break;
     } while (0);
-    if (rc) { free_group(G); cudaFree(d_L); *info = -100 - rc; return; }
+    if (rc) { free_group(h, G); dev_free(h, d_L, (size_t)n * (B + 1)); *info = -100 - rc; return; }
     cudaMemcpyAsync(G.d_fbS, fbS.data(), per_mat * sizeof(double), cudaMemcpyHostToDevice, h->st);
     cudaMemcpyAsync(G.d_fbH0, fbH.data(), per_mat * sizeof(double), cudaMemcpyHostToDevice, h->st);
     cudaMemsetAsync(G.d_fbQ, 0, per_mat * sizeof(double), h->st);
@@ -240,8 +242,8 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
     h->launches++;
     int pd = 0;
     cudaMemcpyAsync(&pd, G.d_pdinfo, sizeof(int), cudaMemcpyDeviceToHost, h->st);
-    if (cudaStreamSynchronize(h->st) != cudaSuccess) { free_group(G); cudaFree(d_L); *info = -100 - BSPATOM_ECUDA; return; }
-    if (pd) { free_group(G); cudaFree(d_L); *info = n + pd; return; }
+    if (cudaStreamSynchronize(h->st) != cudaSuccess) { free_group(h, G); dev_free(h, d_L, (size_t)n * (B + 1)); *info = -100 - BSPATOM_ECUDA; return; }
+    if (pd) { free_group(h, G); dev_free(h, d_L, (size_t)n * (B + 1)); *info = n + pd; return; }
     /* run the eigen stages on this explicit pencil */
     h->groups.clear();
     h->groups.push_back(G);
@@ -267,7 +269,7 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
         if (cudaStreamSynchronize(h->st) != cudaSuccess) rc = BSPATOM_ECUDA;
     }
     if (ev_ok) for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
-    cudaFree(d_L);
+    dev_free(h, d_L, (size_t)n * (B + 1));
     if (rc) { fail(rc); return; }
     free_batch(h);
     /* eigenvectors overwrite A; the Cholesky factor overwrites the stored triangle of B */

@@ -46,6 +46,11 @@
 
 #define BSP_EPS 2.220446049250313e-16
 
+/* rows stored per band matrix: the sweeps bring in row j+B+1 at step j and
+ * prefetch one row further, so npad + B + 2 rows exist (padding rows are
+ * decoupled: diag(H) = 1, rest 0) */
+#define BSP_NROWS(npad, B) ((npad) + (B) + 2)
+
 /* refinement status bits */
 #define BSP_ST_CONVERGED 1
 
@@ -53,7 +58,7 @@ struct BspEigChunk {
     /* geometry */
     int n;        /* basis size                                   */
     int npad;     /* n rounded up to a multiple of B+1            */
-    int nrows;    /* rows stored per band matrix = npad + B + 1   */
+    int nrows;    /* rows stored per band matrix = BSP_NROWS      */
     int xrows;    /* rows of X / R workspaces   = npad + B + 1    */
     int ldw;      /* eigen-index stride (n rounded up to 32)      */
     int npencil;  /* pencils in this chunk                        */
@@ -118,6 +123,15 @@ BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restr
             }
         }
     }
+    /* software pipeline: the band row that enters the window at the end of
+     * step j is loaded during step j-1, so its (L1) latency hides behind the
+     * pivot arithmetic instead of stalling the first FMA that needs it */
+    double nh[K1], ns[K1];
+#pragma unroll
+    for (int m = 0; m <= B; ++m) {
+        nh[m] = BSP_LDG(fbH + (size_t)K1 * FS + m);
+        ns[m] = BSP_LDG(fbS + (size_t)K1 * FS + m);
+    }
     for (int j0 = 0; j0 < npad; j0 += K1) {
 #pragma unroll
         for (int t = 0; t < K1; ++t) {
@@ -139,12 +153,17 @@ BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restr
                     w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
                 }
             }
-            /* row j retires; its slot takes row j+B+1 */
-            const double *hrow = fbH + (size_t)(j + K1) * FS;
-            const double *srow = fbS + (size_t)(j + K1) * FS;
+            /* row j retires; its slot takes row j+B+1 (loaded during the previous
+             * step); the registers are refilled at once with row j+B+2 */
+            {
+                const double *hrow = fbH + (size_t)(j + K1 + 1) * FS;
+                const double *srow = fbS + (size_t)(j + K1 + 1) * FS;
 #pragma unroll
-            for (int m = 0; m <= B; ++m) {
-                w[t][(t + 1 + m) % K1] = fma(-sigma, BSP_LDG(srow + m), BSP_LDG(hrow + m));
+                for (int m = 0; m <= B; ++m) {
+                    w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
+                    nh[m] = BSP_LDG(hrow + m);
+                    ns[m] = BSP_LDG(srow + m);
+                }
             }
         }
     }
@@ -338,6 +357,10 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
 
     double w[K1][K1], y[K1];
     int cnt = 0;
+    auto rhs = [&](int row) -> double {
+        if (row >= n) return 0.0;
+        return (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)row) : sc * Rp[(size_t)row * ldw];
+    };
 #pragma unroll
     for (int r = 0; r < K1; ++r) {
 #pragma unroll
@@ -349,14 +372,23 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
                 w[r][c] = 0.0;
             }
         }
-        if (r < n) y[r] = (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)r)
-                                       : sc * Rp[(size_t)r * ldw];
-        else y[r] = 0.0;
+        y[r] = rhs(r);
+    }
+    /* software pipelines: next band row (L1) one step ahead, right-hand side
+     * (HBM) a whole unrolled block (B+1 rows) ahead */
+    double nh[K1], ns[K1], rq[K1];
+#pragma unroll
+    for (int m = 0; m <= B; ++m) {
+        nh[m] = BSP_LDG(fbH + (size_t)K1 * FS + m);
+        ns[m] = BSP_LDG(fbS + (size_t)K1 * FS + m);
+        rq[m] = rhs(K1 + m);
     }
     for (int j0 = 0; j0 < npad; j0 += K1) {
 #pragma unroll
         for (int t = 0; t < K1; ++t) {
             const int j = j0 + t;
+            const double rnew = rq[t];          /* rhs of row j+K1, loaded K1 steps ago */
+            rq[t] = rhs(j + 2 * K1);
             double d = w[t][t];
             if (fabs(d) < pivmin) d = -pivmin;
             if (d < 0.0) ++cnt;
@@ -379,16 +411,17 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
                     w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
                 }
             }
-            const int rn = j + K1;
-            const double *hrow = fbH + (size_t)rn * FS;
-            const double *srow = fbS + (size_t)rn * FS;
+            {
+                const double *hrow = fbH + (size_t)(j + K1 + 1) * FS;
+                const double *srow = fbS + (size_t)(j + K1 + 1) * FS;
 #pragma unroll
-            for (int m = 0; m <= B; ++m) {
-                w[t][(t + 1 + m) % K1] = fma(-sigma, BSP_LDG(srow + m), BSP_LDG(hrow + m));
+                for (int m = 0; m <= B; ++m) {
+                    w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
+                    nh[m] = BSP_LDG(hrow + m);
+                    ns[m] = BSP_LDG(srow + m);
+                }
             }
-            if (rn < n) y[t] = (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)rn)
-                                           : sc * Rp[(size_t)rn * ldw];
-            else y[t] = 0.0;
+            y[t] = rnew;
         }
     }
     /* inertia -> bracket (buffer 0) */
@@ -405,12 +438,17 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
  *               1 -> h - rho' s  (rho' = Rayleigh quotient known at pass start)
  *               0 -> s
  * ------------------------------------------------------------------------- */
+#ifndef BSP_BACK_PF
+#define BSP_BACK_PF 2 /* factor rows in flight per thread in the back sweep */
+#endif
+
 template <int B>
 BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now, int corr_next)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
     constexpr int W = 2 * B + 1;
+    constexpr int PF = BSP_BACK_PF;
     if (e >= g.n) return;
     const size_t id = (size_t)p * g.ldw + e;
     if (g.status[id] & BSP_ST_CONVERGED) return;
@@ -432,42 +470,66 @@ BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now
     for (int i = 0; i < W; ++i) xw[i] = 0.0;
     double xSx = 0.0, xHx = 0.0, resmax = 0.0;
 
-    for (int j = npad - 1; j >= -B; --j) {
-        double xn = 0.0;
-        if (j >= 0) {
-            const double *Lrow = Lp + (size_t)j * K1 * ldw;
-            double yj = Lrow[0];
+    /* ring of PF factor rows (+ x_old) in flight: row j is consumed PF steps
+     * after its loads were issued, which is what hides the HBM latency of
+     * this purely streaming sweep */
+    double Lq[PF][K1], xq[PF];
+    auto fetch = [&](int q, int row) {
+        if (row >= 0) {
+            const double *Lrow = Lp + (size_t)row * K1 * ldw;
 #pragma unroll
-            for (int i = B; i >= 1; --i) yj = fma(-Lrow[(size_t)i * ldw], yw[i - 1], yj);
+            for (int i = 0; i <= B; ++i) Lq[q][i] = Lrow[(size_t)i * ldw];
+            xq[q] = (corr_now && row < n) ? Xp[(size_t)row * ldw] : 0.0;
+        } else {
 #pragma unroll
-            for (int i = B - 1; i >= 1; --i) yw[i] = yw[i - 1];
-            yw[0] = yj;
-            if (j < n) {
-                const double xo = corr_now ? Xp[(size_t)j * ldw] : 0.0;
-                xn = fma(cx, xo, -yj);
-                Xp[(size_t)j * ldw] = xn;
-            }
+            for (int i = 0; i <= B; ++i) Lq[q][i] = 0.0;
+            xq[q] = 0.0;
         }
+    };
 #pragma unroll
-        for (int c = W - 1; c >= 1; --c) xw[c] = xw[c - 1];
-        xw[0] = xn;
-        /* row i = j + B now has its whole stencil x_new[j .. j+2B] */
-        const int i = j + B;
-        if (i < n) {
-            const double *hrow = fbH + (size_t)i * FS;
-            const double *srow = fbS + (size_t)i * FS;
-            double s = 0.0, h = 0.0;
+    for (int q = 0; q < PF; ++q) fetch(q, npad - 1 - q);
+
+    for (int j0 = npad - 1; j0 >= -B; j0 -= PF) {
 #pragma unroll
-            for (int c = 0; c < W; ++c) {
-                s = fma(BSP_LDG(srow + c), xw[c], s);
-                h = fma(BSP_LDG(hrow + c), xw[c], h);
+        for (int q = 0; q < PF; ++q) {
+            const int j = j0 - q;
+            if (j >= -B) {
+                double xn = 0.0;
+                if (j >= 0) {
+                    double yj = Lq[q][0];
+#pragma unroll
+                    for (int i = B; i >= 1; --i) yj = fma(-Lq[q][i], yw[i - 1], yj);
+#pragma unroll
+                    for (int i = B - 1; i >= 1; --i) yw[i] = yw[i - 1];
+                    yw[0] = yj;
+                    if (j < n) {
+                        xn = fma(cx, xq[q], -yj);
+                        Xp[(size_t)j * ldw] = xn;
+                    }
+                }
+                fetch(q, j - PF);   /* slot q is free again: row j-PF goes in flight */
+#pragma unroll
+                for (int c = W - 1; c >= 1; --c) xw[c] = xw[c - 1];
+                xw[0] = xn;
+                /* row i = j + B now has its whole stencil x_new[j .. j+2B] */
+                const int i = j + B;
+                if (i < n) {
+                    const double *hrow = fbH + (size_t)i * FS;
+                    const double *srow = fbS + (size_t)i * FS;
+                    double s = 0.0, h = 0.0;
+#pragma unroll
+                    for (int c = 0; c < W; ++c) {
+                        s = fma(BSP_LDG(srow + c), xw[c], s);
+                        h = fma(BSP_LDG(hrow + c), xw[c], h);
+                    }
+                    const double xi = xw[B];
+                    xSx = fma(xi, s, xSx);
+                    xHx = fma(xi, h, xHx);
+                    const double r = fma(-rho_p, s, h);
+                    resmax = fmax(resmax, fabs(r));
+                    Rp[(size_t)i * ldw] = corr_next ? r : s;
+                }
             }
-            const double xi = xw[B];
-            xSx = fma(xi, s, xSx);
-            xHx = fma(xi, h, xHx);
-            const double r = fma(-rho_p, s, h);
-            resmax = fmax(resmax, fabs(r));
-            Rp[(size_t)i * ldw] = corr_next ? r : s;
         }
     }
     /* bookkeeping + next shift */

@@ -14,11 +14,34 @@
 
 #define BSP_EIG_THREADS 128
 
+/* resident blocks per SM the register allocator is asked to allow, by half bandwidth:
+ * the pivot window is (B+1)(B+2)/2 doubles, so wide bands get fewer blocks instead of spills */
+#ifndef BSP_MINB_ROUND
+#define BSP_MINB_ROUND 4
+#endif
+#ifndef BSP_MINB_FACTOR
+#define BSP_MINB_FACTOR 3
+#endif
+#ifndef BSP_MINB_BACK
+#define BSP_MINB_BACK 4
+#endif
+constexpr int bsp_minb(int base, int B) { return B <= 6 ? base : (B == 7 ? (base > 3 ? 3 : base) : 2); }
+
 template <int B>
 __global__ void __launch_bounds__(BSP_NCAND) bsp_bounds_kernel(BspEigChunk g, double *cand_s, int *cand_c)
 {
     bsp_bounds_candidate<B>(g, blockIdx.x, threadIdx.x, cand_s, cand_c);
 }
+
+/* device counter -> host-mapped word with a plain store: the host polls convergence without a D2H
+ * memcpy, which would queue behind the multi-hundred-MB result copies on the copy engine */
+__global__ void bsp_publish_counter_kernel(const int *ctr, volatile int *host_word)
+{
+    *host_word = *ctr;
+    __threadfence_system();
+}
+
+__global__ void bsp_zero_counter_kernel(int *ctr) { *ctr = 0; }
 
 __global__ void bsp_bounds_pick_kernel(BspEigChunk g, const double *cand_s, const int *cand_c)
 {
@@ -27,7 +50,7 @@ __global__ void bsp_bounds_pick_kernel(BspEigChunk g, const double *cand_s, cons
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS) bsp_round_kernel(BspEigChunk g, int round)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) bsp_round_kernel(BspEigChunk g, int round)
 {
     bsp_multisection_round<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, round);
 }
@@ -38,13 +61,13 @@ __global__ void bsp_prepare_kernel(BspEigChunk g, int buf)
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS) bsp_factor_kernel(BspEigChunk g, int iter)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_kernel(BspEigChunk g, int iter)
 {
     bsp_factor_forward<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter);
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS) bsp_back_kernel(BspEigChunk g, int corr_now, int corr_next)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_back_kernel(BspEigChunk g, int corr_now, int corr_next)
 {
     bsp_back_substitute<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, corr_now, corr_next);
 }

@@ -258,11 +258,12 @@ class BspAtom(BspInputs):
                    "bspatom_set_option")
 
     def stats(self) -> dict:
-        out = (C.c_double * 16)()
-        self.lib.bspatom_get_stats(self._h, out, 16)
+        out = (C.c_double * 24)()
+        self.lib.bspatom_get_stats(self._h, out, 24)
         keys = ["launches", "rounds", "iters", "ms_assembly", "ms_eigenvalues", "ms_eigenvectors", "ms_finalize",
                 "ms_total", "ms_k_round", "ms_k_factor", "ms_k_back", "ms_k_assembly",
-                "n_k_round", "n_k_factor", "n_k_back", "n_k_assembly"]
+                "n_k_round", "n_k_factor", "n_k_back", "n_k_assembly", "wall_ms_upload", "wall_ms_run",
+                "wall_ms_download", "ms_gap_before_chunk", "ms_gap_after_last_chunk", "wall_ms_copy_tail"]
         return dict(zip(keys, list(out)))
 
     # ---- MATRIX_SVT (matrices.f90:1-200) ------------------------------------------------
@@ -302,23 +303,22 @@ class BspAtom(BspInputs):
         """items: iterable of (Problem, l).  Returns (list of E arrays, list of C arrays, info)."""
         items = list(items)
         arr, keep = build_problem_array(items, nvec)
-        n_e = sum(p.nfun for p, _ in items)
-        n_c = sum(int(arr[i].nfun) * int(arr[i].nvec) for i in range(len(items)))
-        E = out_E if out_E is not None else np.empty(n_e)
-        Cbuf = (out_C if out_C is not None else np.empty(n_c)) if want_vectors else None
+        nfs, nvs = arr.rec["nfun"].astype(np.int64), arr.rec["nvec"].astype(np.int64)
+        n_e = int(nfs.sum())
+        n_c = int((nfs * nvs).sum())
+        E = out_E if out_E is not None else pinned_empty(n_e)
+        Cbuf = (out_C if out_C is not None else pinned_empty(n_c)) if want_vectors else None
         info = np.zeros(len(items), dtype=np.int32)
         rc = self.lib.bspatom_solve_batch(self._h, len(items), arr, E.ctypes.data_as(C.c_void_p),
                                           Cbuf.ctypes.data_as(C.c_void_p) if Cbuf is not None else None,
                                           info.ctypes.data_as(C.c_void_p))
         _lib.check(self.lib, self._h, rc, "bspatom_solve_batch")
-        Es, Cs, eo, co = [], [], 0, 0
-        for i, (p, _) in enumerate(items):
-            nv = int(arr[i].nvec)
-            Es.append(E[eo:eo + p.nfun])
-            eo += p.nfun
-            if Cbuf is not None:
-                Cs.append(Cbuf[co:co + p.nfun * nv].reshape((p.nfun, nv), order="F"))
-                co += p.nfun * nv
+        eo = np.concatenate(([0], np.cumsum(nfs)))
+        co = np.concatenate(([0], np.cumsum(nfs * nvs)))
+        Es = [E[eo[i]:eo[i + 1]] for i in range(len(items))]
+        Cs = []
+        if Cbuf is not None:
+            Cs = [Cbuf[co[i]:co[i + 1]].reshape((int(nfs[i]), int(nvs[i])), order="F") for i in range(len(items))]
         return Es, Cs, info
 
     # staged variant: keeps the batch resident in HBM (bench.py times batch_run alone)
@@ -327,7 +327,7 @@ class BspAtom(BspInputs):
         arr, keep = build_problem_array(items, nvec)
         rc = self.lib.bspatom_batch_upload(self._h, len(items), arr)
         _lib.check(self.lib, self._h, rc, "bspatom_batch_upload")
-        self._resident = (items, [int(arr[i].nvec) for i in range(len(items))])
+        self._resident = (items, arr.rec["nvec"].copy())
 
     def batch_run(self):
         _lib.check(self.lib, self._h, self.lib.bspatom_batch_run(self._h), "bspatom_batch_run")
@@ -372,6 +372,22 @@ class BspAtom(BspInputs):
         return D
 
 
+def pinned_empty(count: int) -> np.ndarray:
+    """float64 array in page-locked host memory (bspatom_alloc_host): results written into it by
+    solve_batch stream out chunk by chunk while the GPU keeps computing."""
+    import weakref
+
+    lib = _lib.load()
+    nbytes = max(1, int(count)) * 8
+    ptr = lib.bspatom_alloc_host(nbytes)
+    if not ptr:
+        raise BspAtomError("bspatom_alloc_host(%d bytes) failed" % nbytes)
+    buf = (C.c_double * max(1, int(count))).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64, count=int(count))
+    weakref.finalize(buf, lib.bspatom_free_host, ptr)
+    return arr
+
+
 def _to_c_problem(p: Problem, l: int, nvec: int, keep: list) -> BspProblem:
     cp = BspProblem()
     cp.k, cp.nfun, cp.nkp, cp.ka = int(p.k), int(p.nfun), int(p.nkp), int(p.ka)
@@ -398,22 +414,50 @@ def _to_c_problem(p: Problem, l: int, nvec: int, keep: list) -> BspProblem:
     return cp
 
 
+_PROBLEM_DTYPE = np.dtype({
+    "names": ["k", "nfun", "nkp", "ka", "rt", "xg", "wg", "pot_kind", "pot_par", "v_tab", "l", "ul_extra", "nvec"],
+    "formats": ["<i4", "<i4", "<i4", "<i4", "<u8", "<u8", "<u8", "<i4", ("<f8", 8), "<u8", "<i4", "<f8", "<i4"],
+    "offsets": [BspProblem.k.offset, BspProblem.nfun.offset, BspProblem.nkp.offset, BspProblem.ka.offset,
+                BspProblem.rt.offset, BspProblem.xg.offset, BspProblem.wg.offset, BspProblem.pot_kind.offset,
+                BspProblem.pot_par.offset, BspProblem.v_tab.offset, BspProblem.l.offset,
+                BspProblem.ul_extra.offset, BspProblem.nvec.offset],
+    "itemsize": C.sizeof(BspProblem),
+})
+
+
 def build_problem_array(items: List, nvec: Optional[int]):
+    """(Problem, l) list -> contiguous array of struct bsp_problem (numpy structured array with the
+    C layout; filled per distinct Problem, not per item: a sweep has few instances and many l)."""
     keep: list = []
-    arr = (BspProblem * len(items))()
-    cache = {}
+    n = len(items)
+    rec = np.zeros(n, dtype=_PROBLEM_DTYPE)
+    groups: dict = {}
     for i, (p, l) in enumerate(items):
-        nv = p.nfun if nvec is None else min(int(nvec), p.nfun)
-        key = id(p)
-        if key not in cache:
-            cache[key] = _to_c_problem(p, 0, 0, keep)
-        base = cache[key]
-        C.memmove(C.byref(arr[i]), C.byref(base), C.sizeof(BspProblem))
-        arr[i].l = int(l)
-        arr[i].ul_extra = float(p.bl[l]) if (p.bl is not None and p.pot_kind == POT_SIMONS_FUES) else 0.0
-        arr[i].nvec = nv
-    arr._keep = keep
-    return arr, keep
+        groups.setdefault(id(p), (p, []))[1].append(i)
+    ls = np.fromiter((l for _, l in items), dtype=np.int32, count=n)
+    rec["l"] = ls
+    for p, idx in groups.values():
+        idx = np.asarray(idx)
+        base = np.frombuffer(bytes(_to_c_problem(p, 0, 0, keep)), dtype=_PROBLEM_DTYPE, count=1)[0]
+        for name in ("k", "nfun", "nkp", "ka", "rt", "xg", "wg", "pot_kind", "pot_par", "v_tab"):
+            rec[name][idx] = base[name]
+        rec["nvec"][idx] = p.nfun if nvec is None else min(int(nvec), p.nfun)
+        if p.bl is not None and p.pot_kind == POT_SIMONS_FUES:
+            rec["ul_extra"][idx] = np.asarray(p.bl, dtype=np.float64)[ls[idx]]
+    keep.append(rec)
+    arr = C.cast(rec.ctypes.data, C.POINTER(BspProblem))
+    return _ProblemArray(arr, rec), keep
+
+
+class _ProblemArray:
+    """pointer to struct bsp_problem[] + the numpy record array that owns the memory"""
+
+    def __init__(self, ptr, rec):
+        self._as_parameter_ = ptr
+        self.rec = rec
+
+    def __getitem__(self, i):
+        return self._as_parameter_[i]
 
 
 def dsygv(H: np.ndarray, S: np.ndarray, jobz: str = "V", uplo: str = "U"):

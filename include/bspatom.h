@@ -25,6 +25,8 @@
 #ifndef BSPATOM_H
 #define BSPATOM_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -75,6 +77,12 @@ int bspatom_create(bspatom_handle *h, int device_id);
 int bspatom_destroy(bspatom_handle h);
 const char *bspatom_last_error(bspatom_handle h);
 int bspatom_version(void);
+
+/* page-locked host memory for E / C: bspatom_solve_batch copies finished chunks into pinned
+ * buffers while the next chunk is still computing (pageable buffers are filled after the run).
+ * A Fortran host maps the pointer with C_F_POINTER.  NULL on failure.                      */
+void *bspatom_alloc_host(size_t bytes);
+void bspatom_free_host(void *p);
 
 /* tunables: name in {"tau","max_rounds","max_iters","chunk","res_tol","polish"} */
 int bspatom_set_option(bspatom_handle h, const char *name, double value);

@@ -1,0 +1,8 @@
+for F in "" ""; do
+python bench.py --steps 4 --warmup 3 --no-cpu-baseline $F > gpurun_out/d2.json 2> gpurun_out/d2.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/d2.json"))
+print("flags '$F' value", round(d["value"]), "ms/step", round(d["ms_per_step"],1), "e2e", d["e2e"] and (round(d["e2e"]["value"]), round(d["e2e"]["ms_per_step"],1), d["e2e"]["wall_ms_last_step"]))
+PY
+done

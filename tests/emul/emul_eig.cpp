@@ -55,7 +55,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     memset(&g, 0, sizeof(g));
     g.n = n;
     g.npad = ((n + K1 - 1) / K1) * K1;
-    g.nrows = g.npad + B + 1;
+    g.nrows = BSP_NROWS(g.npad, B);
     g.xrows = g.npad + B + 1;
     g.ldw = ((n + 31) / 32) * 32;
     g.npencil = npencil;
@@ -115,7 +115,7 @@ extern "C" int emul_solve(int n, int B, int npencil, const double *hb, const dou
 template <int B> static int cnt(int n, const double *hb, const double *sb, double sigma)
 {
     constexpr int K1 = B + 1, FS = 2 * B + 2;
-    int npad = ((n + K1 - 1) / K1) * K1, nrows = npad + B + 1;
+    int npad = ((n + K1 - 1) / K1) * K1, nrows = BSP_NROWS(npad, B);
     std::vector<double> H((size_t)nrows * FS, 0.0), S((size_t)nrows * FS, 0.0);
     for (int i = 0; i < n; ++i)
         for (int d = 0; d <= B; ++d) {
