@@ -15,7 +15,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <mutex>
+#include <thread>
 #include <map>
 #include <string>
 #include <vector>
@@ -40,8 +43,10 @@ struct Options {
     int max_rounds = 90;
     int min_iters = 3;
     int max_iters = 12;
-    int first_check_round = 6;
+    int first_check_round = 14;
+    int check_every = 3;
     int chunk = 0; /* 0 = auto */
+    int workers = 2; /* concurrent chunk streams (1 or 2) */
 };
 
 struct Group {
@@ -92,6 +97,11 @@ struct bspatom_handle_s {
     int *h_counter_dev = nullptr; /* device view of h_counter */
     double stats[24] = {0};
     long long launches = 0;
+    /* second chunk stream: an auxiliary context (own stream, workspace, polling word, event pool)
+     * driven by a helper thread, so two chunks are in flight and the GPU back-fills the tail
+     * waves / polling bubbles of one with blocks of the other */
+    bspatom_handle_s *aux = nullptr;
+    std::mutex mu;
     /* per-kernel-class device timing (CUDA events on the launching stream) */
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_class; /* class of the pair starting at 2*i */
@@ -462,7 +472,7 @@ int run_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, 
     } ex;
     ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.tm = &tm;
     CU(cudaEventRecord(tm.ev[0], h->st));
-    BspSchedule sch = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters, h->opt.first_check_round};
+    BspSchedule sch = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters, h->opt.first_check_round, h->opt.check_every};
     st = bsp_run_chunk(ex, sch);
     if (ex.first_err != cudaSuccess) {
         h->err = std::string("eigen stage: ") + cudaGetErrorString(ex.first_err);
@@ -502,15 +512,16 @@ int run_chunk(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, Bs
     }
 }
 
-int ensure_workspace(bspatom_handle h, size_t bytes)
+int ensure_workspace(bspatom_handle h, size_t bytes, bspatom_handle pool_owner = nullptr)
 {
+    if (!pool_owner) pool_owner = h;
     if (h->ws.bytes >= bytes) return 0;
     if (h->ws.base) cudaFree(h->ws.base);
     h->ws.base = nullptr;
     h->ws.bytes = 0;
     if (cudaMalloc((void **)&h->ws.base, bytes) != cudaSuccess) {
         cudaGetLastError();
-        pool_flush(h);
+        pool_flush(pool_owner);
         CU(cudaMalloc((void **)&h->ws.base, bytes));
     }
     h->ws.bytes = bytes;
@@ -557,6 +568,36 @@ int upload_group_instances(bspatom_handle h, Group &G, const std::vector<const b
     return 0;
 }
 
+bspatom_handle new_context(int device_id)
+{
+    bspatom_handle h = new bspatom_handle_s();
+    h->dev = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->h_counter, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&h->h_counter_dev, h->h_counter, 0) != cudaSuccess) {
+        cudaGetLastError();
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void free_context(bspatom_handle h)
+{
+    if (!h) return;
+    if (h->aux) free_context(h->aux);
+    free_batch(h);
+    pool_flush(h);
+    if (h->ws.base) cudaFree(h->ws.base);
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    if (h->h_counter) cudaFreeHost(h->h_counter);
+    for (auto e : h->chunk_done) cudaEventDestroy(e);
+    if (h->st_copy) cudaStreamDestroy(h->st_copy);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
 int check_device(bspatom_handle h)
 {
     if (!h) return -1;
@@ -591,15 +632,8 @@ int bspatom_create(bspatom_handle *out, int device_id)
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return BSPATOM_ENODEVICE;
     if (device_id < 0 || device_id >= ndev) return -2;
-    bspatom_handle h = new bspatom_handle_s();
-    h->dev = device_id;
-    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaHostAlloc((void **)&h->h_counter, 64, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostGetDevicePointer((void **)&h->h_counter_dev, h->h_counter, 0) != cudaSuccess) {
-        delete h;
-        return BSPATOM_ECUDA;
-    }
+    bspatom_handle h = new_context(device_id);
+    if (!h) return BSPATOM_ECUDA;
     *out = h;
     return 0;
 }
@@ -608,15 +642,7 @@ int bspatom_destroy(bspatom_handle h)
 {
     if (!h) return 0;
     cudaSetDevice(h->dev);
-    free_batch(h);
-    pool_flush(h);
-    if (h->ws.base) cudaFree(h->ws.base);
-    for (auto e : h->ev_pool) cudaEventDestroy(e);
-    if (h->h_counter) cudaFreeHost(h->h_counter);
-    for (auto e : h->chunk_done) cudaEventDestroy(e);
-    if (h->st_copy) cudaStreamDestroy(h->st_copy);
-    if (h->st) cudaStreamDestroy(h->st);
-    delete h;
+    free_context(h);
     return 0;
 }
 
@@ -635,7 +661,9 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "min_iters") h->opt.min_iters = std::max(3, (int)v);
     else if (s == "max_iters") h->opt.max_iters = std::max(3, (int)v);
     else if (s == "first_check_round") h->opt.first_check_round = std::max(1, (int)v);
+    else if (s == "check_every") h->opt.check_every = std::max(1, (int)v);
     else if (s == "chunk") h->opt.chunk = (int)v;
+    else if (s == "workers") h->opt.workers = std::min(2, std::max(1, (int)v));
     else return -2;
     return 0;
 }
@@ -785,22 +813,80 @@ extern "C" int bspatom_batch_run(bspatom_handle h)
 
 namespace {
 
+/* per-worker accumulators of one run */
+struct WorkerAcc {
+    double t_val = 0, t_vec = 0, t_fin = 0;
+    int rounds = 0, iters = 0, rc = 0;
+};
+
+/* one worker = one context (stream, workspace, polling word): pulls chunks off the queue */
+void chunk_worker(bspatom_handle main_h, bspatom_handle hw, Group *G, int chunk, std::atomic<int> *next,
+                  int nchunks, double *E_out, double *C_out, cudaEvent_t asm_done, WorkerAcc *acc)
+{
+    bspatom_handle h = hw; /* CU() reports into the worker's own context */
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(h->dev));
+        CU(cudaStreamWaitEvent(h->st, asm_done, 0));
+        ChunkPtrs c;
+        carve_chunk(*G, chunk, h->ws.base, c);
+        ChunkTimes tm;
+        for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tm.ev[i]));
+        int rc = 0;
+        for (;;) {
+            const int ci = next->fetch_add(1);
+            if (ci >= nchunks) break;
+            const int p0 = ci * chunk;
+            const int np = std::min(chunk, G->npencil - p0);
+            BspRunStats st;
+            if ((rc = run_chunk(h, *G, p0, np, c, st, tm))) break;
+            if (E_out || C_out) {
+                std::lock_guard<std::mutex> lk(main_h->mu);
+                cudaEvent_t e;
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { rc = BSPATOM_ECUDA; break; }
+                main_h->chunk_done.push_back(e);
+                cudaEventRecord(e, h->st);
+                cudaStreamWaitEvent(main_h->st_copy, e, 0);
+                bspatom_handle hm = main_h;
+                {
+                    bspatom_handle h = hm; /* copies are enqueued on the main context's copy stream */
+                    rc = copy_chunk_out(h, *G, p0, np, E_out, C_out);
+                }
+                if (rc) break;
+            }
+            CU(cudaStreamSynchronize(h->st));
+            timed_collect(h);
+            float ms = 0;
+            acc->rounds = std::max(acc->rounds, st.rounds);
+            acc->iters = std::max(acc->iters, st.iters);
+            CU(cudaEventElapsedTime(&ms, tm.ev[0], tm.ev[1])); acc->t_val += ms;
+            CU(cudaEventElapsedTime(&ms, tm.ev[1], tm.ev[2])); acc->t_vec += ms;
+            CU(cudaEventElapsedTime(&ms, tm.ev[2], tm.ev[3])); acc->t_fin += ms;
+        }
+        cudaStreamSynchronize(h->st);
+        for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
+        return rc;
+    };
+    acc->rc = body();
+}
+
 /* E_out / C_out: pinned host buffers (or NULL).  When given, each chunk's results are copied out on
- * st_copy as soon as the chunk is final, overlapping the next chunk's kernels. */
+ * st_copy as soon as the chunk is final, overlapping the kernels of the chunks still in flight.
+ * Chunks are pulled by up to two workers (contexts with their own stream and workspace) so that two
+ * chunks execute concurrently. */
 int run_internal(bspatom_handle h, double *E_out, double *C_out)
 {
     int rc = 0;
     if (!h->uploaded) { h->err = "batch_run before batch_upload"; return BSPATOM_ESTATE; }
-    size_t chunk_no = 0;
-    const long long launches0 = h->launches;
+    const long long launches0 = h->launches + (h->aux ? h->aux->launches : 0);
     for (int i = 0; i < 4; ++i) { h->k_ms[i] = 0; h->k_cnt[i] = 0; }
     h->ev_used = 0;
-    double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0, t_gap_pre = 0, t_gap_post = 0;
+    if (h->aux) { for (int i = 0; i < 4; ++i) { h->aux->k_ms[i] = 0; h->aux->k_cnt[i] = 0; } h->aux->ev_used = 0; }
+    for (auto e : h->chunk_done) cudaEventDestroy(e);
+    h->chunk_done.clear();
+    double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0;
     int rounds = 0, iters = 0;
     cudaEvent_t e0, e1, e2;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
-    ChunkTimes tm;
-    for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tm.ev[i]));
     CU(cudaEventRecord(e0, h->st));
     for (auto &G : h->groups) {
         /* ---- assembly, once per instance ---- */
@@ -821,74 +907,63 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         CU(cudaGetLastError());
         CU(cudaMemsetAsync(G.d_bad, 0, sizeof(int) * G.npencil, h->st));
         CU(cudaEventRecord(e2, h->st));
-        /* ---- eigen stages, chunk by chunk ---- */
+        /* ---- eigen stages: chunk queue ---- */
         ChunkPtrs c;
         const size_t per_pencil = carve_chunk(G, 1, nullptr, c);
+        const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
+        const int fill_pencils = std::max(1, (148 * 4 + blocks_per_pencil - 1) / blocks_per_pencil); /* one full wave */
+        int workers = (h->opt.workers >= 2 && G.npencil >= 2 * fill_pencils) ? 2 : 1;
         int chunk = h->opt.chunk;
         if (chunk <= 0) chunk = G.chunk_cached;
         if (chunk <= 0) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
-            const size_t budget = std::min<size_t>((free_b + h->ws.bytes + h->pool_bytes) / 2, (size_t)64 << 30);
-            chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil, 1024));
+            const size_t have = h->ws.bytes + h->pool_bytes + (h->aux ? h->aux->ws.bytes : 0);
+            const size_t budget = std::min<size_t>((free_b + have) / 2, (size_t)64 << 30);
+            chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil / workers, 1024));
             G.chunk_cached = chunk;
         }
         chunk = std::min(chunk, G.npencil);
-        {   /* equal chunks: no under-filled tail launch.  When results stream to the host, use at
-             * least 4 chunks (if each still fills the GPU) so the D2H of one hides behind the next */
-            int nchunks = (G.npencil + chunk - 1) / chunk;
-            if ((E_out || C_out) && h->opt.chunk <= 0) {
-                const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
-                const int min_pencils = std::max(1, (148 * 4 + blocks_per_pencil - 1) / blocks_per_pencil);
-                const int want = std::min(4, std::max(1, G.npencil / min_pencils));
-                nchunks = std::max(nchunks, want);
-            }
-            chunk = (G.npencil + nchunks - 1) / nchunks;
+        int nchunks = (G.npencil + chunk - 1) / chunk;
+        if (h->opt.chunk <= 0) {
+            /* equal chunks; one per worker, and at least 4 when results stream to the host (if each
+             * still fills the GPU) so that the D2H of a finished chunk hides behind the others */
+            int want = workers;
+            if (E_out || C_out) want = std::max(want, std::min(4 * workers, std::max(1, (2 * G.npencil) / fill_pencils)));
+            nchunks = std::max(nchunks, want);
         }
+        chunk = (G.npencil + nchunks - 1) / nchunks;
+        nchunks = (G.npencil + chunk - 1) / chunk;
+        workers = std::min(workers, nchunks);
         const size_t need = carve_chunk(G, chunk, nullptr, c);
         if ((rc = ensure_workspace(h, need))) return rc;
-        carve_chunk(G, chunk, h->ws.base, c);
-        float ms = 0;
-        for (int p0 = 0; p0 < G.npencil; p0 += chunk) {
-            const int np = std::min(chunk, G.npencil - p0);
-            BspRunStats st;
-            const bool dbg = getenv("BSPATOM_DEBUG_TIMING") != nullptr;
-            auto hnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-            const double th0 = hnow();
-            if ((rc = run_chunk(h, G, p0, np, c, st, tm))) return rc;
-            const double th1 = hnow();
-            if (E_out || C_out) {
-                if (chunk_no >= h->chunk_done.size()) {
-                    cudaEvent_t e;
-                    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                    h->chunk_done.push_back(e);
-                }
-                CU(cudaEventRecord(h->chunk_done[chunk_no], h->st));
-                CU(cudaStreamWaitEvent(h->st_copy, h->chunk_done[chunk_no], 0));
-                if ((rc = copy_chunk_out(h, G, p0, np, E_out, C_out))) return rc;
-                ++chunk_no;
+        if (workers == 2) {
+            if (!h->aux) {
+                h->aux = new_context(h->dev);
+                if (!h->aux) { h->err = "cannot create the second chunk stream"; return BSPATOM_ECUDA; }
             }
-            const double th2 = hnow();
-            CU(cudaStreamSynchronize(h->st));
-            const double th3 = hnow();
-            timed_collect(h);
-            if (dbg) {
-                float g0 = 0, g1 = 0;
-                cudaEventElapsedTime(&g0, e0, tm.ev[0]);
-                cudaEventElapsedTime(&g1, e0, tm.ev[3]);
-                fprintf(stderr, "[bspatom] chunk p0=%d np=%d host: run_chunk %.2f ms, enqueue copy %.2f ms, sync %.2f ms, collect %.2f ms | gpu: start %.2f end %.2f (ms since run start)\n",
-                        p0, np, th1 - th0, th2 - th1, th3 - th2, hnow() - th3, g0, g1);
-            }
-            rounds = std::max(rounds, st.rounds);
-            iters = std::max(iters, st.iters);
-            if (p0 == 0) { CU(cudaEventElapsedTime(&ms, e2, tm.ev[0])); t_gap_pre += ms; }
-            CU(cudaEventElapsedTime(&ms, tm.ev[0], tm.ev[1])); t_val += ms;
-            CU(cudaEventElapsedTime(&ms, tm.ev[1], tm.ev[2])); t_vec += ms;
-            CU(cudaEventElapsedTime(&ms, tm.ev[2], tm.ev[3])); t_fin += ms;
+            h->aux->opt = h->opt;
+            if ((rc = ensure_workspace(h->aux, need, h))) { h->err = h->aux->err; return rc; }
         }
+        std::atomic<int> next(0);
+        WorkerAcc acc[2];
+        if (workers == 2) {
+            std::thread th(chunk_worker, h, h->aux, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[1]);
+            chunk_worker(h, h, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[0]);
+            th.join();
+            CU(cudaSetDevice(h->dev));
+        } else {
+            chunk_worker(h, h, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[0]);
+        }
+        for (int w = 0; w < workers; ++w) {
+            if (acc[w].rc) { if (w == 1) h->err = h->aux->err; return acc[w].rc; }
+            t_val += acc[w].t_val; t_vec += acc[w].t_vec; t_fin += acc[w].t_fin;
+            rounds = std::max(rounds, acc[w].rounds); iters = std::max(iters, acc[w].iters);
+        }
+        float ms = 0;
         CU(cudaEventElapsedTime(&ms, e1, e2)); t_asm += ms;
     }
-    CU(cudaEventRecord(e1, h->st));
+    CU(cudaEventRecord(e1, h->st));   /* every chunk stream has been drained by its worker */
     CU(cudaStreamSynchronize(h->st));
     {
         auto t0 = std::chrono::steady_clock::now();
@@ -897,18 +972,16 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     }
     float total = 0;
     CU(cudaEventElapsedTime(&total, e0, e1));
-    {
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, tm.ev[3], e1));
-        t_gap_post = ms;
-    }
-    h->stats[19] = t_gap_pre; h->stats[20] = t_gap_post;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
-    h->stats[0] = (double)(h->launches - launches0);
+    h->stats[0] = (double)(h->launches + (h->aux ? h->aux->launches : 0) - launches0);
     h->stats[1] = rounds; h->stats[2] = iters;
+    /* stage times are summed over the chunk streams: with two workers they overlap in wall time */
     h->stats[3] = t_asm; h->stats[4] = t_val; h->stats[5] = t_vec; h->stats[6] = t_fin; h->stats[7] = total;
-    for (int i = 0; i < 4; ++i) { h->stats[8 + i] = h->k_ms[i]; h->stats[12 + i] = (double)h->k_cnt[i]; }
+    for (int i = 0; i < 4; ++i) {
+        h->stats[8 + i] = h->k_ms[i] + (h->aux ? h->aux->k_ms[i] : 0.0);
+        h->stats[12 + i] = (double)(h->k_cnt[i] + (h->aux ? h->aux->k_cnt[i] : 0));
+    }
+    h->stats[19] = 0; h->stats[20] = 0;
     h->ran = true;
     return 0;
 }

@@ -21,6 +21,8 @@ struct BspSchedule {
     int min_iters;   /* refinement iterations always done (>= 3)      */
     int max_iters;   /* cap                                           */
     int first_check_round; /* first round after which the host polls  */
+    int check_every;       /* ... and then every so many rounds (finished
+                              brackets make a surplus round nearly free) */
 };
 
 struct BspRunStats {
@@ -40,7 +42,8 @@ inline BspRunStats bsp_run_chunk(Exec &ex, const BspSchedule &sch)
         ex.zero_counter(0);
         ex.round(r);
         ++r;
-        if (r >= sch.first_check_round || r >= sch.max_rounds) {
+        const int ce = sch.check_every > 0 ? sch.check_every : 1;
+        if ((r >= sch.first_check_round && (r - sch.first_check_round) % ce == 0) || r >= sch.max_rounds) {
             st.brackets_open = ex.read_counter(0);
             if (st.brackets_open == 0 || r >= sch.max_rounds) break;
         }

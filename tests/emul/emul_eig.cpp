@@ -85,7 +85,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     g.res = res.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
     g.counters = counters.data(); g.tau = tau; g.delta_rel = delta_rel; g.conv_tol = conv_tol;
     EmulExec<B> ex; ex.g = g;
-    BspSchedule sch = {max_rounds, min_iters, max_iters, 4};
+    BspSchedule sch = {max_rounds, min_iters, max_iters, 4, 1};
     BspRunStats st = bsp_run_chunk(ex, sch);
     std::vector<double> fac(per);
     std::vector<int> bad(npencil, 0);
