@@ -271,8 +271,11 @@ def main():
             e2e_step()
         barrier()
         t0 = time.perf_counter()
+        e2e_steps = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             inf = e2e_step()
+            e2e_steps.append(round(1e3 * (time.perf_counter() - ts), 2))
         barrier()
         e2e_s = time.perf_counter() - t0
         tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -280,7 +283,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": total_solves / float(tt[0]), "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(tt[0]) / args.steps,
-               "bad_info": int(np.count_nonzero(inf)),
+               "bad_info": int(np.count_nonzero(inf)), "ms_each_step": e2e_steps,
                "wall_ms_last_step": {k_: atom.stats()[k_] for k_ in ("wall_ms_upload", "wall_ms_run", "wall_ms_download", "wall_ms_copy_tail", "ms_total")}}
         del C_host
 

@@ -36,15 +36,15 @@
 namespace {
 
 struct Options {
-    double tau = 1e-3;
+    double tau = 1e-4;
     double delta_rel = 1e-4;
     double conv_tol = 1e-11;
     double res_tol = 1e-9;
     int max_rounds = 90;
     int min_iters = 3;
     int max_iters = 12;
-    int first_check_round = 14;
-    int check_every = 3;
+    int first_check_round = 10;
+    int check_every = 2;
     int chunk = 0; /* 0 = auto */
     int workers = 2; /* concurrent chunk streams (1 or 2) */
 };
@@ -388,6 +388,7 @@ struct GpuExec {
          * that is busy streaming results to the host */
         bsp_zero_counter_kernel<<<1, 1, 0, h->st>>>(g.counters + w);
         note();
+        if (w == 0) { bsp_zero_counter_kernel<<<1, 1, 0, h->st>>>(g.counters + 2); note(); }
     }
     int read_counter(int w) {
         bsp_publish_counter_kernel<<<1, 1, 0, h->st>>>(g.counters + w, h->h_counter_dev);
@@ -395,6 +396,7 @@ struct GpuExec {
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
         if (e != cudaSuccess) { if (first_err == cudaSuccess) first_err = e; return 0; }
+        if (getenv("BSPATOM_DEBUG_COUNTERS")) fprintf(stderr, "[bspatom] counter %d = %d\n", w, *h->h_counter);
         return *h->h_counter;
     }
 };
@@ -417,7 +419,8 @@ struct Carver {
 
 struct ChunkPtrs {
     double *fbH, *pbound, *lo, *hi, *samp_s, *gap, *sigma, *rho, *rho_prev, *scale, *res, *L, *X, *R, *cand_s, *fac;
-    int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c;
+    double *samp_fm, *flm, *fhm, *beta;
+    int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c, *samp_fe, *fle, *fhe, *side;
 };
 
 size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
@@ -429,6 +432,9 @@ size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
     c.lo = cv.take<double>(2 * per); c.hi = cv.take<double>(2 * per);
     c.clo = cv.take<int>(2 * per); c.chi = cv.take<int>(2 * per);
     c.samp_s = cv.take<double>(2 * per); c.samp_c = cv.take<int>(2 * per);
+    c.samp_fm = cv.take<double>(2 * per); c.samp_fe = cv.take<int>(2 * per);
+    c.flm = cv.take<double>(per); c.fhm = cv.take<double>(per); c.beta = cv.take<double>(per);
+    c.fle = cv.take<int>(per); c.fhe = cv.take<int>(per); c.side = cv.take<int>(per);
     c.gap = cv.take<double>(per); c.done = cv.take<int>(per);
     c.sigma = cv.take<double>(per); c.rho = cv.take<double>(per); c.rho_prev = cv.take<double>(per);
     c.scale = cv.take<double>(per); c.res = cv.take<double>(per); c.status = cv.take<int>(per);
@@ -457,6 +463,7 @@ int run_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, 
     g.fbH = c.fbH; g.fbS = G.d_fbS; g.inst = G.d_inst + p0; g.nvec = G.d_nvec + p0;
     g.pbound = c.pbound; g.lo = c.lo; g.hi = c.hi; g.clo = c.clo; g.chi = c.chi;
     g.samp_s = c.samp_s; g.samp_c = c.samp_c; g.gap = c.gap; g.done = c.done;
+    g.samp_fm = c.samp_fm; g.samp_fe = c.samp_fe; g.flm = c.flm; g.fhm = c.fhm; g.fle = c.fle; g.fhe = c.fhe; g.side = c.side; g.beta = c.beta;
     g.sigma = c.sigma; g.rho = c.rho; g.rho_prev = c.rho_prev; g.scale = c.scale; g.res = c.res;
     g.status = c.status; g.L = c.L; g.X = c.X; g.R = c.R; g.counters = c.counters;
     g.tau = h->opt.tau; g.delta_rel = h->opt.delta_rel; g.conv_tol = h->opt.conv_tol;
@@ -472,7 +479,9 @@ int run_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, 
     } ex;
     ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.tm = &tm;
     CU(cudaEventRecord(tm.ev[0], h->st));
-    BspSchedule sch = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters, h->opt.first_check_round, h->opt.check_every};
+    /* a few stragglers per hundred thousand eigenpairs are cheaper to finish inside the refinement */
+    const int open_ok = (int)((long long)np * G.n / 20000);
+    BspSchedule sch = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters, h->opt.first_check_round, h->opt.check_every, open_ok};
     st = bsp_run_chunk(ex, sch);
     if (ex.first_err != cudaSuccess) {
         h->err = std::string("eigen stage: ") + cudaGetErrorString(ex.first_err);
@@ -701,6 +710,7 @@ int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs)
     std::map<std::vector<int>, int> gid;
     std::vector<std::vector<const bsp_problem *>> ginsts;
     std::vector<std::multimap<uint64_t, int>> ghash;
+    std::multimap<uint64_t, int> quick;
     for (int i = 0; i < nprob; ++i) {
         const bsp_problem &p = probs[i];
         std::vector<int> key = {p.k, p.nfun, p.nkp, p.ka};
@@ -723,15 +733,34 @@ int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs)
             gi = it->second;
         }
         Group &G = h->groups[gi];
-        const uint64_t hv = instance_hash(p);
+        /* level 1: same pointers and parameters as an earlier problem (all l of one potential) */
+        uint64_t qk = 1469598103934665603ull;
+        qk = hash_bytes(&p.rt, sizeof p.rt, qk);
+        qk = hash_bytes(&p.xg, sizeof p.xg, qk);
+        qk = hash_bytes(&p.v_tab, sizeof p.v_tab, qk);
+        qk = hash_bytes(&p.pot_kind, sizeof p.pot_kind, qk);
+        qk = hash_bytes(p.pot_par, sizeof p.pot_par, qk);
+        qk = hash_bytes(&gi, sizeof gi, qk);
         int inst = -1;
-        auto range = ghash[gi].equal_range(hv);
-        for (auto r = range.first; r != range.second; ++r)
-            if (same_instance(*ginsts[gi][r->second], p)) { inst = r->second; break; }
-        if (inst < 0) {
-            inst = (int)ginsts[gi].size();
-            ginsts[gi].push_back(&p);
-            ghash[gi].insert({hv, inst});
+        {
+            auto range = quick.equal_range(qk);
+            for (auto r = range.first; r != range.second; ++r) {
+                const bsp_problem &o = *ginsts[gi][r->second];
+                if (o.rt == p.rt && o.xg == p.xg && o.wg == p.wg && o.v_tab == p.v_tab && o.pot_kind == p.pot_kind &&
+                    memcmp(o.pot_par, p.pot_par, sizeof p.pot_par) == 0) { inst = r->second; break; }
+            }
+        }
+        if (inst < 0) {   /* level 2: equal contents behind different pointers */
+            const uint64_t hv = instance_hash(p);
+            auto range = ghash[gi].equal_range(hv);
+            for (auto r = range.first; r != range.second; ++r)
+                if (same_instance(*ginsts[gi][r->second], p)) { inst = r->second; break; }
+            if (inst < 0) {
+                inst = (int)ginsts[gi].size();
+                ginsts[gi].push_back(&p);
+                ghash[gi].insert({hv, inst});
+            }
+            quick.insert({qk, inst});
         }
         G.prob_index.push_back(i);
         G.inst.push_back(inst);
@@ -812,6 +841,30 @@ extern "C" int bspatom_batch_run(bspatom_handle h)
 }
 
 namespace {
+
+template <int B>
+int launch_pdcheck_b(bspatom_handle h, Group &G)
+{
+    bsp_pdcheck_fast_kernel<B><<<(G.ninst + 31) / 32, 32, 0, h->st>>>(G.d_fbS, G.n, G.npad, G.nrows, G.ninst, G.d_pdinfo);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_pdcheck(bspatom_handle h, Group &G)
+{
+    switch (G.B) {
+    case 2: return launch_pdcheck_b<2>(h, G);
+    case 3: return launch_pdcheck_b<3>(h, G);
+    case 4: return launch_pdcheck_b<4>(h, G);
+    case 5: return launch_pdcheck_b<5>(h, G);
+    case 6: return launch_pdcheck_b<6>(h, G);
+    case 7: return launch_pdcheck_b<7>(h, G);
+    case 8: return launch_pdcheck_b<8>(h, G);
+    case 9: return launch_pdcheck_b<9>(h, G);
+    default: return BSPATOM_EUNSUPPORTED;
+    }
+}
 
 /* per-worker accumulators of one run */
 struct WorkerAcc {
@@ -902,9 +955,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             timed_end(h, s);
             if (rc) return rc;
         }
-        bsp_pdcheck_kernel<<<(G.ninst + 31) / 32, 32, 0, h->st>>>(G.d_fbS, G.n, G.nrows, G.B, G.ninst, G.d_pdinfo, nullptr);
-        h->launches++;
-        CU(cudaGetLastError());
+        if ((rc = launch_pdcheck(h, G))) return rc;
         CU(cudaMemsetAsync(G.d_bad, 0, sizeof(int) * G.npencil, h->st));
         CU(cudaEventRecord(e2, h->st));
         /* ---- eigen stages: chunk queue ---- */

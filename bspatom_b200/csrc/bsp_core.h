@@ -29,6 +29,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define BSP_HD __host__ __device__ __forceinline__
@@ -53,6 +54,7 @@
 
 /* refinement status bits */
 #define BSP_ST_CONVERGED 1
+#define BSP_F_UNKNOWN (-2000000000)
 
 struct BspEigChunk {
     /* geometry */
@@ -73,6 +75,13 @@ struct BspEigChunk {
     int *clo, *chi;
     double *samp_s; /* [2][npencil][ldw] published samples        */
     int *samp_c;
+    double *samp_fm; /* [2][npencil][ldw] det(H - s S) of the sample: */
+    int *samp_fe;    /*   mantissa in +-[0.5,1) and binary exponent   */
+    /* private per eigen index [npencil][ldw]: det at the bracket ends
+     * (exponent BSP_F_UNKNOWN = not evaluated) and the Illinois side flag */
+    double *flm, *fhm;
+    int *fle, *fhe, *side;
+    double *beta; /* bracket width at the previous sample (stall detection) */
     double *gap;    /* [npencil][ldw] lower bound of the gap      */
     int *done;      /* [npencil][ldw]                             */
     /* refinement state [npencil][ldw] */
@@ -103,14 +112,36 @@ BSP_HD double bsp_hash_uniform(uint32_t a, uint32_t b, uint32_t c)
  * Sturm count: number of negative pivots of LDL^T(H - sigma S) over rows
  * 0..npad-1.  first_neg (optional) receives the first row with a pivot <= 0.
  * ------------------------------------------------------------------------- */
+BSP_HD void bsp_renorm(double &m, int &e)
+{
+    /* m <- m / 2^k with |m| in [0.5, 1), e += k  (m finite, non-zero, normal) */
+#if defined(__CUDA_ARCH__)
+    long long b = __double_as_longlong(m);
+#else
+    long long b;
+    memcpy(&b, &m, sizeof b);
+#endif
+    const int ex = (int)((b >> 52) & 0x7ff) - 1022;
+    b = (b & (long long)0x800fffffffffffffULL) | (long long)0x3fe0000000000000ULL;
+#if defined(__CUDA_ARCH__)
+    m = __longlong_as_double(b);
+#else
+    memcpy(&m, &b, sizeof b);
+#endif
+    e += ex;
+}
+
 template <int B>
 BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restrict__ fbS, int npad,
-                           double sigma, double pivmin, int *first_neg)
+                           double sigma, double pivmin, int *first_neg, double *det_m = nullptr,
+                           int *det_e = nullptr)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
     double w[K1][K1];
     int cnt = 0, first = -1;
+    double fm = 0.5; /* det(H - sigma S) = prod of pivots = fm * 2^fe */
+    int fe = 1;
 #pragma unroll
     for (int r = 0; r < K1; ++r) {
 #pragma unroll
@@ -139,6 +170,8 @@ BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restr
             double d = w[t][t];
             if (fabs(d) < pivmin) d = -pivmin;
             if (d < 0.0) { ++cnt; if (first < 0) first = j; }
+            fm *= d;
+            bsp_renorm(fm, fe);
             const double rinv = BSP_RCP(d);
             double col[K1], l[K1];
 #pragma unroll
@@ -168,6 +201,7 @@ BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restr
         }
     }
     if (first_neg) *first_neg = first;
+    if (det_m) { *det_m = fm; *det_e = fe; }
     return cnt;
 }
 
@@ -221,8 +255,16 @@ BSP_HD void bsp_bounds_pick(const BspEigChunk &g, int p, const double *cand_s, c
 }
 
 /* ------------------------------------------------------------------------- *
- * one multisection round for eigen index e of pencil p.
+ * one bracketing round for eigen index e of pencil p.
  * reads bracket buffer (round&1), writes buffer ((round+1)&1).
+ *
+ * While a bracket holds m > 1 eigenvalues its owners split it evenly
+ * (multisection).  Once it isolates eigenvalue e (m == 1) and det(H - sigma S)
+ * is known at both ends (the product of the pivots comes for free with the
+ * count), the sample is the regula-falsi point of the determinant, pushed to
+ * twice its distance from the nearer end when it hugs that end: pairs of
+ * rounds then square the bracket width (order ~1.41 per round) instead of one
+ * bit per round.  The inertia of every sample keeps the bracket rigorous.
  * ------------------------------------------------------------------------- */
 template <int B>
 BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round)
@@ -233,20 +275,22 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
     const size_t per = (size_t)g.npencil * g.ldw;
     const size_t id = (size_t)p * g.ldw + e;
     const size_t rd = (size_t)(round & 1) * per, wr = (size_t)((round + 1) & 1) * per;
-    double lo, hi;
-    int clo, chi;
+    double lo, hi, flm = 0.0, fhm = 0.0, beta = 0.0;
+    int clo, chi, fle = BSP_F_UNKNOWN, fhe = BSP_F_UNKNOWN, side = 0; /* side: 1 = last sample was an interpolated one */
     if (round == 0) {
         lo = g.pbound[p * 4 + 0]; hi = g.pbound[p * 4 + 1]; clo = 0; chi = n;
         if (lo > hi) { const double t_ = lo; lo = hi; hi = t_; } /* unbracketed: flagged in finalize */
     } else {
         lo = g.lo[rd + id]; hi = g.hi[rd + id]; clo = g.clo[rd + id]; chi = g.chi[rd + id];
+        flm = g.flm[id]; fle = g.fle[id]; fhm = g.fhm[id]; fhe = g.fhe[id]; side = g.side[id]; beta = g.beta[id];
     }
     int was_done = (round == 0) ? 0 : g.done[id];
     if (round > 0 && !was_done) {
         /* tighten with the samples every eigen index of this pencil published
          * last round: s is non-decreasing in the index, c = nu(s) monotone */
-        const double *S = g.samp_s + (size_t)((round - 1) & 1) * per + (size_t)p * g.ldw;
-        const int *Cc = g.samp_c + (size_t)((round - 1) & 1) * per + (size_t)p * g.ldw;
+        const size_t so = (size_t)((round - 1) & 1) * per + (size_t)p * g.ldw;
+        const double *S = g.samp_s + so;
+        const int *Cc = g.samp_c + so;
         int a = -1, b = n;
         while (b - a > 1) {
             const int mid = (a + b) >> 1;
@@ -254,11 +298,11 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
         }
         if (a >= 0) {
             const double s = S[a];
-            if (s > lo && s < hi) { lo = s; clo = Cc[a]; }
+            if (s > lo && s < hi) { lo = s; clo = Cc[a]; flm = g.samp_fm[so + a]; fle = g.samp_fe[so + a]; }
         }
         if (b < n) {
             const double s = S[b];
-            if (s < hi && s > lo) { hi = s; chi = Cc[b]; }
+            if (s < hi && s > lo) { hi = s; chi = Cc[b]; fhm = g.samp_fm[so + b]; fhe = g.samp_fe[so + b]; }
         }
     }
     /* gap to the neighbours' brackets (theirs as of last round: still valid) */
@@ -277,8 +321,8 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
         if (wdt <= 4.0 * BSP_EPS * amax + 1e-300) done = 1;
         else if (e < g.nvec[p] && gp > 0.0 && wdt <= g.tau * gp) done = 1;
     }
-    double s = lo;
-    int c = clo;
+    double s = lo, sfm = flm;
+    int c = clo, sfe = fle;
     if (!done) {
         int m = chi - clo, rk = e - clo;
         if (m < 1) m = 1;
@@ -286,27 +330,93 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
         if (rk > m - 1) rk = m - 1;
         double frac = ((double)rk + 0.5) / (double)m;
         if (round == 0) frac = frac * frac; /* box states: E_i ~ i^2 */
+        bool secant = false;
+        /* beta holds the bracket width at the previous interpolated sample: if that sample did not at
+         * least halve the bracket, this round bisects (Brent-style safeguard against creeping) */
+        const bool stalled = (side == 1) && (wdt > 0.5 * beta);
+        if (m == 1 && round > 0 && !stalled && fle != BSP_F_UNKNOWN && fhe != BSP_F_UNKNOWN &&
+            ((flm < 0.0) != (fhm < 0.0))) {
+            /* det(H - sigma S) = prod_k (lambda_k - sigma) varies over the bracket like
+             * (lambda_e - sigma) * exp(beta sigma), beta = sum_{k != e} 1/(sigma - lambda_k) (hundreds of
+             * clustered levels make |beta| w >> 1).  Deflate that factor with the other brackets'
+             * current midpoints (Maehly deflation; float reciprocals are plenty for a slope). */
+            double bsum = 0.0;
+            {
+                const double mid = 0.5 * (lo + hi);
+                const double *Lo = g.lo + rd + (size_t)p * g.ldw, *Hi = g.hi + rd + (size_t)p * g.ldw;
+                float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f; /* independent chains: loads overlap */
+                int k = 0;
+                for (; k + 4 <= n; k += 4) {
+                    const float d0 = (float)(mid - 0.5 * (Lo[k] + Hi[k]));
+                    const float d1 = (float)(mid - 0.5 * (Lo[k + 1] + Hi[k + 1]));
+                    const float d2 = (float)(mid - 0.5 * (Lo[k + 2] + Hi[k + 2]));
+                    const float d3 = (float)(mid - 0.5 * (Lo[k + 3] + Hi[k + 3]));
+                    b0 += (k != e && d0 != 0.0f) ? 1.0f / d0 : 0.0f;
+                    b1 += (k + 1 != e && d1 != 0.0f) ? 1.0f / d1 : 0.0f;
+                    b2 += (k + 2 != e && d2 != 0.0f) ? 1.0f / d2 : 0.0f;
+                    b3 += (k + 3 != e && d3 != 0.0f) ? 1.0f / d3 : 0.0f;
+                }
+                for (; k < n; ++k) {
+                    const float dk = (float)(mid - 0.5 * (Lo[k] + Hi[k]));
+                    b0 += (k != e && dk != 0.0f) ? 1.0f / dk : 0.0f;
+                }
+                bsum = (double)b0 + (double)b1 + (double)b2 + (double)b3;
+            }
+            /* regula falsi on the deflated determinant: root at lo + w / (1 + r),
+             * r = |f(hi)/f(lo)| exp(-beta w) */
+            const double shift = -bsum * wdt * 1.4426950408889634; /* in powers of two */
+            double de = (double)(fhe - fle) + shift;
+            de = de > 1000.0 ? 1000.0 : (de < -1000.0 ? -1000.0 : de);
+            const double dei = floor(de);
+            const double r = ldexp(fabs(fhm / flm) * exp2(de - dei), (int)dei);
+            const double t = 1.0 / (1.0 + r);
+            /* the estimate sits at fraction t; when it hugs one end, sample at twice its distance
+             * from that end: the root then (almost surely) lies between the end and the sample and
+             * the bracket collapses to ~2x the interpolation error instead of creeping one-sidedly */
+            if (t > 0.0 && t < 1.0) {
+                frac = t < 0.25 ? 2.0 * t : (t > 0.75 ? 1.0 - 2.0 * (1.0 - t) : t);
+                secant = true;
+            }
+        }
         s = lo + wdt * frac;
+        if (!(s > lo && s < hi)) { s = lo + 0.5 * wdt; secant = false; }
+        side = secant ? 1 : 0;
+        beta = wdt;
         if (!(s > lo && s < hi)) {
             done = 1; s = lo; c = clo;
         } else {
             const double *fbH = g.fbH + (size_t)p * g.nrows * FS;
             const double *fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
             const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(s) * g.pbound[p * 4 + 3]);
-            c = bsp_sturm_count<B>(fbH, fbS, g.npad, s, pivmin, nullptr);
-            if (c <= e) { lo = s; clo = c; } else { hi = s; chi = c; }
+            c = bsp_sturm_count<B>(fbH, fbS, g.npad, s, pivmin, nullptr, &sfm, &sfe);
+            if (c <= e) {
+                lo = s; clo = c; flm = sfm; fle = sfe;
+            } else {
+                hi = s; chi = c; fhm = sfm; fhe = sfe;
+            }
         }
     }
+#if defined(BSP_TRACE) && !defined(__CUDA_ARCH__)
+    if (round >= BSP_TRACE && !done) printf("r%d e%d lo=%.17g hi=%.17g w=%.3e gp=%.3e clo=%d chi=%d fl=(%g,%d) fh=(%g,%d) s=%.17g c=%d\n", round, e, lo, hi, hi-lo, gp, clo, chi, flm, fle, fhm, fhe, s, c);
+#endif
     g.lo[wr + id] = lo; g.hi[wr + id] = hi; g.clo[wr + id] = clo; g.chi[wr + id] = chi;
-    g.samp_s[(size_t)(round & 1) * per + id] = s;
-    g.samp_c[(size_t)(round & 1) * per + id] = c;
+    g.flm[id] = flm; g.fle[id] = fle; g.fhm[id] = fhm; g.fhe[id] = fhe; g.side[id] = side; g.beta[id] = beta;
+    const size_t po = (size_t)(round & 1) * per + id;
+    g.samp_s[po] = s;
+    g.samp_c[po] = c;
+    g.samp_fm[po] = sfm;
+    g.samp_fe[po] = sfe;
     g.gap[id] = gp;
     g.done[id] = done;
     if (!done) {
+        /* counters[0]: brackets still open; counters[2]: open AND not yet isolating one eigenvalue */
+        const int crowded = (chi - clo != 1 || !(gp > 0.0)) ? 1 : 0;
 #if defined(__CUDA_ARCH__)
         atomicAdd(g.counters + 0, 1);
+        if (crowded) atomicAdd(g.counters + 2, 1);
 #else
         g.counters[0] += 1;
+        g.counters[2] += crowded;
 #endif
     }
 }

@@ -10,8 +10,8 @@
  *   void factor(int iter);                 // F pass
  *   void back(int corr_now, int corr_next);// B pass
  *   void check(int allow);                 // convergence marks
- *   void zero_counter(int which);
- *   int  read_counter(int which);          // blocking read
+ *   void zero_counter(int which);          // which: 0 open brackets (also clears 2), 1 unconverged
+ *   int  read_counter(int which);          // blocking read; 2 = open brackets that do not isolate yet
  */
 #ifndef BSP_DRIVER_H
 #define BSP_DRIVER_H
@@ -23,6 +23,9 @@ struct BspSchedule {
     int first_check_round; /* first round after which the host polls  */
     int check_every;       /* ... and then every so many rounds (finished
                               brackets make a surplus round nearly free) */
+    int open_ok;           /* hand over with this many brackets still open, provided each
+                              isolates its eigenvalue: the refinement keeps bracketing
+                              with the inertia of its own factorisations */
 };
 
 struct BspRunStats {
@@ -46,6 +49,7 @@ inline BspRunStats bsp_run_chunk(Exec &ex, const BspSchedule &sch)
         if ((r >= sch.first_check_round && (r - sch.first_check_round) % ce == 0) || r >= sch.max_rounds) {
             st.brackets_open = ex.read_counter(0);
             if (st.brackets_open == 0 || r >= sch.max_rounds) break;
+            if (st.brackets_open <= sch.open_ok && ex.read_counter(2) == 0) break;
         }
     }
     st.rounds = r;

@@ -117,6 +117,19 @@ __global__ void bsp_combine_kernel(double *fbH, const double *fbH0, const double
     fbH[(size_t)p * per_mat + i] = fma(cl[p], fbQ[src], fbH0[src]);
 }
 
+/* S positive definite?  one thread per instance walks the LDL^T pivots of S with the register-window
+ * recurrence of the Sturm count (H := S, sigma = 0).  pd_info as below. */
+template <int B>
+__global__ void bsp_pdcheck_fast_kernel(const double *fbS, int n, int npad, int nrows, int ninst, int *pd_info)
+{
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= ninst) return;
+    const double *S = fbS + (size_t)inst * nrows * (2 * B + 2);
+    int first = -1;
+    bsp_sturm_count<B>(S, S, npad, 0.0, 1e-300, &first);
+    pd_info[inst] = (first >= 0 && first < n) ? first + 1 : 0;
+}
+
 /* S positive definite?  one thread per instance: banded Cholesky pivots.
  * pd_info[inst] = 0 or the 1-based index of the first non-positive pivot
  * (LAPACK dpotrf numbering; DSYGV reports N + that, matrices.f90:250). */

@@ -41,7 +41,7 @@ struct EmulExec {
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_check_converged(g, p, e, allow);
     }
-    void zero_counter(int w) { g.counters[w] = 0; }
+    void zero_counter(int w) { g.counters[w] = 0; if (w == 0) g.counters[2] = 0; }
     int read_counter(int w) { return g.counters[w]; }
 };
 
@@ -76,16 +76,20 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     std::vector<double> pbound(npencil * 4), lo(2 * per), hi(2 * per), samp_s(2 * per), gap(per), sigma(per),
         rho(per), rho_prev(per), scale(per), res(per);
     std::vector<int> clo(2 * per), chi(2 * per), samp_c(2 * per), done(per), status(per), counters(4);
+    std::vector<double> samp_fm(2 * per), flm(per), fhm(per), beta(per);
+    std::vector<int> samp_fe(2 * per), fle(per), fhe(per), side(per);
     std::vector<double> L((size_t)npencil * g.npad * K1 * g.ldw), X((size_t)npencil * g.xrows * g.ldw, 0.0),
         R((size_t)npencil * g.xrows * g.ldw, 0.0);
     g.fbH = fbH.data(); g.fbS = fbS.data(); g.inst = inst.data(); g.nvec = nvec.data();
     g.pbound = pbound.data(); g.lo = lo.data(); g.hi = hi.data(); g.clo = clo.data(); g.chi = chi.data();
     g.samp_s = samp_s.data(); g.samp_c = samp_c.data(); g.gap = gap.data(); g.done = done.data();
+    g.samp_fm = samp_fm.data(); g.samp_fe = samp_fe.data(); g.flm = flm.data(); g.fhm = fhm.data();
+    g.fle = fle.data(); g.fhe = fhe.data(); g.side = side.data(); g.beta = beta.data();
     g.sigma = sigma.data(); g.rho = rho.data(); g.rho_prev = rho_prev.data(); g.scale = scale.data();
     g.res = res.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
     g.counters = counters.data(); g.tau = tau; g.delta_rel = delta_rel; g.conv_tol = conv_tol;
     EmulExec<B> ex; ex.g = g;
-    BspSchedule sch = {max_rounds, min_iters, max_iters, 4, 1};
+    BspSchedule sch = {max_rounds, min_iters, max_iters, 4, 1, 0};
     BspRunStats st = bsp_run_chunk(ex, sch);
     std::vector<double> fac(per);
     std::vector<int> bad(npencil, 0);
