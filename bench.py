@@ -307,48 +307,72 @@ def main():
                "tolerance": "max(1e-12|E|, 1e-10, 32 eps |E_max|)", "l_checked": ls, "info_nonzero": int(np.count_nonzero(info))}
 
     # ---------------- roofline of the dominant kernel ----------------
+    # The value above runs two chunk streams concurrently, so a kernel's event-bracketed duration there
+    # contains time shared with the other stream.  For the roofline the same batch is run `steps` more
+    # times on ONE stream (every kernel alone on the GPU) and each launch is bracketed by CUDA events on
+    # that stream (bspatom_get_stats out[8..15]).
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    peak_src = "measured copy bandwidth (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    atom.set_option("workers", 1)
+    atom.batch_upload(items)
+    atom.batch_run()
+    k1ms, k1cnt, one_ms, it1 = np.zeros(4), np.zeros(4), 0.0, 0
+    for _ in range(args.steps):
+        atom.batch_run()
+        s1 = atom.stats()
+        k1ms += [s1["ms_k_round"], s1["ms_k_factor"], s1["ms_k_back"], s1["ms_k_assembly"]]
+        k1cnt += [s1["n_k_round"], s1["n_k_factor"], s1["n_k_back"], s1["n_k_assembly"]]
+        one_ms += s1["ms_total"]
+        it1 = int(s1["iters"])
+    if args.workers:
+        atom.set_option("workers", args.workers)
     B = K - 1
     npad = ((NFUN + B) // (B + 1)) * (B + 1)
-    per_pair = {   # algorithmic bytes per (pencil, eigenpair) and launch, DESIGN.md "Kernels"
+    per_pair = {   # algorithmic bytes per (pencil, eigenpair) and launch, DESIGN.md section 6
         "bsp_factor_kernel": 8 * (npad * (B + 1) + NFUN),                 # write (zd,l_1..l_B) rows, read rhs
-        "bsp_back_kernel": 8 * (npad * (B + 1) + 3 * NFUN),               # read factors, x_old; write x, rhs
-        "bsp_round_kernel": 8 * 4,                                         # bracket state only: compute bound
+        "bsp_back_kernel": 8 * (npad * (B + 1) + 3 * NFUN),               # read factors + x_old; write x, rhs
     }
     names = ["bsp_round_kernel", "bsp_factor_kernel", "bsp_back_kernel", "bsp_assemble_kernel"]
-    share = kms / max(dev_ms, 1e-9)
-    dom = int(np.argmax(kms[:3]))
+    share = k1ms / max(one_ms, 1e-9)
+    dom = 1 + int(np.argmax(k1ms[1:3]))          # the HBM-bound sweep with the larger share
     dom_name = names[dom]
-    roofline = None
-    if kcnt[dom] > 0:
-        avg_ms = kms[dom] / kcnt[dom]
-        chunk_pencils = nsolve * args.steps * (kcnt[dom] and 1)  # every launch of a class covers one chunk
-        launches_per_step = kcnt[dom] / args.steps
-        # units per launch: pencils of one chunk * N eigenpairs; chunks per step = n_k_round / rounds
-        chunks_per_step = max(1.0, (kcnt[0] / args.steps) / max(1.0, last_stats["rounds"]))
-        pairs_per_launch = nsolve / chunks_per_step * NFUN
-        if dom_name == "bsp_round_kernel":
-            flops_per_pair = npad * (2 * (B * (B + 1) // 2) + 2 * (B + 1) + B + 10)   # FMA=2 flops, rcp ~ 10
-            ach = pairs_per_launch * flops_per_pair / (avg_ms * 1e-3) / 1e12
-            roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": 37.0, "unit": "TFLOP/s",
-                        "frac": ach / 37.0, "traffic": None,
-                        "note": "FP64 FMA-pipe bound serial recurrence; peak = nominal B200 FP64 (not in "
-                                "MEASURED_PEAKS.json); share of step %.2f" % share[dom]}
-        else:
-            ach = pairs_per_launch * per_pair[dom_name] / (avg_ms * 1e-3) / 1e9
-            roofline = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                        "avg_launch_ms": avg_ms, "launches_per_step": launches_per_step,
-                        "share_of_step": float(share[dom])}
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "roofline_r1.json")))
+    except Exception:
+        pass
+    launches = k1cnt[dom] / args.steps
+    avg_ms = k1ms[dom] / max(k1cnt[dom], 1)
+    full_launches = min(launches, it1) if it1 else launches   # launches after the scheduled ones only touch stragglers
+    bytes_per_launch = nsolve * NFUN * per_pair[dom_name]
+    ach = bytes_per_launch * full_launches / (k1ms[dom] / args.steps * 1e-3) / 1e9
+    traffic = None
+    nk = ncu.get(dom_name)
+    if nk:
+        traffic = nk["dram_bytes"] * (nsolve / nk["pencils_per_launch"])
+    roofline = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                "launches_per_step": launches, "share_of_step": float(share[dom]),
+                "how": "single chunk stream, %d pencils per launch, CUDA events around every launch; traffic = "
+                       "dram__bytes_read+write of one `ncu --set full` launch of %s pencils scaled to %d"
+                       % (nsolve, nk["pencils_per_launch"] if nk else "n/a", nsolve),
+                "other_kernels": {
+                    "bsp_factor_kernel" if dom == 2 else "bsp_back_kernel": {
+                        "achieved_GBs": nsolve * NFUN * per_pair[names[3 - dom]] * full_launches
+                        / (k1ms[3 - dom] / args.steps * 1e-3) / 1e9, "share_of_step": float(share[3 - dom])},
+                    "bsp_round_kernel": {"share_of_step": float(share[0]), "bound": "fp64 pipe (serial pivot recurrence), "
+                                         "sm__pipe_fp64_cycles_active 40 % in profiles/"}},
+                "single_stream_ms_per_step": one_ms / args.steps}
     b_alg = 8 * ((NFUN + K) + 4 * K * NFUN + NFUN + NFUN * NFUN)       # 8.24 MB per solve
     step_roof = {"bytes_per_solve": b_alg, "achieved_gbs": value / world * b_alg / 1e9,
-                 "frac_of_hbm": value / world * b_alg / 1e9 / hbm_peak}
+                 "frac_of_hbm": value / world * b_alg / 1e9 / hbm_peak,
+                 "note": "SURVEY 8(d) whole-solve figure; the sweeps move ~2x57 MB of factor per pencil and iteration"}
 
     if rank == 0:
         line = {
@@ -368,7 +392,7 @@ def main():
             "step_roofline": step_roof,
             "cpu_baseline": cpu_baseline,
             "accuracy": acc,
-            "kernel_ms_per_step": {n_: float(m_) / args.steps for n_, m_ in zip(names, kms)},
+            "kernel_ms_per_step_single_stream": {n_: float(m_) / args.steps for n_, m_ in zip(names, k1ms)},
             "stage_ms_per_step": dict(zip(("assembly", "eigenvalues", "eigenvectors", "finalize"),
                                           (stage_ms / args.steps).tolist())),
             "rounds": int(last_stats["rounds"]), "iters": int(last_stats["iters"]),

@@ -46,7 +46,7 @@ struct Options {
     int first_check_round = 10;
     int check_every = 2;
     int chunk = 0; /* 0 = auto */
-    int workers = 2; /* concurrent chunk streams (1 or 2) */
+    int workers = 2; /* concurrent chunk streams (1..4) */
 };
 
 struct Group {
@@ -100,7 +100,7 @@ struct bspatom_handle_s {
     /* second chunk stream: an auxiliary context (own stream, workspace, polling word, event pool)
      * driven by a helper thread, so two chunks are in flight and the GPU back-fills the tail
      * waves / polling bubbles of one with blocks of the other */
-    bspatom_handle_s *aux = nullptr;
+    std::vector<bspatom_handle_s *> aux; /* helper contexts 1..workers-1 */
     std::mutex mu;
     /* per-kernel-class device timing (CUDA events on the launching stream) */
     std::vector<cudaEvent_t> ev_pool;
@@ -595,7 +595,7 @@ bspatom_handle new_context(int device_id)
 void free_context(bspatom_handle h)
 {
     if (!h) return;
-    if (h->aux) free_context(h->aux);
+    for (auto x : h->aux) free_context(x);
     free_batch(h);
     pool_flush(h);
     if (h->ws.base) cudaFree(h->ws.base);
@@ -672,7 +672,7 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "first_check_round") h->opt.first_check_round = std::max(1, (int)v);
     else if (s == "check_every") h->opt.check_every = std::max(1, (int)v);
     else if (s == "chunk") h->opt.chunk = (int)v;
-    else if (s == "workers") h->opt.workers = std::min(2, std::max(1, (int)v));
+    else if (s == "workers") h->opt.workers = std::min(4, std::max(1, (int)v));
     else return -2;
     return 0;
 }
@@ -930,10 +930,11 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
 {
     int rc = 0;
     if (!h->uploaded) { h->err = "batch_run before batch_upload"; return BSPATOM_ESTATE; }
-    const long long launches0 = h->launches + (h->aux ? h->aux->launches : 0);
+    auto aux_launches = [&] { long long s = 0; for (auto x : h->aux) s += x->launches; return s; };
+    const long long launches0 = h->launches + aux_launches();
     for (int i = 0; i < 4; ++i) { h->k_ms[i] = 0; h->k_cnt[i] = 0; }
     h->ev_used = 0;
-    if (h->aux) { for (int i = 0; i < 4; ++i) { h->aux->k_ms[i] = 0; h->aux->k_cnt[i] = 0; } h->aux->ev_used = 0; }
+    for (auto x : h->aux) { for (int i = 0; i < 4; ++i) { x->k_ms[i] = 0; x->k_cnt[i] = 0; } x->ev_used = 0; }
     for (auto e : h->chunk_done) cudaEventDestroy(e);
     h->chunk_done.clear();
     double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0;
@@ -963,13 +964,14 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         const size_t per_pencil = carve_chunk(G, 1, nullptr, c);
         const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
         const int fill_pencils = std::max(1, (148 * 4 + blocks_per_pencil - 1) / blocks_per_pencil); /* one full wave */
-        int workers = (h->opt.workers >= 2 && G.npencil >= 2 * fill_pencils) ? 2 : 1;
+        int workers = std::max(1, std::min(h->opt.workers, G.npencil / fill_pencils));
         int chunk = h->opt.chunk;
         if (chunk <= 0) chunk = G.chunk_cached;
         if (chunk <= 0) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
-            const size_t have = h->ws.bytes + h->pool_bytes + (h->aux ? h->aux->ws.bytes : 0);
+            size_t have = h->ws.bytes + h->pool_bytes;
+            for (auto x : h->aux) have += x->ws.bytes;
             const size_t budget = std::min<size_t>((free_b + have) / 2, (size_t)64 << 30);
             chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil / workers, 1024));
             G.chunk_cached = chunk;
@@ -980,7 +982,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             /* equal chunks; one per worker, and at least 4 when results stream to the host (if each
              * still fills the GPU) so that the D2H of a finished chunk hides behind the others */
             int want = workers;
-            if (E_out || C_out) want = std::max(want, std::min(4 * workers, std::max(1, (2 * G.npencil) / fill_pencils)));
+            if (E_out || C_out) want = std::max(want, std::min(8, std::max(1, (2 * G.npencil) / fill_pencils)));
             nchunks = std::max(nchunks, want);
         }
         chunk = (G.npencil + nchunks - 1) / nchunks;
@@ -988,26 +990,27 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         workers = std::min(workers, nchunks);
         const size_t need = carve_chunk(G, chunk, nullptr, c);
         if ((rc = ensure_workspace(h, need))) return rc;
-        if (workers == 2) {
-            if (!h->aux) {
-                h->aux = new_context(h->dev);
-                if (!h->aux) { h->err = "cannot create the second chunk stream"; return BSPATOM_ECUDA; }
-            }
-            h->aux->opt = h->opt;
-            if ((rc = ensure_workspace(h->aux, need, h))) { h->err = h->aux->err; return rc; }
+        while ((int)h->aux.size() < workers - 1) {
+            bspatom_handle x = new_context(h->dev);
+            if (!x) { h->err = "cannot create a helper chunk stream"; return BSPATOM_ECUDA; }
+            h->aux.push_back(x);
+        }
+        for (int w = 1; w < workers; ++w) {
+            h->aux[w - 1]->opt = h->opt;
+            if ((rc = ensure_workspace(h->aux[w - 1], need, h))) { h->err = h->aux[w - 1]->err; return rc; }
         }
         std::atomic<int> next(0);
-        WorkerAcc acc[2];
-        if (workers == 2) {
-            std::thread th(chunk_worker, h, h->aux, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[1]);
+        WorkerAcc acc[4];
+        {
+            std::vector<std::thread> th;
+            for (int w = 1; w < workers; ++w)
+                th.emplace_back(chunk_worker, h, h->aux[w - 1], &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[w]);
             chunk_worker(h, h, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[0]);
-            th.join();
+            for (auto &t : th) t.join();
             CU(cudaSetDevice(h->dev));
-        } else {
-            chunk_worker(h, h, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[0]);
         }
         for (int w = 0; w < workers; ++w) {
-            if (acc[w].rc) { if (w == 1) h->err = h->aux->err; return acc[w].rc; }
+            if (acc[w].rc) { if (w >= 1) h->err = h->aux[w - 1]->err; return acc[w].rc; }
             t_val += acc[w].t_val; t_vec += acc[w].t_vec; t_fin += acc[w].t_fin;
             rounds = std::max(rounds, acc[w].rounds); iters = std::max(iters, acc[w].iters);
         }
@@ -1024,13 +1027,14 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     float total = 0;
     CU(cudaEventElapsedTime(&total, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-    h->stats[0] = (double)(h->launches + (h->aux ? h->aux->launches : 0) - launches0);
+    h->stats[0] = (double)(h->launches + aux_launches() - launches0);
     h->stats[1] = rounds; h->stats[2] = iters;
     /* stage times are summed over the chunk streams: with two workers they overlap in wall time */
     h->stats[3] = t_asm; h->stats[4] = t_val; h->stats[5] = t_vec; h->stats[6] = t_fin; h->stats[7] = total;
     for (int i = 0; i < 4; ++i) {
-        h->stats[8 + i] = h->k_ms[i] + (h->aux ? h->aux->k_ms[i] : 0.0);
-        h->stats[12 + i] = (double)(h->k_cnt[i] + (h->aux ? h->aux->k_cnt[i] : 0));
+        h->stats[8 + i] = h->k_ms[i];
+        h->stats[12 + i] = (double)h->k_cnt[i];
+        for (auto x : h->aux) { h->stats[8 + i] += x->k_ms[i]; h->stats[12 + i] += (double)x->k_cnt[i]; }
     }
     h->stats[19] = 0; h->stats[20] = 0;
     h->ran = true;

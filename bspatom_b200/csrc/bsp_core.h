@@ -467,9 +467,12 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
 
     double w[K1][K1], y[K1];
     int cnt = 0;
+    /* raw right-hand side (unscaled): the multiply by `sc` happens when the value is consumed, so
+     * that the load issued a whole block ahead has nothing waiting on it */
+    const double scr = (iter == 0) ? 1.0 : sc;
     auto rhs = [&](int row) -> double {
         if (row >= n) return 0.0;
-        return (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)row) : sc * Rp[(size_t)row * ldw];
+        return (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)row) : Rp[(size_t)row * ldw];
     };
 #pragma unroll
     for (int r = 0; r < K1; ++r) {
@@ -482,7 +485,7 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
                 w[r][c] = 0.0;
             }
         }
-        y[r] = rhs(r);
+        y[r] = scr * rhs(r);
     }
     /* software pipelines: next band row (L1) one step ahead, right-hand side
      * (HBM) a whole unrolled block (B+1 rows) ahead */
@@ -497,7 +500,7 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
 #pragma unroll
         for (int t = 0; t < K1; ++t) {
             const int j = j0 + t;
-            const double rnew = rq[t];          /* rhs of row j+K1, loaded K1 steps ago */
+            const double rnew = scr * rq[t];    /* rhs of row j+K1, loaded K1 steps ago */
             rq[t] = rhs(j + 2 * K1);
             double d = w[t][t];
             if (fabs(d) < pivmin) d = -pivmin;
@@ -557,7 +560,6 @@ BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
-    constexpr int W = 2 * B + 1;
     constexpr int PF = BSP_BACK_PF;
     if (e >= g.n) return;
     const size_t id = (size_t)p * g.ldw + e;
@@ -572,17 +574,20 @@ BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now
     const double rho_p = g.rho[id]; /* rho' */
     const double cx = corr_now ? sc : 0.0;
 
-    double yw[B > 0 ? B : 1];  /* y_{j+1..j+B} */
-    double xw[W];              /* x_new[j .. j+2B] */
+    /* windows over rows j .. j+B (index 0 = row j after the shift of step j):
+     *   yw : solution of L^T y = zd         xv : x_new
+     *   hs, ss : partial sums of (H x_new)_i and (S x_new)_i.
+     * Column sweep: when x_new[j] appears, column j of the (symmetric) band adds A(i,j) x_j to the
+     * rows i = j+1..j+B and row j collects its upper part sum_d A(j,j+d) x_{j+d}; row i is complete
+     * once x_{i-B} is in, i.e. at step j = i-B.  Only the B+1 entries A(j, j..j+B) of each matrix
+     * are read per step (half of a full-band row). */
+    double yw[K1], xv[K1], hs[K1], ss[K1];
 #pragma unroll
-    for (int i = 0; i < B; ++i) yw[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < W; ++i) xw[i] = 0.0;
+    for (int i = 0; i < K1; ++i) { yw[i] = 0.0; xv[i] = 0.0; hs[i] = 0.0; ss[i] = 0.0; }
     double xSx = 0.0, xHx = 0.0, resmax = 0.0;
 
-    /* ring of PF factor rows (+ x_old) in flight: row j is consumed PF steps
-     * after its loads were issued, which is what hides the HBM latency of
-     * this purely streaming sweep */
+    /* ring of PF factor rows (+ x_old) in flight: row j is consumed PF steps after its loads were
+     * issued, which is what hides the HBM latency of this purely streaming sweep */
     double Lq[PF][K1], xq[PF];
     auto fetch = [&](int q, int row) {
         if (row >= 0) {
@@ -598,46 +603,73 @@ BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now
     };
 #pragma unroll
     for (int q = 0; q < PF; ++q) fetch(q, npad - 1 - q);
+    /* band column of the row about to be processed, one step ahead (L1 latency) */
+    double ah[K1], as[K1];
+    {
+        const int r0 = npad - 1;
+#pragma unroll
+        for (int d = 0; d <= B; ++d) {
+            ah[d] = BSP_LDG(fbH + (size_t)r0 * FS + B + d);
+            as[d] = BSP_LDG(fbS + (size_t)r0 * FS + B + d);
+        }
+    }
 
     for (int j0 = npad - 1; j0 >= -B; j0 -= PF) {
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
             const int j = j0 - q;
             if (j >= -B) {
+                /* shift the windows: index 0 becomes row j */
+#pragma unroll
+                for (int i = B; i >= 1; --i) { yw[i] = yw[i - 1]; xv[i] = xv[i - 1]; hs[i] = hs[i - 1]; ss[i] = ss[i - 1]; }
                 double xn = 0.0;
                 if (j >= 0) {
                     double yj = Lq[q][0];
 #pragma unroll
-                    for (int i = B; i >= 1; --i) yj = fma(-Lq[q][i], yw[i - 1], yj);
-#pragma unroll
-                    for (int i = B - 1; i >= 1; --i) yw[i] = yw[i - 1];
+                    for (int i = B; i >= 1; --i) yj = fma(-Lq[q][i], yw[i], yj);   /* yw[i] = y_{j+i} */
                     yw[0] = yj;
                     if (j < n) {
                         xn = fma(cx, xq[q], -yj);
                         Xp[(size_t)j * ldw] = xn;
                     }
+                } else {
+                    yw[0] = 0.0;
                 }
                 fetch(q, j - PF);   /* slot q is free again: row j-PF goes in flight */
+                xv[0] = xn;
+                /* column j: A(j+d, j) = A(j, j+d) = ah[d] */
+                double h0 = 0.0, s0 = 0.0;
+                if (j >= 0) {
 #pragma unroll
-                for (int c = W - 1; c >= 1; --c) xw[c] = xw[c - 1];
-                xw[0] = xn;
-                /* row i = j + B now has its whole stencil x_new[j .. j+2B] */
+                    for (int d = 1; d <= B; ++d) {
+                        hs[d] = fma(ah[d], xn, hs[d]);
+                        ss[d] = fma(as[d], xn, ss[d]);
+                    }
+#pragma unroll
+                    for (int d = 0; d <= B; ++d) {
+                        h0 = fma(ah[d], xv[d], h0);
+                        s0 = fma(as[d], xv[d], s0);
+                    }
+                    /* prefetch the column of row j-1 */
+                    if (j >= 1) {
+#pragma unroll
+                        for (int d = 0; d <= B; ++d) {
+                            ah[d] = BSP_LDG(fbH + (size_t)(j - 1) * FS + B + d);
+                            as[d] = BSP_LDG(fbS + (size_t)(j - 1) * FS + B + d);
+                        }
+                    }
+                }
+                hs[0] = h0;
+                ss[0] = s0;
+                /* row i = j + B is complete */
                 const int i = j + B;
                 if (i < n) {
-                    const double *hrow = fbH + (size_t)i * FS;
-                    const double *srow = fbS + (size_t)i * FS;
-                    double s = 0.0, h = 0.0;
-#pragma unroll
-                    for (int c = 0; c < W; ++c) {
-                        s = fma(BSP_LDG(srow + c), xw[c], s);
-                        h = fma(BSP_LDG(hrow + c), xw[c], h);
-                    }
-                    const double xi = xw[B];
-                    xSx = fma(xi, s, xSx);
+                    const double h = hs[B], sv = ss[B], xi = xv[B];
+                    xSx = fma(xi, sv, xSx);
                     xHx = fma(xi, h, xHx);
-                    const double r = fma(-rho_p, s, h);
+                    const double r = fma(-rho_p, sv, h);
                     resmax = fmax(resmax, fabs(r));
-                    Rp[(size_t)i * ldw] = corr_next ? r : s;
+                    Rp[(size_t)i * ldw] = corr_next ? r : sv;
                 }
             }
         }

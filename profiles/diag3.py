@@ -1,5 +1,5 @@
-"""e2e sensitivity to host polling: solve_batch with different first_check_round (diagnostic)."""
-import sys, time, json
+"""resident + e2e sensitivity to the number of chunk streams (diagnostic)."""
+import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
 import bspatom_b200 as bsp
@@ -9,14 +9,22 @@ inp, items = workload_items(bsp, 0, 8, "lin")
 n = len(items)
 E = torch.empty(n * NFUN, dtype=torch.float64).pin_memory().numpy()
 Cb = torch.empty(n * NFUN * NFUN, dtype=torch.float64).pin_memory().numpy()
-for fcr in (6,):
-    atom.set_option("first_check_round", fcr)
+for workers, chunk in ((1, 0), (2, 0), (3, 0), (4, 0), (4, 51), (4, 34), (3, 34)):
+    atom.set_option("workers", workers)
+    atom.set_option("chunk", chunk)
+    atom.batch_upload(items)
+    for _ in range(2):
+        atom.batch_run()
+    r = []
+    for _ in range(4):
+        atom.batch_run(); r.append(atom.stats()["ms_total"])
     for _ in range(2):
         atom.solve_batch(items, out_E=E, out_C=Cb)
-    t0 = time.perf_counter()
-    for _ in range(3):
+    ts = []
+    for _ in range(6):
+        t0 = time.perf_counter()
         atom.solve_batch(items, out_E=E, out_C=Cb)
-    dt = (time.perf_counter() - t0) / 3
+        ts.append(1e3 * (time.perf_counter() - t0))
     st = atom.stats()
-    print("first_check_round", fcr, "e2e ms/step %.1f" % (1e3 * dt), "ms_total %.1f rounds %d iters %d tail %.1f launches %d" %
-          (st["ms_total"], st["rounds"], st["iters"], st["wall_ms_copy_tail"], st["launches"]), flush=True)
+    print("workers", workers, "chunk", chunk, "resident ms %.1f | e2e ms/step median %.1f min %.1f" % (np.median(r), np.median(ts), min(ts)),
+          "ms_total %.1f tail %.1f launches %d" % (st["ms_total"], st["wall_ms_copy_tail"], st["launches"]), flush=True)
