@@ -296,7 +296,25 @@ class BspAtom(BspInputs):
             raise BspAtomError("ERROR DIAGONALIZING THE MATRIX! info=%d  l = %d" % (bad[0][1], bad[0][0]))
         self.Enl = np.stack(E, axis=1)
         self.cinl = Cs
+        # bookkeeping of matrices.f90:269-346 on the gathered eigenpairs (host side, like the reference)
+        self.sel = None
+        if self.KIND_PI != 0:
+            from . import postproc
+
+            self.sel = postproc.select_states(self.Enl, self.KIND_PI, self.l_ini, self.l_fin, self.Emax_fin)
+            self.Emax_fin = self.sel.Emax_fin
         return self.Enl, self.cinl
+
+    def write_outputs(self, directory: str = "."):
+        """Enl.dat (matrices.f90:239-265) and, for KIND_PI >= 3, Eigenvec_All.dat (matrices.f90:366-378)."""
+        import os
+
+        from . import postproc
+
+        postproc.write_enl(os.path.join(directory, "Enl.dat"), self.Enl)
+        if self.KIND_PI >= 3 and self.sel is not None:
+            cinl = postproc.collect_cinl(self.cinl, self.sel)
+            postproc.write_eigenvec_all(os.path.join(directory, "Eigenvec_All.dat"), cinl)
 
     def solve_batch(self, items: Iterable, nvec: Optional[int] = None, want_vectors: bool = True,
                     out_E: Optional[np.ndarray] = None, out_C: Optional[np.ndarray] = None):

@@ -1,0 +1,173 @@
+"""Host-side post-processing of SOLVE_SYSTEM: state limits, density of
+states, and the two text files the companion TDSE codes read back.
+
+Follows matrices.f90:239-240,261-265 (Enl.dat), :269-346 (selection logic, both KIND_PI branches),
+:352-378 (n1_max, cinl, Eigenvec_All.dat) and the FORMATs at :391-392.  Pure bookkeeping on the
+gathered eigenpairs (O(N) per l); nothing here touches the GPU."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+
+# ---- Fortran edit descriptors -------------------------------------------------------------
+def fortran_e(v: float, w: int, d: int) -> str:
+    """Ew.d with scale factor 0: sign, '0.', d digits, 'E+ee'."""
+    if v == 0.0:
+        body = "0." + "0" * d + "E+00"
+    else:
+        m, ex = ("%.*E" % (d - 1, abs(v))).split("E")
+        digits = m.replace(".", "")
+        ex10 = int(ex) + 1
+        es = "%+03d" % ex10 if abs(ex10) <= 99 else "%+04d" % ex10
+        body = "0." + digits + ("E" + es if abs(ex10) <= 99 else es)
+    if v < 0 or (v == 0.0 and np.signbit(v)):
+        body = "-" + body
+    return body.rjust(w) if len(body) <= w else "*" * w
+
+
+def fortran_g(v: float, w: int, d: int) -> str:
+    """Gw.d (F2008 10.7.5.2.2): F(w-4).(d-k) followed by 4 blanks when 0.1 <= |v| < 10**d after
+    rounding to d significant digits (k = decimal exponent), else Ew.d."""
+    n = abs(v)
+    if n == 0.0:
+        body = ("%.*f" % (d - 1, 0.0)).rjust(w - 4) + "    "
+        return body
+    ex10 = int(("%.*E" % (d - 1, n)).split("E")[1]) + 1      # |v| = 0.ddd x 10**ex10 after rounding
+    if 0 <= ex10 <= d:
+        s = "%.*f" % (d - ex10, v)
+        return (s.rjust(w - 4) if len(s) <= w - 4 else "*" * (w - 4)) + "    "
+    return fortran_e(v, w, d)
+
+
+def _t2_i4_t8_g22(i: int, e: float) -> str:
+    """FORMAT(T2,I4,T8,G22.15)  matrices.f90:391"""
+    return " " + "%4d" % i + "  " + fortran_g(e, 22, 15)
+
+
+def write_enl(path: str, Enl: np.ndarray) -> None:
+    """Enl.dat: nfun, then for l = 0..lmax the lines (i, En(i)), i = 1..nfun  (matrices.f90:239-240,264)."""
+    nfun, nl = Enl.shape
+    with open(path, "w") as f:
+        f.write("%12d\n" % nfun)                       # WRITE(75,*) nfun  (list-directed integer)
+        for l in range(nl):
+            col = Enl[:, l]
+            f.write("\n".join(_t2_i4_t8_g22(i + 1, float(col[i])) for i in range(nfun)) + "\n")
+
+
+def write_eigenvec_all(path: str, cinl: np.ndarray) -> None:
+    """Eigenvec_All.dat (matrices.f90:366-378): header nfun, n1_max, lmax; per l the line `l` and
+    n1_max records FORMAT(I5,5000G20.10).  cinl has shape (nfun, n1_max, lmax+1)."""
+    nfun, n1_max, nl = cinl.shape
+    with open(path, "w") as f:
+        f.write("%12d%12d%12d\n" % (nfun, n1_max, nl - 1))
+        for l in range(nl):
+            f.write("%12d\n" % l)
+            for ni in range(n1_max):
+                f.write("%5d" % (ni + 1) + "".join(fortran_g(float(x), 20, 10) for x in cinl[:, ni, l]) + "\n")
+
+
+# ---- selection logic ----------------------------------------------------------------------
+@dataclass
+class StateSelection:
+    """what SOLVE_SYSTEM leaves in MOD_PHOTOION for the photo-ionisation stage"""
+
+    n0_fin: int = -1
+    n1_fin: int = -1
+    Emax_fin: float = -1.0
+    n1_max: int = -1
+    nbds: int = 0
+    n01: Optional[np.ndarray] = None      # (lmax+1, 3)                 KIND_PI >= 3
+    rEki: Optional[np.ndarray] = None     # (nfun, lmax+1)              KIND_PI >= 3
+    ntemp: List[int] = field(default_factory=list)   # columns of Hij kept per l (ctemp)
+    E_ini: Optional[np.ndarray] = None    # KIND_PI = 1, 2
+    E_fin: Optional[np.ndarray] = None
+
+
+def select_states(Enl: np.ndarray, kind_pi: int, l_ini: int, l_fin: int, Emax_fin: float) -> StateSelection:
+    """The bookkeeping of the l-loop of SOLVE_SYSTEM (matrices.f90:269-346) and of its epilogue
+    (:352-356) on the eigenvalues of all l.  Indices in the result are the reference's 1-based ones.
+    State that the reference carries from one l to the next (n0_fin, n1_fin, nlim, nbds, a stale
+    ntemp, Emax_fin once replaced) is carried here in the same way."""
+    nfun, nl = Enl.shape
+    sel = StateSelection(Emax_fin=float(Emax_fin))
+    n0_fin = n1_fin = -1
+    nlim = nbds = 0
+    ntemp = 0
+    if kind_pi >= 3:
+        sel.n01 = np.zeros((nl, 3), dtype=np.int64)
+        sel.rEki = np.ones((nfun, nl))
+    for l in range(nl):
+        En = Enl[:, l]
+        if kind_pi in (1, 2):
+            if l == l_ini:
+                sel.E_ini = En.copy()
+            elif l == l_fin:
+                sel.E_fin = En.copy()
+                if sel.Emax_fin == -1.0:
+                    sel.Emax_fin = float(En[-1])
+                neg = np.nonzero(En < 0.0)[0]
+                le = np.nonzero(En <= sel.Emax_fin)[0]
+                if neg.size:
+                    n0_fin = int(neg[-1]) + 1
+                if le.size:
+                    n1_fin = int(le[-1]) + 1
+                n0_fin = min(n0_fin + 1, nfun - 1)
+        elif kind_pi >= 3:
+            if sel.Emax_fin == -1.0:
+                sel.Emax_fin = float(En[-1])
+                Elim = sel.Emax_fin
+            else:
+                Elim = sel.Emax_fin + 0.25
+                if kind_pi >= 8:
+                    Elim = sel.Emax_fin
+            # the search loop leaves at the first level above both limits
+            above = np.nonzero((En > sel.Emax_fin) & (En > Elim))[0]
+            last = int(above[0]) if above.size else nfun - 1          # 0-based index of the last level visited
+            seen = En[: last + 1]
+            neg = np.nonzero(seen < 0.0)[0]
+            nbold = int(neg.size)
+            if neg.size:
+                n0_fin = int(neg[-1]) + 1
+            le = np.nonzero(seen <= sel.Emax_fin)[0]
+            if le.size:
+                n1_fin = int(le[-1]) + 1
+            lt = np.nonzero(seen <= Elim)[0]
+            if lt.size:
+                ntemp = int(lt[-1]) + 1
+            nbds = max(nbds, nbold)
+            n0_fin += 1
+            n1_fin += 1
+            nE0 = n0_fin
+            if kind_pi >= 5:
+                n0_fin = 1
+            nlim = max(nlim, ntemp)
+            sel.n01[l] = (n0_fin, n1_fin, nE0 - 1)
+            ntemp = min(max(n1_fin + 40, nlim), nfun)
+            sel.ntemp.append(ntemp)
+            # density of states (matrices.f90:338-342), 1-based i = nE0+1 .. nfun-1
+            i = np.arange(nE0 + 1, nfun)                       # 1-based
+            if i.size:
+                sel.rEki[i - 1, l] = np.sqrt(2.0 / (En[i] - En[i - 2]))
+            if 1 <= nE0 < nfun:
+                sel.rEki[nE0 - 1, l] = np.sqrt(1.0 / (En[nE0] - En[nE0 - 1]))
+            sel.rEki[nfun - 1, l] = np.sqrt(1.0 / (En[nfun - 1] - En[nfun - 2]))
+    sel.n0_fin, sel.n1_fin, sel.nbds = n0_fin, n1_fin, nbds
+    sel.n1_max = n1_fin
+    if kind_pi >= 3:
+        sel.n1_max = min(max(int(sel.n01[:, 1].max()) + 20, nlim), nfun)
+    return sel
+
+
+def collect_cinl(C_per_l: List[np.ndarray], sel: StateSelection) -> np.ndarray:
+    """cinl(1:nfun, 1:n1_max, l) = ctemp(1:nfun, 1:n1_max, l)  (matrices.f90:369-373); ctemp holds the
+    first ntemp(l) eigenvectors of each l and zeros beyond (it is zero-initialised at l = 0)."""
+    nfun = C_per_l[0].shape[0]
+    nl = len(C_per_l)
+    cinl = np.zeros((nfun, sel.n1_max, nl), order="F")
+    for l in range(nl):
+        keep = min(sel.ntemp[l], sel.n1_max, C_per_l[l].shape[1])
+        cinl[:, :keep, l] = C_per_l[l][:, :keep]
+    return cinl

@@ -1,0 +1,108 @@
+"""Literal (loop by loop, 1-based) restatement of the bookkeeping in SOLVE_SYSTEM, matrices.f90:269-346
+and :352-356, and of the record formats at :391-392.  TEST INFRASTRUCTURE ONLY (see oracle/bsp_oracle.c)."""
+import math
+
+import numpy as np
+
+
+def g_edit(v, w, d):
+    """Gw.d by the text of the standard: pick the F sub-format from the magnitude thresholds
+    10**(k-1) - 0.5*10**(k-1-d) <= |v| < 10**k - 0.5*10**(k-d), k = 0..d; otherwise Ew.d."""
+    from decimal import Decimal
+
+    n = Decimal(repr(abs(float(v)))) if v != 0 else Decimal(0)
+    exact = Decimal(abs(float(v)))                    # exact binary value
+    if exact == 0:
+        return ("%.*f" % (d - 1, 0.0)).rjust(w - 4) + " " * 4
+    for k in range(0, d + 1):
+        lo = Decimal(10) ** (k - 1) - Decimal(5) * Decimal(10) ** (k - 2 - d)
+        hi = Decimal(10) ** k - Decimal(5) * Decimal(10) ** (k - 1 - d)
+        if lo <= exact < hi:
+            return ("%.*f" % (d - k, float(v))).rjust(w - 4) + " " * 4
+    m, ex = ("%.*E" % (d - 1, abs(float(v)))).split("E")
+    ex = int(ex) + 1
+    s = ("-" if v < 0 else "") + "0." + m.replace(".", "") + "E" + ("+" if ex >= 0 else "-") + "%02d" % abs(ex)
+    return s.rjust(w)
+
+
+def solve_system_bookkeeping(Enl, kind_pi, l_ini, l_fin, emax_fin):
+    """returns dict with the reference's variables after the l-loop (all 1-based)."""
+    nfun, nl = Enl.shape
+    lmax = nl - 1
+    n0_fin = -1                                              # :234
+    n1_fin = -1                                              # :235
+    nlim = 0                                                 # :236
+    nbds = 0                                                 # :237
+    ntemp = 0
+    n01 = np.zeros((lmax + 1, 3), dtype=np.int64)
+    rEki = np.ones((nfun, lmax + 1))                         # :231
+    ntemps = []
+    E_ini = E_fin = None
+    for l in range(0, lmax + 1):                             # :242
+        En = [None] + [float(x) for x in Enl[:, l]]          # 1-based
+        if kind_pi == 1 or kind_pi == 2:                     # :269
+            if l == l_ini:                                   # :271
+                E_ini = np.array(En[1:])
+            elif l == l_fin:                                 # :274
+                E_fin = np.array(En[1:])
+                if emax_fin == -1.0:
+                    emax_fin = En[nfun]                      # :276
+                i = 1
+                while True:                                  # :278-283
+                    if En[i] < 0.0:
+                        n0_fin = i
+                    if En[i] <= emax_fin:
+                        n1_fin = i
+                    i = i + 1
+                    if i > nfun:
+                        break
+                n0_fin = n0_fin + 1                          # :284
+                n0_fin = min(n0_fin, nfun - 1)               # :285
+        elif kind_pi >= 3:                                   # :292
+            if emax_fin == -1.0:                             # :295-301
+                emax_fin = En[nfun]
+                elim = emax_fin
+            else:
+                elim = emax_fin + 0.25
+                if kind_pi >= 8:
+                    elim = emax_fin
+            i = 1
+            nbold = 0
+            while True:                                      # :305-315
+                if En[i] < 0.0:
+                    n0_fin = i
+                    nbold = nbold + 1
+                if En[i] <= emax_fin:
+                    n1_fin = i
+                if En[i] <= elim:
+                    ntemp = i
+                if En[i] > emax_fin and En[i] > elim:
+                    break
+                i = i + 1
+                if i > nfun:
+                    break
+            nbds = max(nbds, nbold)                          # :316
+            n0_fin = n0_fin + 1
+            n1_fin = n1_fin + 1
+            nE0 = n0_fin
+            if kind_pi >= 5:
+                n0_fin = 1
+            if ntemp > nlim:
+                nlim = ntemp
+            n01[l, 0] = n0_fin
+            n01[l, 1] = n1_fin
+            n01[l, 2] = nE0 - 1
+            ntemp = max(n1_fin + 40, nlim)                   # :328
+            ntemp = min(ntemp, nfun)
+            ntemps.append(ntemp)
+            for i in range(nE0 + 1, nfun - 1 + 1):           # :338-340
+                rEki[i - 1, l] = math.sqrt(2.0 / (En[i + 1] - En[i - 1]))
+            if 1 <= nE0 < nfun:
+                rEki[nE0 - 1, l] = math.sqrt(1.0 / (En[nE0 + 1] - En[nE0]))          # :341
+            rEki[nfun - 1, l] = math.sqrt(1.0 / (En[nfun] - En[nfun - 1]))           # :342
+    n1_max = n1_fin                                          # :352
+    if kind_pi >= 3:
+        n1_max = max(int(n01[:, 1].max()) + 20, nlim)        # :355
+        n1_max = min(n1_max, nfun)
+    return dict(n0_fin=n0_fin, n1_fin=n1_fin, Emax_fin=emax_fin, n1_max=n1_max, nbds=nbds, n01=n01, rEki=rEki,
+                ntemp=ntemps, E_ini=E_ini, E_fin=E_fin)
