@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--zrep", type=int, default=ZREP_DEFAULT, help="nuclear charges per GPU per step")
     ap.add_argument("--ref-ls", type=int, default=3, help="l values per reference step")
     ap.add_argument("--workers", type=int, default=0, help="chunk streams (0 = library default)")
+    ap.add_argument("--recompute", type=int, default=-1, help="1/0: check-pointed vs stored-factor refinement (-1 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -207,6 +208,8 @@ def main():
     atom = bsp.BspAtom(device=local)
     if args.workers:
         atom.set_option("workers", args.workers)
+    if args.recompute >= 0:
+        atom.set_option("recompute", args.recompute)
     inp, items = workload_items(bsp, rank, args.zrep, args.grid)
     nsolve = len(items)
     n_e = nsolve * NFUN

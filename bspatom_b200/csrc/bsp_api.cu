@@ -47,6 +47,8 @@ struct Options {
     int check_every = 2;
     int chunk = 0; /* 0 = auto */
     int workers = 2; /* concurrent chunk streams (1..4) */
+    int recompute = 0; /* 1: check-pointed refinement (re-eliminate in the back sweep; measured slower, see
+                          DESIGN.md section 12), 0: store the factor */
 };
 
 struct Group {
@@ -372,14 +374,20 @@ struct GpuExec {
         timed_end(h, s);
     }
     void prepare(int buf) { bsp_prepare_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, buf); note(); }
+    int cur_iter = 0;
     void factor(int it) {
+        cur_iter = it;
         const int s = timed_begin(h, 1);
-        bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it); note();
+        if (h->opt.recompute) bsp_factor_ckpt_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it);
+        else bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it);
+        note();
         timed_end(h, s);
     }
     void back(int cn, int cx) {
         const int s = timed_begin(h, 2);
-        bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx); note();
+        if (h->opt.recompute) bsp_back_rc_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx, cur_iter);
+        else bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx);
+        note();
         timed_end(h, s);
     }
     void check(int allow) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, allow); note(); }
@@ -423,7 +431,7 @@ struct ChunkPtrs {
     int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c, *samp_fe, *fle, *fhe, *side;
 };
 
-size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
+size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c, bool recompute = false)
 {
     Carver cv{base};
     const size_t per = (size_t)np * G.ldw;
@@ -441,7 +449,8 @@ size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
     c.fac = cv.take<double>(per);
     c.counters = cv.take<int>(64);
     c.cand_s = cv.take<double>((size_t)np * BSP_NCAND); c.cand_c = cv.take<int>((size_t)np * BSP_NCAND);
-    c.L = cv.take<double>((size_t)np * G.npad * (G.B + 1) * G.ldw);
+    c.L = recompute ? cv.take<double>((size_t)np * (G.npad / BSP_SEG_STEPS(G.B)) * BSP_CK_DOUBLES(G.B) * G.ldw)
+                    : cv.take<double>((size_t)np * G.npad * (G.B + 1) * G.ldw);
     c.X = cv.take<double>((size_t)np * G.xrows * G.ldw);
     c.R = cv.take<double>((size_t)np * G.xrows * G.ldw);
     return cv.used;
@@ -672,6 +681,7 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "first_check_round") h->opt.first_check_round = std::max(1, (int)v);
     else if (s == "check_every") h->opt.check_every = std::max(1, (int)v);
     else if (s == "chunk") h->opt.chunk = (int)v;
+    else if (s == "recompute") { h->opt.recompute = v != 0.0; for (auto &G : h->groups) G.chunk_cached = 0; }
     else if (s == "workers") h->opt.workers = std::min(4, std::max(1, (int)v));
     else return -2;
     return 0;
@@ -725,7 +735,7 @@ int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs)
             Group &G = h->groups.back();
             G.k = p.k; G.B = p.k - 1; G.n = p.nfun; G.nkp = p.nkp; G.ka = p.ka;
             G.FS = 2 * G.B + 2;
-            G.npad = ((G.n + G.B) / (G.B + 1)) * (G.B + 1);
+            G.npad = BSP_NPAD(G.n, G.B);
             G.nrows = BSP_NROWS(G.npad, G.B);
             G.xrows = G.npad + G.B + 1;
             G.ldw = ((G.n + 31) / 32) * 32;
@@ -881,7 +891,7 @@ void chunk_worker(bspatom_handle main_h, bspatom_handle hw, Group *G, int chunk,
         CU(cudaSetDevice(h->dev));
         CU(cudaStreamWaitEvent(h->st, asm_done, 0));
         ChunkPtrs c;
-        carve_chunk(*G, chunk, h->ws.base, c);
+        carve_chunk(*G, chunk, h->ws.base, c, main_h->opt.recompute != 0);
         ChunkTimes tm;
         for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tm.ev[i]));
         int rc = 0;
@@ -961,7 +971,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         CU(cudaEventRecord(e2, h->st));
         /* ---- eigen stages: chunk queue ---- */
         ChunkPtrs c;
-        const size_t per_pencil = carve_chunk(G, 1, nullptr, c);
+        const size_t per_pencil = carve_chunk(G, 1, nullptr, c, h->opt.recompute != 0);
         const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
         const int fill_pencils = std::max(1, (148 * 4 + blocks_per_pencil - 1) / blocks_per_pencil); /* one full wave */
         int workers = std::max(1, std::min(h->opt.workers, G.npencil / fill_pencils));
@@ -988,7 +998,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         chunk = (G.npencil + nchunks - 1) / nchunks;
         nchunks = (G.npencil + chunk - 1) / chunk;
         workers = std::min(workers, nchunks);
-        const size_t need = carve_chunk(G, chunk, nullptr, c);
+        const size_t need = carve_chunk(G, chunk, nullptr, c, h->opt.recompute != 0);
         if ((rc = ensure_workspace(h, need))) return rc;
         while ((int)h->aux.size() < workers - 1) {
             bspatom_handle x = new_context(h->dev);
@@ -1113,7 +1123,7 @@ int bspatom_assemble_band(bspatom_handle h, const bsp_problem *p, double *S, dou
     if ((rc = validate_problem(q))) return rc;
     Group G;
     G.k = q.k; G.B = q.k - 1; G.n = q.nfun; G.nkp = q.nkp; G.ka = q.ka; G.FS = 2 * G.B + 2;
-    G.npad = ((G.n + G.B) / (G.B + 1)) * (G.B + 1);
+    G.npad = BSP_NPAD(G.n, G.B);
     G.nrows = BSP_NROWS(G.npad, G.B);
     std::vector<const bsp_problem *> insts = {&q};
     G.ninst = 1;

@@ -195,7 +195,7 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
     const int B = std::max(kd, BSP_KMIN - 1);
     Group G;
     G.k = B + 1; G.B = B; G.n = n; G.nkp = n + G.k; G.ka = 1; G.FS = 2 * B + 2;
-    G.npad = ((n + B) / (B + 1)) * (B + 1);
+    G.npad = BSP_NPAD(n, B);
     G.nrows = BSP_NROWS(G.npad, B); G.xrows = G.npad + B + 1; G.ldw = ((n + 31) / 32) * 32;
     G.ninst = 1; G.npencil = 1;
     G.prob_index = {0}; G.inst = {0}; G.nvec = {wantz ? n : 0}; G.cl = {0.0}; G.coff = {0};
@@ -249,14 +249,14 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
     h->groups.push_back(G);
     Group &GG = h->groups.back();
     ChunkPtrs c;
-    const size_t need = carve_chunk(GG, 1, nullptr, c);
+    const size_t need = carve_chunk(GG, 1, nullptr, c, h->opt.recompute != 0);
     ChunkTimes tm;
     BspRunStats st;
     bool ev_ok = true;
     for (int i = 0; i < 4; ++i) ev_ok = ev_ok && (cudaEventCreate(&tm.ev[i]) == cudaSuccess);
     rc = ev_ok ? ensure_workspace(h, need) : BSPATOM_ECUDA;
     if (!rc) {
-        carve_chunk(GG, 1, h->ws.base, c);
+        carve_chunk(GG, 1, h->ws.base, c, h->opt.recompute != 0);
         rc = run_chunk(h, GG, 0, 1, c, st, tm);
     }
     std::vector<double> Lb((size_t)n * (B + 1)), Cout(wantz ? (size_t)n * n : 0);

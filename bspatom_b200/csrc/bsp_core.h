@@ -52,6 +52,19 @@
  * decoupled: diag(H) = 1, rest 0) */
 #define BSP_NROWS(npad, B) ((npad) + (B) + 2)
 
+/* Check-pointed refinement: the forward sweep keeps only the elimination state (pivot window + rhs
+ * window, BSP_CK_DOUBLES(B) doubles) at the start of every segment of BSP_SEG_BLOCKS*(B+1) rows
+ * instead of the whole factor; the back sweep re-eliminates one segment at a time into a
+ * thread-private scratch (L1/L2 resident) and consumes it at once.  Factor traffic to HBM drops from
+ * (B+1) doubles per row to BSP_CK_DOUBLES/(BSP_SEG_BLOCKS*(B+1)), at the price of eliminating twice. */
+#ifndef BSP_SEG_BLOCKS
+#define BSP_SEG_BLOCKS 4
+#endif
+#define BSP_SEG_STEPS(B) (BSP_SEG_BLOCKS * ((B) + 1))
+#define BSP_CK_DOUBLES(B) ((((B) + 1) * ((B) + 2)) / 2 + (B) + 1)
+/* rows are padded to a whole number of segments */
+#define BSP_NPAD(n, B) ((((n) + BSP_SEG_STEPS(B) - 1) / BSP_SEG_STEPS(B)) * BSP_SEG_STEPS(B))
+
 /* refinement status bits */
 #define BSP_ST_CONVERGED 1
 #define BSP_F_UNKNOWN (-2000000000)
@@ -59,7 +72,7 @@
 struct BspEigChunk {
     /* geometry */
     int n;        /* basis size                                   */
-    int npad;     /* n rounded up to a multiple of B+1            */
+    int npad;     /* BSP_NPAD(n, B): whole segments of (B+1) blocks */
     int nrows;    /* rows stored per band matrix = BSP_NROWS      */
     int xrows;    /* rows of X / R workspaces   = npad + B + 1    */
     int ldw;      /* eigen-index stride (n rounded up to 32)      */
@@ -88,7 +101,8 @@ struct BspEigChunk {
     double *sigma, *rho, *rho_prev, *scale, *res;
     int *status;
     /* workspaces */
-    double *L; /* [npencil][npad][B+1][ldw]  (zd, l_1..l_B)       */
+    double *L; /* [npencil][npad][B+1][ldw]  (zd, l_1..l_B), or, check-pointed:
+                  [npencil][npad/SEG][BSP_CK_DOUBLES][ldw]        */
     double *X; /* [npencil][xrows][ldw]                           */
     double *R; /* [npencil][xrows][ldw]                           */
     int *counters; /* [0] brackets not done, [1] eigenpairs not converged */
@@ -673,6 +687,316 @@ BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now
                 }
             }
         }
+    }
+    /* bookkeeping + next shift */
+    double lo = g.lo[id], hi = g.hi[id];
+    const double good = (xSx > 0.0 && xSx < INFINITY) ? 1.0 : 0.0;
+    double rho_new = rho_p, scn = sc, res = INFINITY;
+    if (good != 0.0) {
+        rho_new = xHx / xSx;
+        scn = 1.0 / sqrt(xSx);
+        res = resmax * scn;
+    }
+    g.rho_prev[id] = rho_p;
+    g.rho[id] = rho_new;
+    g.scale[id] = scn;
+    g.res[id] = res;
+    double sig = (rho_new > lo && rho_new < hi) ? rho_new : 0.5 * (lo + hi);
+    if (corr_next) {
+        double gp = g.gap[id];
+        if (!(gp > 0.0) || !(gp < INFINITY)) gp = fmax(hi - lo, fabs(rho_new) * 1e-6 + 1e-12);
+        const double delta = g.delta_rel * gp;
+        if (fabs(sig - rho_p) < delta) sig = (rho_p + delta < hi) ? rho_p + delta : rho_p - delta;
+    }
+    g.sigma[id] = sig;
+}
+
+/* ------------------------------------------------------------------------- *
+ * Check-pointed F pass: same elimination + forward substitution as
+ * bsp_factor_forward, but nothing is stored per row; at the start of every
+ * segment the live state (lower triangle of the pivot window, rhs window) goes
+ * to CK[p][seg][0..BSP_CK_DOUBLES)[e].
+ * ------------------------------------------------------------------------- */
+template <int B>
+BSP_HD void bsp_factor_checkpoint(const BspEigChunk &g, int p, int e, int iter)
+{
+    constexpr int K1 = B + 1;
+    constexpr int FS = 2 * B + 2;
+    constexpr int CKD = BSP_CK_DOUBLES(B);
+    if (e >= g.n) return;
+    const size_t id = (size_t)p * g.ldw + e;
+    if (g.status[id] & BSP_ST_CONVERGED) return;
+    const int n = g.n, npad = g.npad, ldw = g.ldw;
+    const int nseg = npad / BSP_SEG_STEPS(B);
+    const double *__restrict__ fbH = g.fbH + (size_t)p * g.nrows * FS;
+    const double *__restrict__ fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
+    const double sigma = g.sigma[id];
+    const double sc = g.scale[id];
+    const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(sigma) * g.pbound[p * 4 + 3]);
+    const double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
+    double *__restrict__ Cp = g.L + (size_t)p * nseg * CKD * ldw + e;
+    const double scr = (iter == 0) ? 1.0 : sc;
+    auto rhs = [&](int row) -> double {
+        if (row >= n) return 0.0;
+        return (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)row) : Rp[(size_t)row * ldw];
+    };
+    double w[K1][K1], y[K1];
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < K1; ++r) {
+#pragma unroll
+        for (int c = 0; c < K1; ++c) {
+            if (c <= r) {
+                const int off = r * FS + (c - r + B);
+                w[r][c] = fma(-sigma, BSP_LDG(fbS + off), BSP_LDG(fbH + off));
+            } else {
+                w[r][c] = 0.0;
+            }
+        }
+        y[r] = scr * rhs(r);
+    }
+    double nh[K1], ns[K1], rq[K1];
+#pragma unroll
+    for (int m = 0; m <= B; ++m) {
+        nh[m] = BSP_LDG(fbH + (size_t)K1 * FS + m);
+        ns[m] = BSP_LDG(fbS + (size_t)K1 * FS + m);
+        rq[m] = rhs(K1 + m);
+    }
+    for (int seg = 0; seg < nseg; ++seg) {
+        /* check-point: at a segment start the window slots are in identity position */
+        {
+            double *ck = Cp + (size_t)seg * CKD * ldw;
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < K1; ++r) {
+#pragma unroll
+                for (int c = 0; c <= r; ++c) { ck[(size_t)q * ldw] = w[r][c]; ++q; }
+            }
+#pragma unroll
+            for (int r = 0; r < K1; ++r) { ck[(size_t)q * ldw] = y[r]; ++q; }
+        }
+#pragma unroll 1
+        for (int blk = 0; blk < BSP_SEG_BLOCKS; ++blk) {
+            const int j0 = (seg * BSP_SEG_BLOCKS + blk) * K1;
+#pragma unroll
+            for (int t = 0; t < K1; ++t) {
+                const int j = j0 + t;
+                const double rnew = scr * rq[t];
+                rq[t] = rhs(j + 2 * K1);
+                double d = w[t][t];
+                if (fabs(d) < pivmin) d = -pivmin;
+                if (d < 0.0) ++cnt;
+                const double rinv = BSP_RCP(d);
+                double col[K1], l[K1];
+                const double y0 = y[t];
+#pragma unroll
+                for (int i = 1; i <= B; ++i) {
+                    col[i] = w[(t + i) % K1][t];
+                    l[i] = col[i] * rinv;
+                    y[(t + i) % K1] = fma(-l[i], y0, y[(t + i) % K1]);
+                }
+#pragma unroll
+                for (int m = 1; m <= B; ++m) {
+#pragma unroll
+                    for (int i = m; i <= B; ++i) {
+                        w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
+                    }
+                }
+                {
+                    const double *hrow = fbH + (size_t)(j + K1 + 1) * FS;
+                    const double *srow = fbS + (size_t)(j + K1 + 1) * FS;
+#pragma unroll
+                    for (int m = 0; m <= B; ++m) {
+                        w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
+                        nh[m] = BSP_LDG(hrow + m);
+                        ns[m] = BSP_LDG(srow + m);
+                    }
+                }
+                y[t] = rnew;
+            }
+        }
+    }
+    if (cnt <= e) { if (sigma > g.lo[id]) g.lo[id] = sigma; }
+    else { if (sigma < g.hi[id]) g.hi[id] = sigma; }
+}
+
+/* ------------------------------------------------------------------------- *
+ * Check-pointed B pass: per segment (last to first) re-run the elimination from
+ * its check-point into a thread-private scratch, then do the back substitution
+ * and the column-sweep matvecs of bsp_back_substitute over that segment.
+ * ------------------------------------------------------------------------- */
+template <int B>
+BSP_HD void bsp_back_recompute(const BspEigChunk &g, int p, int e, int corr_now, int corr_next, int iter)
+{
+    constexpr int K1 = B + 1;
+    constexpr int FS = 2 * B + 2;
+    constexpr int CKD = BSP_CK_DOUBLES(B);
+    constexpr int T = BSP_SEG_STEPS(B);
+    if (e >= g.n) return;
+    const size_t id = (size_t)p * g.ldw + e;
+    if (g.status[id] & BSP_ST_CONVERGED) return;
+    const int n = g.n, npad = g.npad, ldw = g.ldw;
+    const int nseg = npad / T;
+    const double *__restrict__ fbH = g.fbH + (size_t)p * g.nrows * FS;
+    const double *__restrict__ fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
+    const double *__restrict__ Cp = g.L + (size_t)p * nseg * CKD * ldw + e;
+    double *__restrict__ Xp = g.X + (size_t)p * g.xrows * ldw + e;
+    double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
+    const double sc = g.scale[id];
+    const double rho_p = g.rho[id]; /* rho' */
+    const double sigma = g.sigma[id];
+    const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(sigma) * g.pbound[p * 4 + 3]);
+    const double cx = corr_now ? sc : 0.0;
+    const double scr = (iter == 0) ? 1.0 : sc;
+    /* NOTE: R is overwritten by this very pass (rows >= the current one); the rhs of a segment is read
+     * in its re-elimination, before the back sweep of that segment rewrites those rows, and rows of
+     * later segments are never read again -- except through the (B+1)-row look-ahead of the rhs
+     * window, which is why the window of every segment comes from the check-point, not from R. */
+    auto rhs = [&](int row) -> double {
+        if (row >= n) return 0.0;
+        return (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)row) : Rp[(size_t)row * ldw];
+    };
+
+    double yw[K1], xv[K1], hs[K1], ss[K1];
+#pragma unroll
+    for (int i = 0; i < K1; ++i) { yw[i] = 0.0; xv[i] = 0.0; hs[i] = 0.0; ss[i] = 0.0; }
+    double xSx = 0.0, xHx = 0.0, resmax = 0.0;
+    double scratch[T][K1]; /* (zd, l_1..l_B) of the rows of the current segment */
+    double xold[T];        /* x_old of the segment, fetched during the re-elimination (HBM latency hidden) */
+    double ah[K1], as[K1]; /* band column of the row about to be processed, one step ahead */
+#pragma unroll
+    for (int d = 0; d <= B; ++d) {
+        ah[d] = BSP_LDG(fbH + (size_t)(npad - 1) * FS + B + d);
+        as[d] = BSP_LDG(fbS + (size_t)(npad - 1) * FS + B + d);
+    }
+
+    auto back_step = [&](int j, const double *Lrow, double xo) {
+        /* identical to one step of bsp_back_substitute */
+#pragma unroll
+        for (int i = B; i >= 1; --i) { yw[i] = yw[i - 1]; xv[i] = xv[i - 1]; hs[i] = hs[i - 1]; ss[i] = ss[i - 1]; }
+        double xn = 0.0;
+        if (j >= 0) {
+            double yj = Lrow[0];
+#pragma unroll
+            for (int i = B; i >= 1; --i) yj = fma(-Lrow[i], yw[i], yj);
+            yw[0] = yj;
+            if (j < n) {
+                xn = fma(cx, xo, -yj);
+                Xp[(size_t)j * ldw] = xn;
+            }
+        } else {
+            yw[0] = 0.0;
+        }
+        xv[0] = xn;
+        double h0 = 0.0, s0 = 0.0;
+        if (j >= 0) {
+#pragma unroll
+            for (int d = 1; d <= B; ++d) {
+                hs[d] = fma(ah[d], xn, hs[d]);
+                ss[d] = fma(as[d], xn, ss[d]);
+            }
+#pragma unroll
+            for (int d = 0; d <= B; ++d) {
+                h0 = fma(ah[d], xv[d], h0);
+                s0 = fma(as[d], xv[d], s0);
+            }
+            if (j >= 1) {
+#pragma unroll
+                for (int d = 0; d <= B; ++d) {
+                    ah[d] = BSP_LDG(fbH + (size_t)(j - 1) * FS + B + d);
+                    as[d] = BSP_LDG(fbS + (size_t)(j - 1) * FS + B + d);
+                }
+            }
+        }
+        hs[0] = h0;
+        ss[0] = s0;
+        const int i = j + B;
+        if (i < n && i >= 0) {
+            const double h = hs[B], sv = ss[B], xi = xv[B];
+            xSx = fma(xi, sv, xSx);
+            xHx = fma(xi, h, xHx);
+            const double r = fma(-rho_p, sv, h);
+            resmax = fmax(resmax, fabs(r));
+            Rp[(size_t)i * ldw] = corr_next ? r : sv;
+        }
+    };
+
+    for (int seg = nseg - 1; seg >= 0; --seg) {
+        const int js = seg * T;
+        /* ---- phase A: re-eliminate rows js .. js+T-1 from the check-point ---- */
+        {
+            double w[K1][K1], y[K1], nh[K1], ns[K1], rq[K1];
+            const double *ck = Cp + (size_t)seg * CKD * ldw;
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < K1; ++r) {
+#pragma unroll
+                for (int c = 0; c < K1; ++c) {
+                    if (c <= r) { w[r][c] = ck[(size_t)q * ldw]; ++q; } else w[r][c] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < K1; ++r) { y[r] = ck[(size_t)q * ldw]; ++q; }
+#pragma unroll
+            for (int m = 0; m <= B; ++m) {
+                nh[m] = BSP_LDG(fbH + (size_t)(js + K1) * FS + m);
+                ns[m] = BSP_LDG(fbS + (size_t)(js + K1) * FS + m);
+                rq[m] = rhs(js + K1 + m);
+            }
+#pragma unroll 1
+            for (int blk = 0; blk < BSP_SEG_BLOCKS; ++blk) {
+                const int j0 = js + blk * K1;
+#pragma unroll
+                for (int t = 0; t < K1; ++t) {
+                    const int j = j0 + t;
+                    const double rnew = scr * rq[t];
+                    /* rows of the NEXT segment were already rewritten by its back sweep; they only feed
+                     * window entries that the next check-point supersedes, so any finite value will do */
+                    rq[t] = (j + 2 * K1 < js + T + K1) ? rhs(j + 2 * K1) : 0.0;
+                    double d = w[t][t];
+                    if (fabs(d) < pivmin) d = -pivmin;
+                    const double rinv = BSP_RCP(d);
+                    double col[K1], l[K1];
+                    const double y0 = y[t];
+                    double *srow_ = scratch[blk * K1 + t];
+                    xold[blk * K1 + t] = (corr_now && j < n) ? Xp[(size_t)j * ldw] : 0.0;
+                    srow_[0] = y0 * rinv;
+#pragma unroll
+                    for (int i = 1; i <= B; ++i) {
+                        col[i] = w[(t + i) % K1][t];
+                        l[i] = col[i] * rinv;
+                        srow_[i] = l[i];
+                        y[(t + i) % K1] = fma(-l[i], y0, y[(t + i) % K1]);
+                    }
+#pragma unroll
+                    for (int m = 1; m <= B; ++m) {
+#pragma unroll
+                        for (int i = m; i <= B; ++i) {
+                            w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
+                        }
+                    }
+                    {
+                        const double *hrow = fbH + (size_t)(j + K1 + 1) * FS;
+                        const double *srow = fbS + (size_t)(j + K1 + 1) * FS;
+#pragma unroll
+                        for (int m = 0; m <= B; ++m) {
+                            w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
+                            nh[m] = BSP_LDG(hrow + m);
+                            ns[m] = BSP_LDG(srow + m);
+                        }
+                    }
+                    y[t] = rnew;
+                }
+            }
+        }
+        /* ---- phase B: back substitution + matvecs over the segment, last row first ---- */
+#pragma unroll 1
+        for (int jj = T - 1; jj >= 0; --jj) back_step(js + jj, scratch[jj], xold[jj]);
+    }
+    {
+        const double zero[K1] = {0.0};
+#pragma unroll 1
+        for (int j = -1; j >= -B; --j) back_step(j, zero, 0.0);
     }
     /* bookkeeping + next shift */
     double lo = g.lo[id], hi = g.hi[id];

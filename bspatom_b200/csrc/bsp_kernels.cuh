@@ -72,6 +72,18 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) b
     bsp_back_substitute<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, corr_now, corr_next);
 }
 
+template <int B>
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_ckpt_kernel(BspEigChunk g, int iter)
+{
+    bsp_factor_checkpoint<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter);
+}
+
+template <int B>
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_back_rc_kernel(BspEigChunk g, int corr_now, int corr_next, int iter)
+{
+    bsp_back_recompute<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, corr_now, corr_next, iter);
+}
+
 __global__ void bsp_check_kernel(BspEigChunk g, int allow)
 {
     bsp_check_converged(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, allow);

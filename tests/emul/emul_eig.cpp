@@ -29,13 +29,21 @@ struct EmulExec {
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_refine_prepare(g, p, e, buf);
     }
+    int recompute = 0, cur_iter = 0;
     void factor(int it) {
+        cur_iter = it;
         for (int p = 0; p < g.npencil; ++p)
-            for (int e = 0; e < g.n; ++e) bsp_factor_forward<B>(g, p, e, it);
+            for (int e = 0; e < g.n; ++e) {
+                if (recompute) bsp_factor_checkpoint<B>(g, p, e, it);
+                else bsp_factor_forward<B>(g, p, e, it);
+            }
     }
     void back(int cn, int cx) {
         for (int p = 0; p < g.npencil; ++p)
-            for (int e = 0; e < g.n; ++e) bsp_back_substitute<B>(g, p, e, cn, cx);
+            for (int e = 0; e < g.n; ++e) {
+                if (recompute) bsp_back_recompute<B>(g, p, e, cn, cx, cur_iter);
+                else bsp_back_substitute<B>(g, p, e, cn, cx);
+            }
     }
     void check(int allow) {
         for (int p = 0; p < g.npencil; ++p)
@@ -54,7 +62,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     BspEigChunk g;
     memset(&g, 0, sizeof(g));
     g.n = n;
-    g.npad = ((n + K1 - 1) / K1) * K1;
+    g.npad = BSP_NPAD(n, B);
     g.nrows = BSP_NROWS(g.npad, B);
     g.xrows = g.npad + B + 1;
     g.ldw = ((n + 31) / 32) * 32;
@@ -88,7 +96,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     g.sigma = sigma.data(); g.rho = rho.data(); g.rho_prev = rho_prev.data(); g.scale = scale.data();
     g.res = res.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
     g.counters = counters.data(); g.tau = tau; g.delta_rel = delta_rel; g.conv_tol = conv_tol;
-    EmulExec<B> ex; ex.g = g;
+    EmulExec<B> ex; ex.g = g; ex.recompute = getenv("BSP_EMUL_RECOMPUTE") ? atoi(getenv("BSP_EMUL_RECOMPUTE")) : 0;
     BspSchedule sch = {max_rounds, min_iters, max_iters, 4, 1, 0};
     BspRunStats st = bsp_run_chunk(ex, sch);
     std::vector<double> fac(per);
@@ -119,7 +127,7 @@ extern "C" int emul_solve(int n, int B, int npencil, const double *hb, const dou
 template <int B> static int cnt(int n, const double *hb, const double *sb, double sigma)
 {
     constexpr int K1 = B + 1, FS = 2 * B + 2;
-    int npad = ((n + K1 - 1) / K1) * K1, nrows = BSP_NROWS(npad, B);
+    int npad = BSP_NPAD(n, B), nrows = BSP_NROWS(npad, B);
     std::vector<double> H((size_t)nrows * FS, 0.0), S((size_t)nrows * FS, 0.0);
     for (int i = 0; i < n; ++i)
         for (int d = 0; d <= B; ++d) {

@@ -110,3 +110,21 @@ def test_partial_vectors_still_give_all_eigenvalues(emul, oracle):
     w, v, _ = oracle.dsygv(H, m["S"])
     assert np.all(np.abs(E - w) <= np.maximum(1e-12 * np.abs(w), 1e-10))
     assert Cm.shape[1] == 5 and np.abs(np.abs(np.sum(Cm * (m["S"] @ v[:, :5]), 0)) - 1).max() < 1e-9
+
+
+def test_checkpointed_refinement_equals_stored_factor(oracle):
+    """the check-pointed sweeps (re-elimination in the back sweep) do the same arithmetic as the
+    stored-factor sweeps: bit-identical eigenpairs."""
+    import importlib
+
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=150, rb=80.0)
+    m = oracle.matrix_svt(b, lmax=1)
+    H = oracle.hamiltonian(m["T"], m["U"][:, :, 1], m["V"])
+    out = []
+    for mode in ("0", "1"):
+        os.environ["BSP_EMUL_RECOMPUTE"] = mode
+        lib = C.CDLL(SO)
+        lib.emul_solve.argtypes = [C.c_int] * 3 + [dp, dp, ip] + [C.c_double] * 3 + [C.c_int] * 3 + [dp] * 3
+        out.append(solve(lib, H, m["S"], 6))
+    os.environ.pop("BSP_EMUL_RECOMPUTE")
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
