@@ -131,10 +131,8 @@ int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf
     bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, ni), 128, 0, h->st>>>(n, kd, d_A, ni, d_Ci, d_Y);
     h->launches++;
     CU(cudaGetLastError());
-    bsp_dgemm_tn_kernel<<<dim3((nf + BSP_GT_M - 1) / BSP_GT_M, (ni + BSP_GT_N - 1) / BSP_GT_N), 128, 0, h->st>>>(
-        nf, ni, n, d_Cf, n, d_Y, n, d_D, nf);
+    CU(bsp_launch_dgemm_tn(h->st, nf, ni, n, d_Cf, n, d_Y, n, d_D, nf, 1, 0, 0, 0));
     h->launches++;
-    CU(cudaGetLastError());
     CU(cudaEventRecord(e1, h->st));
     CU(cudaMemcpyAsync(D, d_D, sizeof(double) * (size_t)nf * ni, cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
@@ -145,6 +143,50 @@ int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf
     dev_free(h, d_A, (size_t)ld * n); dev_free(h, d_Ci, (size_t)n * ni); dev_free(h, d_Y, (size_t)n * ni);
     dev_free(h, d_D, (size_t)nf * ni);
     if (!same) dev_free(h, d_Cf, (size_t)n * nf);
+    return 0;
+}
+
+/* D_l = C_{l+1}^T A C_l for l = 0..nl-2 in two launches (cfg5: all bound/continuum pairs of
+ * neighbouring angular momenta).  C_all: nl blocks n x nvec, D_all: nl-1 blocks nvec x nvec. */
+int bspatom_dipole_chain(bspatom_handle h, int n, int kd, const double *A_band, int nl, int nvec,
+                         const double *C_all, double *D_all)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (n < 1) return -2;
+    if (kd < 0 || kd >= n) return -3;
+    if (!A_band) return -4;
+    if (nl < 2) return -5;
+    if (nvec < 1) return -6;
+    if (!C_all) return -7;
+    if (!D_all) return -8;
+    const int ld = 2 * kd + 1;
+    const size_t blk = (size_t)n * nvec, dblk = (size_t)nvec * nvec;
+    double *d_A = nullptr, *d_C = nullptr, *d_Y = nullptr, *d_D = nullptr;
+    if ((rc = dev_alloc(h, &d_A, (size_t)ld * n))) return rc;
+    if ((rc = dev_alloc(h, &d_C, blk * nl))) return rc;
+    if ((rc = dev_alloc(h, &d_Y, blk * (nl - 1)))) return rc;
+    if ((rc = dev_alloc(h, &d_D, dblk * (nl - 1)))) return rc;
+    CU(cudaMemcpyAsync(d_A, A_band, sizeof(double) * (size_t)ld * n, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(d_C, C_all, sizeof(double) * blk * nl, cudaMemcpyHostToDevice, h->st));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, h->st));
+    bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, nvec, nl - 1), 128, 0, h->st>>>(n, kd, d_A, nvec, d_C, d_Y);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(bsp_launch_dgemm_tn(h->st, nvec, nvec, n, d_C + blk, n, d_Y, n, d_D, nvec, nl - 1, (long long)blk, (long long)blk,
+                           (long long)dblk));
+    h->launches++;
+    CU(cudaEventRecord(e1, h->st));
+    CU(cudaMemcpyAsync(D_all, d_D, sizeof(double) * dblk * (nl - 1), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    h->stats[0] = 2; h->stats[7] = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dev_free(h, d_A, (size_t)ld * n); dev_free(h, d_C, blk * nl); dev_free(h, d_Y, blk * (nl - 1));
+    dev_free(h, d_D, dblk * (nl - 1));
     return 0;
 }
 

@@ -12,7 +12,9 @@
 #include <cuda_runtime.h>
 #include "bsp_core.h"
 
+#ifndef BSP_EIG_THREADS
 #define BSP_EIG_THREADS 128
+#endif
 
 /* resident blocks per SM the register allocator is asked to allow, by half bandwidth:
  * the pivot window is (B+1)(B+2)/2 doubles, so wide bands get fewer blocks instead of spills */
@@ -25,7 +27,9 @@
 #ifndef BSP_MINB_BACK
 #define BSP_MINB_BACK 4
 #endif
-constexpr int bsp_minb(int base, int B) { return B <= 6 ? base : (B == 7 ? (base > 3 ? 3 : base) : 2); }
+constexpr int bsp_minb_128(int base, int B) { return B <= 6 ? base : (B == 7 ? (base > 3 ? 3 : base) : 2); }
+/* `base` counts blocks of 128 threads; larger blocks keep the same number of resident warps */
+constexpr int bsp_minb(int base, int B) { return (bsp_minb_128(base, B) * 128) / BSP_EIG_THREADS > 0 ? (bsp_minb_128(base, B) * 128) / BSP_EIG_THREADS : 1; }
 
 template <int B>
 __global__ void __launch_bounds__(BSP_NCAND) bsp_bounds_kernel(BspEigChunk g, double *cand_s, int *cand_c)

@@ -390,6 +390,26 @@ class BspAtom(BspInputs):
         return D
 
 
+def _dipole_chain(self, A_band: np.ndarray, C_blocks) -> np.ndarray:
+    """D[l] = C[l+1]^T A C[l] for all neighbouring l in two launches (cfg5).  C_blocks: sequence of
+    (n, nvec) arrays (e.g. BspAtom.cinl); returns (nl-1, nvec, nvec) with D[l] Fortran-ordered blocks."""
+    A_band = np.asfortranarray(A_band, dtype=np.float64)
+    nl = len(C_blocks)
+    n, nvec = C_blocks[0].shape
+    kd = (A_band.shape[0] - 1) // 2
+    C_all = np.empty((nl, nvec, n))
+    for l, Cm in enumerate(C_blocks):
+        C_all[l] = np.asarray(Cm, dtype=np.float64).T      # block l column-major n x nvec
+    D = np.empty((nl - 1, nvec, nvec))
+    rc = self.lib.bspatom_dipole_chain(self._h, n, kd, A_band.ctypes.data_as(C.c_void_p), nl, nvec,
+                                       C_all.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p))
+    _lib.check(self.lib, self._h, rc, "bspatom_dipole_chain")
+    return np.transpose(D, (0, 2, 1))                       # D[l][f, i]
+
+
+BspAtom.dipole_chain = _dipole_chain
+
+
 def pinned_empty(count: int) -> np.ndarray:
     """float64 array in page-locked host memory (bspatom_alloc_host): results written into it by
     solve_batch stream out chunk by chunk while the GPU keeps computing."""

@@ -131,6 +131,12 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
 int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf, const double *Cf,
                    int ni, const double *Ci, double *D);
 
+/* all neighbouring-l blocks at once (BASELINE cfg5): D_l = C_{l+1}^T A C_l, l = 0..nl-2.
+ * C_all: nl column-major blocks n x nvec back to back (cinl(:,:,l), matrices.f90:369-373);
+ * D_all: nl-1 column-major blocks nvec x nvec.                                  */
+int bspatom_dipole_chain(bspatom_handle h, int n, int kd, const double *A_band, int nl, int nvec,
+                         const double *C_all, double *D_all);
+
 /* ---- wavefunction synthesis: WRITE_WF (Bsp_Atom.f90:101-152) --------------- *
  * psi(ip, iv) = sum_j C(j,iv) B_j(r_ip), r_ip = ra + ip (rb-ra)/npts, ip=0..npts */
 int bspatom_wavefunction(bspatom_handle h, int k, int nfun, int nkp, const double *rt, double ra,

@@ -1,6 +1,6 @@
-for V in "" _v2 _v3; do
+for V in _v2 _v3; do
 echo "== variant $V"
-BSPATOM_LIB=$PWD/bspatom_b200/libbspatom$V.so python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --recompute 1 > gpurun_out/d2.json 2> gpurun_out/d2.err
+BSPATOM_LIB=$PWD/bspatom_b200/libbspatom$V.so python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/d2.json 2> gpurun_out/d2.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/d2.json"))

@@ -49,6 +49,21 @@ def test_dipole_velocity_form_nonsymmetric_operator(atom, oracle):
     assert np.max(np.abs(D - ref)) < 1e-12 * np.linalg.norm(Cf, axis=0).max() * np.linalg.norm(A @ Ci, axis=0).max()
 
 
+def test_dipole_chain_equals_pairwise(atom, oracle):
+    """bspatom_dipole_chain: all neighbouring-l blocks in two launches (cfg5) = pair-by-pair calls."""
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=160, rb=80.0)
+    m = oracle.matrix_svt(b, lmax=3)
+    Cs = [oracle.solve_system(m, l)[1][:, :90] for l in range(4)]
+    Rb = general_band(m["R"], 6)
+    D = atom.dipole_chain(Rb, Cs)
+    assert D.shape == (3, 90, 90)
+    for l in range(3):
+        ref = atom.dipole(Rb, Cs[l + 1], Cs[l])
+        assert np.array_equal(D[l], ref)
+        exact = Cs[l + 1].T @ (m["R"] @ Cs[l])
+        assert np.max(np.abs(D[l] - exact)) < 1e-12 * np.abs(exact).max()
+
+
 def test_dipole_ragged_tiles(atom):
     rng = np.random.default_rng(5)
     n, kd = 203, 3
