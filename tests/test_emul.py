@@ -128,3 +128,14 @@ def test_checkpointed_refinement_equals_stored_factor(oracle):
         out.append(solve(lib, H, m["S"], 6))
     os.environ.pop("BSP_EMUL_RECOMPUTE")
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_tiny_bases(emul, oracle):
+    for k, nfun in ((7, 8), (3, 4), (10, 12)):
+        b = oracle.make_basis(kind_grid=0, k=k, nfun=nfun, rb=20.0)
+        m = oracle.matrix_svt(b, lmax=1)
+        H = oracle.hamiltonian(m["T"], m["U"][:, :, 1], m["V"])
+        E, Cm, st = solve(emul, H, m["S"], k - 1)
+        w, v, _ = oracle.dsygv(H, m["S"])
+        assert np.all(np.abs(E - w) <= np.maximum(1e-12 * np.abs(w), 1e-10)), (k, nfun)
+        assert st[3] == 0 and st[5] == 0

@@ -217,3 +217,44 @@ def test_dsygv_entry_is_a_drop_in(atom, oracle):
     assert info == b.nfun + 11
     _, _, _, info = bsp.dsygv(np.ones((40, 40)), np.eye(40))
     assert info == -5                                              # not banded
+
+
+def test_empty_batch_and_tiny_problems(atom, oracle):
+    """edge cases: an empty work list; bases smaller than one elimination block; a single function."""
+    Es, Cs, info = atom.solve_batch([])
+    assert Es == [] and Cs == [] and info.size == 0
+    for k, nfun in ((7, 8), (3, 4), (5, 6), (10, 12)):
+        a = host_basis(kind_grid=0, k=k, nfun=nfun, rb=20.0)
+        b, H, S = oracle_pencil(oracle, a, nfun, 1)
+        w, v, _ = oracle.dsygv(H, S)
+        Es, Cs, inf = atom.solve_batch([(a.problem(), 1)])
+        assert inf[0] == 0
+        assert np.all(np.abs(Es[0] - w) <= eig_tolerance(w)), (k, nfun)
+        check_eigenpairs(Es[0], Cs[0], H, S, res_tol=1e-11, orth_tol=1e-9)
+
+
+@pytest.mark.parametrize("k,nfun,grid", [(3, 300, 0), (4, 257, 1), (9, 200, 0), (10, 180, 0)])
+def test_other_orders_solve(atom, oracle, k, nfun, grid):
+    a = host_basis(kind_grid=grid, k=k, nfun=nfun, rb=100.0, zatom=2.0)
+    b, H, S = oracle_pencil(oracle, a, nfun, 2, par=oracle.pot_params(0, 2.0))
+    w, v, _ = oracle.dsygv(H, S)
+    p = a.problem()
+    p.xg, p.wg = b.xg, b.wg
+    Es, Cs, inf = atom.solve_batch([(p, 2)])
+    assert inf[0] == 0
+    assert np.all(np.abs(Es[0] - w) <= eig_tolerance(w)), np.max(np.abs(Es[0] - w) / eig_tolerance(w))
+    check_eigenpairs(Es[0], Cs[0], H, S, res_tol=1e-11, orth_tol=1e-9)
+
+
+def test_check_pointed_refinement_option_is_bit_identical(atom):
+    """option `recompute` (check-pointed sweeps, off by default) must reproduce the stored-factor results."""
+    a = host_basis(kind_grid=0, k=7, nfun=260, rb=130.0)
+    items = [(a.problem(), l) for l in range(3)]
+    E0, C0, _ = atom.solve_batch(items)
+    atom.set_option("recompute", 1)
+    try:
+        E1, C1, _ = atom.solve_batch(items)
+    finally:
+        atom.set_option("recompute", 0)
+    for x, y in zip(E0 + C0, E1 + C1):
+        assert np.array_equal(x, y)
