@@ -47,6 +47,7 @@ struct Options {
     int check_every = 2;
     int chunk = 0; /* 0 = auto */
     int workers = 2; /* concurrent chunk streams (1..4) */
+    int stream_chunks = 8; /* chunks per group when results stream to the host */
     int recompute = 0; /* 1: check-pointed refinement (re-eliminate in the back sweep; measured slower, see
                           DESIGN.md section 12), 0: store the factor */
 };
@@ -682,6 +683,7 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "check_every") h->opt.check_every = std::max(1, (int)v);
     else if (s == "chunk") h->opt.chunk = (int)v;
     else if (s == "recompute") { h->opt.recompute = v != 0.0; for (auto &G : h->groups) G.chunk_cached = 0; }
+    else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
     else if (s == "workers") h->opt.workers = std::min(4, std::max(1, (int)v));
     else return -2;
     return 0;
@@ -884,7 +886,8 @@ struct WorkerAcc {
 
 /* one worker = one context (stream, workspace, polling word): pulls chunks off the queue */
 void chunk_worker(bspatom_handle main_h, bspatom_handle hw, Group *G, int chunk, std::atomic<int> *next,
-                  int nchunks, double *E_out, double *C_out, cudaEvent_t asm_done, WorkerAcc *acc)
+                  int nchunks, double *E_out, double *C_out, cudaEvent_t asm_done, WorkerAcc *acc,
+                  const std::vector<int> *bounds)
 {
     bspatom_handle h = hw; /* CU() reports into the worker's own context */
     auto body = [&]() -> int {
@@ -898,8 +901,8 @@ void chunk_worker(bspatom_handle main_h, bspatom_handle hw, Group *G, int chunk,
         for (;;) {
             const int ci = next->fetch_add(1);
             if (ci >= nchunks) break;
-            const int p0 = ci * chunk;
-            const int np = std::min(chunk, G->npencil - p0);
+            const int p0 = (*bounds)[ci];
+            const int np = (*bounds)[ci + 1] - p0;
             BspRunStats st;
             if ((rc = run_chunk(h, *G, p0, np, c, st, tm))) break;
             if (E_out || C_out) {
@@ -992,12 +995,33 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             /* equal chunks; one per worker, and at least 4 when results stream to the host (if each
              * still fills the GPU) so that the D2H of a finished chunk hides behind the others */
             int want = workers;
-            if (E_out || C_out) want = std::max(want, std::min(8, std::max(1, (2 * G.npencil) / fill_pencils)));
+            if (E_out || C_out) want = std::max(want, std::min(h->opt.stream_chunks, std::max(1, (2 * G.npencil) / fill_pencils)));
             nchunks = std::max(nchunks, want);
         }
         chunk = (G.npencil + nchunks - 1) / nchunks;
         nchunks = (G.npencil + chunk - 1) / chunk;
         workers = std::min(workers, nchunks);
+        /* chunk boundaries.  When results stream to the host the chunks shrink towards the end
+         * (weights 6,5,4,3,... over the same number of chunks): the copies start as early as before,
+         * but the last chunks -- whose copies nothing can hide -- are small. */
+        std::vector<int> bounds(1, 0);
+        if ((E_out || C_out) && h->opt.chunk <= 0 && nchunks >= 4) {
+            std::vector<double> wgt(nchunks);
+            double tot = 0.0;
+            for (int i = 0; i < nchunks; ++i) { wgt[i] = (double)(nchunks + 2 - i); tot += wgt[i]; }
+            double accw = 0.0;
+            for (int i = 0; i < nchunks; ++i) {
+                accw += wgt[i];
+                int b = (i + 1 == nchunks) ? G.npencil : (int)(G.npencil * accw / tot + 0.5);
+                b = std::max(b, bounds.back() + 1);
+                b = std::min(b, G.npencil - (nchunks - 1 - i));
+                bounds.push_back(b);
+            }
+            chunk = 0;
+            for (int i = 0; i < nchunks; ++i) chunk = std::max(chunk, bounds[i + 1] - bounds[i]);
+        } else {
+            for (int i = 1; i <= nchunks; ++i) bounds.push_back(std::min(i * chunk, G.npencil));
+        }
         const size_t need = carve_chunk(G, chunk, nullptr, c, h->opt.recompute != 0);
         if ((rc = ensure_workspace(h, need))) return rc;
         while ((int)h->aux.size() < workers - 1) {
@@ -1014,8 +1038,8 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         {
             std::vector<std::thread> th;
             for (int w = 1; w < workers; ++w)
-                th.emplace_back(chunk_worker, h, h->aux[w - 1], &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[w]);
-            chunk_worker(h, h, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[0]);
+                th.emplace_back(chunk_worker, h, h->aux[w - 1], &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[w], &bounds);
+            chunk_worker(h, h, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[0], &bounds);
             for (auto &t : th) t.join();
             CU(cudaSetDevice(h->dev));
         }
