@@ -349,9 +349,9 @@ def main():
         ncu = json.load(open(os.path.join(ROOT, "profiles", "roofline_r1.json")))
     except Exception:
         pass
-    launches = k1cnt[dom] / args.steps
+    dom_launches = k1cnt[dom] / args.steps
     avg_ms = k1ms[dom] / max(k1cnt[dom], 1)
-    full_launches = min(launches, it1) if it1 else launches   # launches after the scheduled ones only touch stragglers
+    full_launches = min(dom_launches, it1) if it1 else dom_launches   # later launches only touch stragglers
     bytes_per_launch = nsolve * NFUN * per_pair[dom_name]
     ach = bytes_per_launch * full_launches / (k1ms[dom] / args.steps * 1e-3) / 1e9
     traffic = None
@@ -361,7 +361,7 @@ def main():
     roofline = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
-                "launches_per_step": launches, "share_of_step": float(share[dom]),
+                "launches_per_step": dom_launches, "share_of_step": float(share[dom]),
                 "how": "single chunk stream, %d pencils per launch, CUDA events around every launch; traffic = "
                        "dram__bytes_read+write of one `ncu --set full` launch of %s pencils scaled to %d"
                        % (nsolve, nk["pencils_per_launch"] if nk else "n/a", nsolve),

@@ -10,7 +10,7 @@ python profiles/run_configs.py cfg3 cfg4 cfg5 > gpurun_out/configs_r1.jsonl 2> g
 # launch list of one full-size step (1 chunk stream so that launches are in program order)
 BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --workers 1"
 $BENCH > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 93 -c 31 --csv --log-file gpurun_out/launches_r1.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 189 -c 63 --csv --log-file gpurun_out/launches_r1.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
 echo launches_rc=$?
 # full counters of the three hot kernels, half-size step (204 pencils, ~2.8 waves)
 BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --workers 1 --zrep 4"
