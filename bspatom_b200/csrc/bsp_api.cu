@@ -15,10 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
-#include <atomic>
 #include <chrono>
 #include <mutex>
-#include <thread>
 #include <map>
 #include <string>
 #include <vector>
@@ -40,11 +38,10 @@ struct Options {
     double delta_rel = 1e-4;
     double conv_tol = 1e-11;
     double res_tol = 1e-9;
-    int max_rounds = 90;
+    int max_rounds = 90;      /* cap used when a chunk has to be redone */
+    int rounds_enqueued = 26; /* bracketing rounds enqueued up front (surplus ones return at once) */
     int min_iters = 3;
     int max_iters = 12;
-    int first_check_round = 10;
-    int check_every = 2;
     int chunk = 0; /* 0 = auto */
     int workers = 2; /* concurrent chunk streams (1..4) */
     int stream_chunks = 8; /* chunks per group when results stream to the host */
@@ -358,6 +355,9 @@ struct GpuExec {
     BspEigChunk g;
     double *cand_s;
     int *cand_c;
+    int open_ok = 0;
+    int cur_iter = 0;
+    cudaEvent_t ev_refine = nullptr; /* recorded between the bracketing and the refinement */
     cudaError_t first_err = cudaSuccess;
     dim3 grid() const { return dim3((g.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS, g.npencil); }
     void note() {
@@ -369,45 +369,31 @@ struct GpuExec {
         bsp_bounds_kernel<B><<<g.npencil, BSP_NCAND, 0, h->st>>>(g, cand_s, cand_c); note();
         bsp_bounds_pick_kernel<<<(g.npencil + 127) / 128, 128, 0, h->st>>>(g, cand_s, cand_c); note();
     }
-    void round(int r) {
+    void round(int r, int max_rounds) {
         const int s = timed_begin(h, 0);
-        bsp_round_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, r); note();
+        bsp_round_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, r, max_rounds, open_ok); note();
         timed_end(h, s);
     }
-    void prepare(int buf) { bsp_prepare_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, buf); note(); }
-    int cur_iter = 0;
-    void factor(int it) {
+    void prepare() {
+        if (ev_refine) cudaEventRecord(ev_refine, h->st);
+        bsp_prepare_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g); note();
+    }
+    void factor(int it, int optional) {
         cur_iter = it;
         const int s = timed_begin(h, 1);
-        if (h->opt.recompute) bsp_factor_ckpt_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it);
-        else bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it);
+        if (h->opt.recompute) bsp_factor_ckpt_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional);
+        else bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional);
         note();
         timed_end(h, s);
     }
-    void back(int cn, int cx) {
+    void back(int cn, int cx, int optional) {
         const int s = timed_begin(h, 2);
-        if (h->opt.recompute) bsp_back_rc_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx, cur_iter);
-        else bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx);
+        if (h->opt.recompute) bsp_back_rc_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx, cur_iter, optional);
+        else bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx, optional);
         note();
         timed_end(h, s);
     }
-    void check(int allow) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, allow); note(); }
-    void zero_counter(int w) {
-        /* a kernel, not cudaMemsetAsync: nothing on the compute stream may queue on a copy engine
-         * that is busy streaming results to the host */
-        bsp_zero_counter_kernel<<<1, 1, 0, h->st>>>(g.counters + w);
-        note();
-        if (w == 0) { bsp_zero_counter_kernel<<<1, 1, 0, h->st>>>(g.counters + 2); note(); }
-    }
-    int read_counter(int w) {
-        bsp_publish_counter_kernel<<<1, 1, 0, h->st>>>(g.counters + w, h->h_counter_dev);
-        h->launches++;
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
-        if (e != cudaSuccess) { if (first_err == cudaSuccess) first_err = e; return 0; }
-        if (getenv("BSPATOM_DEBUG_COUNTERS")) fprintf(stderr, "[bspatom] counter %d = %d\n", w, *h->h_counter);
-        return *h->h_counter;
-    }
+    void check(int it) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it); note(); }
 };
 
 struct ChunkTimes {
@@ -457,10 +443,14 @@ size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c, bool recomp
     return cv.used;
 }
 
+/* Enqueue the whole stage schedule of pencils [p0, p0+np) of G on h's stream: no host read-back.
+ * report: BSP_C_WORDS ints on the device that receive the chunk's control block at the end. */
 template <int B>
-int run_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, BspRunStats &st, ChunkTimes &tm)
+int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, const BspSchedule &sch,
+                    ChunkTimes &tm, int *report)
 {
     const size_t per_mat = (size_t)G.nrows * G.FS;
+    CU(cudaEventRecord(tm.ev[0], h->st));
     {
         dim3 grid((unsigned)((per_mat + 255) / 256), np);
         bsp_combine_kernel<<<grid, 256, 0, h->st>>>(c.fbH, G.d_fbH0, G.d_fbQ, G.d_inst + p0, G.d_cl + p0, per_mat);
@@ -478,21 +468,13 @@ int run_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, 
     g.status = c.status; g.L = c.L; g.X = c.X; g.R = c.R; g.counters = c.counters;
     g.tau = h->opt.tau; g.delta_rel = h->opt.delta_rel; g.conv_tol = h->opt.conv_tol;
 
-    /* the driver runs bounds+rounds, then the refinement; we want a time stamp
-     * between the two, so wrap the executor */
-    struct Timed : GpuExec<B> {
-        ChunkTimes *tm;
-        void prepare(int buf) {
-            cudaEventRecord(tm->ev[1], this->h->st);
-            GpuExec<B>::prepare(buf);
-        }
-    } ex;
-    ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.tm = &tm;
-    CU(cudaEventRecord(tm.ev[0], h->st));
+    GpuExec<B> ex;
+    ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.ev_refine = tm.ev[1];
     /* a few stragglers per hundred thousand eigenpairs are cheaper to finish inside the refinement */
-    const int open_ok = (int)((long long)np * G.n / 20000);
-    BspSchedule sch = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters, h->opt.first_check_round, h->opt.check_every, open_ok};
-    st = bsp_run_chunk(ex, sch);
+    ex.open_ok = (int)((long long)np * G.n / 20000);
+    bsp_zero_words_kernel<<<1, 32, 0, h->st>>>(c.counters, BSP_C_WORDS);
+    h->launches++;
+    bsp_enqueue_chunk(ex, sch);
     if (ex.first_err != cudaSuccess) {
         h->err = std::string("eigen stage: ") + cudaGetErrorString(ex.first_err);
         return BSPATOM_ECUDA;
@@ -511,22 +493,26 @@ int run_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, 
             h->launches++;
             CU(cudaGetLastError());
         }
+        bsp_report_kernel<<<1, 32, 0, h->st>>>(g, report);
+        h->launches++;
+        CU(cudaGetLastError());
     }
     CU(cudaEventRecord(tm.ev[3], h->st));
     return 0;
 }
 
-int run_chunk(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, BspRunStats &st, ChunkTimes &tm)
+int enqueue_chunk(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs &c, const BspSchedule &sch,
+                  ChunkTimes &tm, int *report)
 {
     switch (G.B) {
-    case 2: return run_chunk_b<2>(h, G, p0, np, c, st, tm);
-    case 3: return run_chunk_b<3>(h, G, p0, np, c, st, tm);
-    case 4: return run_chunk_b<4>(h, G, p0, np, c, st, tm);
-    case 5: return run_chunk_b<5>(h, G, p0, np, c, st, tm);
-    case 6: return run_chunk_b<6>(h, G, p0, np, c, st, tm);
-    case 7: return run_chunk_b<7>(h, G, p0, np, c, st, tm);
-    case 8: return run_chunk_b<8>(h, G, p0, np, c, st, tm);
-    case 9: return run_chunk_b<9>(h, G, p0, np, c, st, tm);
+    case 2: return enqueue_chunk_b<2>(h, G, p0, np, c, sch, tm, report);
+    case 3: return enqueue_chunk_b<3>(h, G, p0, np, c, sch, tm, report);
+    case 4: return enqueue_chunk_b<4>(h, G, p0, np, c, sch, tm, report);
+    case 5: return enqueue_chunk_b<5>(h, G, p0, np, c, sch, tm, report);
+    case 6: return enqueue_chunk_b<6>(h, G, p0, np, c, sch, tm, report);
+    case 7: return enqueue_chunk_b<7>(h, G, p0, np, c, sch, tm, report);
+    case 8: return enqueue_chunk_b<8>(h, G, p0, np, c, sch, tm, report);
+    case 9: return enqueue_chunk_b<9>(h, G, p0, np, c, sch, tm, report);
     default: return BSPATOM_EUNSUPPORTED;
     }
 }
@@ -679,8 +665,8 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "max_rounds") h->opt.max_rounds = (int)v;
     else if (s == "min_iters") h->opt.min_iters = std::max(3, (int)v);
     else if (s == "max_iters") h->opt.max_iters = std::max(3, (int)v);
-    else if (s == "first_check_round") h->opt.first_check_round = std::max(1, (int)v);
-    else if (s == "check_every") h->opt.check_every = std::max(1, (int)v);
+    else if (s == "rounds_enqueued") h->opt.rounds_enqueued = std::max(1, (int)v);
+    else if (s == "first_check_round" || s == "check_every") { /* accepted for compatibility: the schedule no longer polls */ }
     else if (s == "chunk") h->opt.chunk = (int)v;
     else if (s == "recompute") { h->opt.recompute = v != 0.0; for (auto &G : h->groups) G.chunk_cached = 0; }
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
@@ -878,67 +864,27 @@ int launch_pdcheck(bspatom_handle h, Group &G)
     }
 }
 
-/* per-worker accumulators of one run */
-struct WorkerAcc {
-    double t_val = 0, t_vec = 0, t_fin = 0;
-    int rounds = 0, iters = 0, rc = 0;
-};
-
-/* one worker = one context (stream, workspace, polling word): pulls chunks off the queue */
-void chunk_worker(bspatom_handle main_h, bspatom_handle hw, Group *G, int chunk, std::atomic<int> *next,
-                  int nchunks, double *E_out, double *C_out, cudaEvent_t asm_done, WorkerAcc *acc,
-                  const std::vector<int> *bounds)
+BspRunStats stats_from_report(const int *r)
 {
-    bspatom_handle h = hw; /* CU() reports into the worker's own context */
-    auto body = [&]() -> int {
-        CU(cudaSetDevice(h->dev));
-        CU(cudaStreamWaitEvent(h->st, asm_done, 0));
-        ChunkPtrs c;
-        carve_chunk(*G, chunk, h->ws.base, c, main_h->opt.recompute != 0);
-        ChunkTimes tm;
-        for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tm.ev[i]));
-        int rc = 0;
-        for (;;) {
-            const int ci = next->fetch_add(1);
-            if (ci >= nchunks) break;
-            const int p0 = (*bounds)[ci];
-            const int np = (*bounds)[ci + 1] - p0;
-            BspRunStats st;
-            if ((rc = run_chunk(h, *G, p0, np, c, st, tm))) break;
-            if (E_out || C_out) {
-                std::lock_guard<std::mutex> lk(main_h->mu);
-                cudaEvent_t e;
-                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { rc = BSPATOM_ECUDA; break; }
-                main_h->chunk_done.push_back(e);
-                cudaEventRecord(e, h->st);
-                cudaStreamWaitEvent(main_h->st_copy, e, 0);
-                bspatom_handle hm = main_h;
-                {
-                    bspatom_handle h = hm; /* copies are enqueued on the main context's copy stream */
-                    rc = copy_chunk_out(h, *G, p0, np, E_out, C_out);
-                }
-                if (rc) break;
-            }
-            CU(cudaStreamSynchronize(h->st));
-            timed_collect(h);
-            float ms = 0;
-            acc->rounds = std::max(acc->rounds, st.rounds);
-            acc->iters = std::max(acc->iters, st.iters);
-            CU(cudaEventElapsedTime(&ms, tm.ev[0], tm.ev[1])); acc->t_val += ms;
-            CU(cudaEventElapsedTime(&ms, tm.ev[1], tm.ev[2])); acc->t_vec += ms;
-            CU(cudaEventElapsedTime(&ms, tm.ev[2], tm.ev[3])); acc->t_fin += ms;
-        }
-        cudaStreamSynchronize(h->st);
-        for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
-        return rc;
-    };
-    acc->rc = body();
+    BspRunStats st = {r[BSP_C_ROUNDS], r[BSP_C_ITERS], r[BSP_C_OPEN_END], r[BSP_C_CROWDED_END], r[BSP_C_UNCONV_END]};
+    return st;
 }
 
-/* E_out / C_out: pinned host buffers (or NULL).  When given, each chunk's results are copied out on
- * st_copy as soon as the chunk is final, overlapping the kernels of the chunks still in flight.
- * Chunks are pulled by up to two workers (contexts with their own stream and workspace) so that two
- * chunks execute concurrently. */
+/* enqueue (on the copy stream, after the chunk's own stream reached this point) the D2H of a chunk */
+int stream_chunk_out(bspatom_handle h, bspatom_handle ctx, Group &G, int p0, int np, double *E_out, double *C_out)
+{
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->chunk_done.push_back(e);
+    CU(cudaEventRecord(e, ctx->st));
+    CU(cudaStreamWaitEvent(h->st_copy, e, 0));
+    return copy_chunk_out(h, G, p0, np, E_out, C_out);
+}
+
+/* E_out / C_out: pinned host buffers (or NULL).  Every chunk's whole schedule is enqueued up front on one
+ * of `workers` streams (each with its own workspace) -- the host reads nothing back while the batch runs,
+ * so the GPU never waits for it and the chunk streams back-fill each other's tail waves.  When E_out / C_out
+ * are given, each chunk's results are copied out on st_copy as soon as the chunk is final. */
 int run_internal(bspatom_handle h, double *E_out, double *C_out)
 {
     int rc = 0;
@@ -951,10 +897,13 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     for (auto e : h->chunk_done) cudaEventDestroy(e);
     h->chunk_done.clear();
     double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0;
-    int rounds = 0, iters = 0;
+    int rounds = 0, iters = 0, redone = 0;
     cudaEvent_t e0, e1, e2;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
     CU(cudaEventRecord(e0, h->st));
+    const BspSchedule sch = {std::min(h->opt.rounds_enqueued, h->opt.max_rounds), h->opt.min_iters,
+                             std::min(h->opt.max_iters, h->opt.min_iters + 2)};
+    const BspSchedule sch_redo = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters};
     for (auto &G : h->groups) {
         /* ---- assembly, once per instance ---- */
         CU(cudaEventRecord(e1, h->st));
@@ -972,7 +921,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         if ((rc = launch_pdcheck(h, G))) return rc;
         CU(cudaMemsetAsync(G.d_bad, 0, sizeof(int) * G.npencil, h->st));
         CU(cudaEventRecord(e2, h->st));
-        /* ---- eigen stages: chunk queue ---- */
+        /* ---- chunking ---- */
         ChunkPtrs c;
         const size_t per_pencil = carve_chunk(G, 1, nullptr, c, h->opt.recompute != 0);
         const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
@@ -992,8 +941,8 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         chunk = std::min(chunk, G.npencil);
         int nchunks = (G.npencil + chunk - 1) / chunk;
         if (h->opt.chunk <= 0) {
-            /* equal chunks; one per worker, and at least 4 when results stream to the host (if each
-             * still fills the GPU) so that the D2H of a finished chunk hides behind the others */
+            /* equal chunks; one per stream, and more when results go to the host (if each still fills
+             * the GPU) so that the D2H of a finished chunk hides behind the others */
             int want = workers;
             if (E_out || C_out) want = std::max(want, std::min(h->opt.stream_chunks, std::max(1, (2 * G.npencil) / fill_pencils)));
             nchunks = std::max(nchunks, want);
@@ -1002,7 +951,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         nchunks = (G.npencil + chunk - 1) / chunk;
         workers = std::min(workers, nchunks);
         /* chunk boundaries.  When results stream to the host the chunks shrink towards the end
-         * (weights 6,5,4,3,... over the same number of chunks): the copies start as early as before,
+         * (weights n+2, n+1, ... over the same number of chunks): the copies start as early as before,
          * but the last chunks -- whose copies nothing can hide -- are small. */
         std::vector<int> bounds(1, 0);
         if ((E_out || C_out) && h->opt.chunk <= 0 && nchunks >= 4) {
@@ -1029,29 +978,72 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             if (!x) { h->err = "cannot create a helper chunk stream"; return BSPATOM_ECUDA; }
             h->aux.push_back(x);
         }
+        std::vector<bspatom_handle> ctx(1, h);
         for (int w = 1; w < workers; ++w) {
             h->aux[w - 1]->opt = h->opt;
             if ((rc = ensure_workspace(h->aux[w - 1], need, h))) { h->err = h->aux[w - 1]->err; return rc; }
+            CU(cudaStreamWaitEvent(h->aux[w - 1]->st, e2, 0));     /* after the assembly */
+            ctx.push_back(h->aux[w - 1]);
         }
-        std::atomic<int> next(0);
-        WorkerAcc acc[4];
-        {
-            std::vector<std::thread> th;
-            for (int w = 1; w < workers; ++w)
-                th.emplace_back(chunk_worker, h, h->aux[w - 1], &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[w], &bounds);
-            chunk_worker(h, h, &G, chunk, &next, nchunks, E_out, C_out, e2, &acc[0], &bounds);
-            for (auto &t : th) t.join();
-            CU(cudaSetDevice(h->dev));
+        /* ---- enqueue every chunk; no host read-back in here ---- */
+        int *d_report = nullptr;
+        if ((rc = dev_alloc(h, &d_report, (size_t)nchunks * BSP_C_WORDS))) return rc;
+        std::vector<ChunkTimes> tms(nchunks);
+        for (int ci = 0; ci < nchunks; ++ci)
+            for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tms[ci].ev[i]));
+        std::vector<long long> load(workers, 0);      /* pencils assigned to each stream so far */
+        for (int ci = 0; ci < nchunks; ++ci) {
+            int wsel = 0;
+            for (int w = 1; w < workers; ++w) if (load[w] < load[wsel]) wsel = w;
+            load[wsel] += bounds[ci + 1] - bounds[ci];
+            bspatom_handle x = ctx[wsel];
+            ChunkPtrs cc;
+            carve_chunk(G, chunk, x->ws.base, cc, h->opt.recompute != 0);
+            const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
+            if ((rc = enqueue_chunk(x, G, p0, np, cc, sch, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) {
+                if (x != h) h->err = x->err;
+                return rc;
+            }
+            if (E_out || C_out)
+                if ((rc = stream_chunk_out(h, x, G, p0, np, E_out, C_out))) return rc;
         }
-        for (int w = 0; w < workers; ++w) {
-            if (acc[w].rc) { if (w >= 1) h->err = h->aux[w - 1]->err; return acc[w].rc; }
-            t_val += acc[w].t_val; t_vec += acc[w].t_vec; t_fin += acc[w].t_fin;
-            rounds = std::max(rounds, acc[w].rounds); iters = std::max(iters, acc[w].iters);
+        for (auto x : ctx) CU(cudaStreamSynchronize(x->st));
+        /* ---- reports; chunks that ran out of rounds / iterations are redone with the full limits ---- */
+        std::vector<int> report((size_t)nchunks * BSP_C_WORDS);
+        CU(cudaMemcpy(report.data(), d_report, report.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int ci = 0; ci < nchunks; ++ci) {
+            BspRunStats st = stats_from_report(&report[(size_t)ci * BSP_C_WORDS]);
+            const bool again = (st.brackets_crowded > 0 || st.unconverged > 0) &&
+                               (sch.rounds < sch_redo.rounds || sch.max_iters < sch_redo.max_iters);
+            if (again) {
+                ++redone;
+                ChunkPtrs cc;
+                carve_chunk(G, chunk, h->ws.base, cc, h->opt.recompute != 0);
+                const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
+                CU(cudaMemsetAsync(G.d_bad + p0, 0, sizeof(int) * np, h->st));
+                if ((rc = enqueue_chunk(h, G, p0, np, cc, sch_redo, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) return rc;
+                if (E_out || C_out)
+                    if ((rc = stream_chunk_out(h, h, G, p0, np, E_out, C_out))) return rc;
+                CU(cudaStreamSynchronize(h->st));
+                CU(cudaMemcpy(&report[(size_t)ci * BSP_C_WORDS], d_report + (size_t)ci * BSP_C_WORDS, BSP_C_WORDS * sizeof(int),
+                              cudaMemcpyDeviceToHost));
+                st = stats_from_report(&report[(size_t)ci * BSP_C_WORDS]);
+            }
+            rounds = std::max(rounds, st.rounds);
+            iters = std::max(iters, st.iters);
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, tms[ci].ev[0], tms[ci].ev[1])); t_val += ms;
+            CU(cudaEventElapsedTime(&ms, tms[ci].ev[1], tms[ci].ev[2])); t_vec += ms;
+            CU(cudaEventElapsedTime(&ms, tms[ci].ev[2], tms[ci].ev[3])); t_fin += ms;
         }
+        for (auto x : ctx) timed_collect(x);
+        for (int ci = 0; ci < nchunks; ++ci)
+            for (int i = 0; i < 4; ++i) cudaEventDestroy(tms[ci].ev[i]);
+        dev_free(h, d_report, (size_t)nchunks * BSP_C_WORDS);
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, e1, e2)); t_asm += ms;
     }
-    CU(cudaEventRecord(e1, h->st));   /* every chunk stream has been drained by its worker */
+    CU(cudaEventRecord(e1, h->st));   /* every chunk stream has been drained */
     CU(cudaStreamSynchronize(h->st));
     {
         auto t0 = std::chrono::steady_clock::now();
@@ -1063,14 +1055,14 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     h->stats[0] = (double)(h->launches + aux_launches() - launches0);
     h->stats[1] = rounds; h->stats[2] = iters;
-    /* stage times are summed over the chunk streams: with two workers they overlap in wall time */
+    /* stage times are summed over the chunk streams: with several streams they overlap in wall time */
     h->stats[3] = t_asm; h->stats[4] = t_val; h->stats[5] = t_vec; h->stats[6] = t_fin; h->stats[7] = total;
     for (int i = 0; i < 4; ++i) {
         h->stats[8 + i] = h->k_ms[i];
         h->stats[12 + i] = (double)h->k_cnt[i];
         for (auto x : h->aux) { h->stats[8 + i] += x->k_ms[i]; h->stats[12 + i] += (double)x->k_cnt[i]; }
     }
-    h->stats[19] = 0; h->stats[20] = 0;
+    h->stats[19] = redone; h->stats[20] = 0;
     h->ran = true;
     return 0;
 }

@@ -293,13 +293,16 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
     ChunkPtrs c;
     const size_t need = carve_chunk(GG, 1, nullptr, c, h->opt.recompute != 0);
     ChunkTimes tm;
-    BspRunStats st;
     bool ev_ok = true;
     for (int i = 0; i < 4; ++i) ev_ok = ev_ok && (cudaEventCreate(&tm.ev[i]) == cudaSuccess);
     rc = ev_ok ? ensure_workspace(h, need) : BSPATOM_ECUDA;
+    int *d_report = nullptr;
+    if (!rc) rc = dev_alloc(h, &d_report, (size_t)BSP_C_WORDS);
     if (!rc) {
         carve_chunk(GG, 1, h->ws.base, c, h->opt.recompute != 0);
-        rc = run_chunk(h, GG, 0, 1, c, st, tm);
+        h->ev_used = 0;
+        const BspSchedule sch = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters};   /* one pencil: full limits at once */
+        rc = enqueue_chunk(h, GG, 0, 1, c, sch, tm, d_report);
     }
     std::vector<double> Lb((size_t)n * (B + 1)), Cout(wantz ? (size_t)n * n : 0);
     int bad = 0;
@@ -311,6 +314,9 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
         if (cudaStreamSynchronize(h->st) != cudaSuccess) rc = BSPATOM_ECUDA;
     }
     if (ev_ok) for (int i = 0; i < 4; ++i) cudaEventDestroy(tm.ev[i]);
+    cudaStreamSynchronize(h->st);
+    h->ev_used = 0;
+    if (d_report) dev_free(h, d_report, (size_t)BSP_C_WORDS);
     dev_free(h, d_L, (size_t)n * (B + 1));
     if (rc) { fail(rc); return; }
     free_batch(h);

@@ -69,6 +69,22 @@
 #define BSP_ST_CONVERGED 1
 #define BSP_F_UNKNOWN (-2000000000)
 
+/* device-side control block of a chunk (BspEigChunk::counters): the whole stage schedule of a chunk is
+ * enqueued without any host read; kernels that are no longer needed see a flag and return at once */
+#define BSP_C_OPEN 0        /* brackets still open after the current round                      */
+#define BSP_C_UNCONV 1      /* eigenpairs above conv_tol after the current iteration            */
+#define BSP_C_CROWDED 2     /* open brackets that do not isolate one eigenvalue yet             */
+#define BSP_C_BRACKETED 3   /* flag: bracketing finished, later round kernels are no-ops        */
+#define BSP_C_BUF 4         /* bracket buffer (0/1) holding the final brackets                  */
+#define BSP_C_ROUNDS 5      /* rounds executed                                                  */
+#define BSP_C_REFINED 6     /* flag: every eigenpair converged, later iterations are no-ops     */
+#define BSP_C_ITERS 7       /* refinement iterations executed                                   */
+#define BSP_C_ARRIVE 9      /* block arrival counter of the "last block does the bookkeeping"   */
+#define BSP_C_OPEN_END 10   /* open brackets at hand-over                                       */
+#define BSP_C_CROWDED_END 11
+#define BSP_C_UNCONV_END 12
+#define BSP_C_WORDS 16
+
 struct BspEigChunk {
     /* geometry */
     int n;        /* basis size                                   */
@@ -105,7 +121,7 @@ struct BspEigChunk {
                   [npencil][npad/SEG][BSP_CK_DOUBLES][ldw]        */
     double *X; /* [npencil][xrows][ldw]                           */
     double *R; /* [npencil][xrows][ldw]                           */
-    int *counters; /* [0] brackets not done, [1] eigenpairs not converged */
+    int *counters; /* control block, BSP_C_* */
     /* tunables */
     double tau;       /* bracket width / gap at hand-over         */
     double delta_rel; /* shift offset / gap in correction steps   */
@@ -426,22 +442,53 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
         /* counters[0]: brackets still open; counters[2]: open AND not yet isolating one eigenvalue */
         const int crowded = (chi - clo != 1 || !(gp > 0.0)) ? 1 : 0;
 #if defined(__CUDA_ARCH__)
-        atomicAdd(g.counters + 0, 1);
-        if (crowded) atomicAdd(g.counters + 2, 1);
+        atomicAdd(g.counters + BSP_C_OPEN, 1);
+        if (crowded) atomicAdd(g.counters + BSP_C_CROWDED, 1);
 #else
-        g.counters[0] += 1;
-        g.counters[2] += crowded;
+        g.counters[BSP_C_OPEN] += 1;
+        g.counters[BSP_C_CROWDED] += crowded;
 #endif
     }
+}
+
+/* bookkeeping after a bracketing round (one thread, after every eigen index of the chunk has run):
+ * decides whether the bracketing is finished.  open_ok stragglers may be handed over open provided each
+ * isolates its eigenvalue: the refinement keeps bracketing with the inertia of its own factorisations. */
+BSP_HD void bsp_round_ctl(const BspEigChunk &g, int round, int max_rounds, int open_ok)
+{
+    int *c = g.counters;
+    if (c[BSP_C_BRACKETED]) return;
+    const int open = c[BSP_C_OPEN], crowded = c[BSP_C_CROWDED];
+    c[BSP_C_ROUNDS] = round + 1;
+    if (open == 0 || (open <= open_ok && crowded == 0) || round + 1 >= max_rounds) {
+        c[BSP_C_BRACKETED] = 1;
+        c[BSP_C_BUF] = (round + 1) & 1;
+        c[BSP_C_OPEN_END] = open;
+        c[BSP_C_CROWDED_END] = crowded;
+    }
+    c[BSP_C_OPEN] = 0;
+    c[BSP_C_CROWDED] = 0;
+}
+
+/* bookkeeping after a convergence check */
+BSP_HD void bsp_check_ctl(const BspEigChunk &g, int iter)
+{
+    int *c = g.counters;
+    if (c[BSP_C_REFINED]) return;
+    c[BSP_C_ITERS] = iter + 1;
+    c[BSP_C_UNCONV_END] = c[BSP_C_UNCONV];
+    if (c[BSP_C_UNCONV] == 0) c[BSP_C_REFINED] = 1;
+    c[BSP_C_UNCONV] = 0;
 }
 
 /* ------------------------------------------------------------------------- *
  * hand-over: final brackets live in buffer `buf`; copy to buffer 0, set the
  * first shift to the bracket midpoint.
  * ------------------------------------------------------------------------- */
-BSP_HD void bsp_refine_prepare(const BspEigChunk &g, int p, int e, int buf)
+BSP_HD void bsp_refine_prepare(const BspEigChunk &g, int p, int e)
 {
     if (e >= g.n) return;
+    const int buf = g.counters[BSP_C_BUF];
     const size_t per = (size_t)g.npencil * g.ldw;
     const size_t id = (size_t)p * g.ldw + e;
     const double lo = g.lo[(size_t)buf * per + id], hi = g.hi[(size_t)buf * per + id];
@@ -1033,9 +1080,9 @@ BSP_HD void bsp_check_converged(const BspEigChunk &g, int p, int e, int allow)
         g.status[id] |= BSP_ST_CONVERGED;
     } else {
 #if defined(__CUDA_ARCH__)
-        atomicAdd(g.counters + 1, 1);
+        atomicAdd(g.counters + BSP_C_UNCONV, 1);
 #else
-        g.counters[1] += 1;
+        g.counters[BSP_C_UNCONV] += 1;
 #endif
     }
 }

@@ -1,75 +1,51 @@
 /*
- * bsp_driver.h -- stage schedule of the banded eigensolver for one chunk of
- * pencils, written against an executor so that the CUDA launcher
- * (bsp_api.cu) and the CPU replay used by tests/emul share one schedule.
+ * bsp_driver.h -- stage schedule of the banded eigensolver for one chunk of pencils, written against
+ * an executor so that the CUDA enqueuer (bsp_api.cu) and the CPU replay used by tests/emul share it.
+ *
+ * The schedule is STATIC: everything is enqueued up front and nothing is read back by the host while
+ * a chunk runs.  Data-dependent control lives in the chunk's device-side control block (BSP_C_* in
+ * bsp_core.h): once the bracketing is finished the remaining round kernels see BSP_C_BRACKETED and
+ * return at once, and the optional extra refinement iterations see BSP_C_REFINED.  The host inspects the
+ * per-chunk report after the whole batch and re-runs a chunk with larger limits only if it had to.
  *
  * Exec must provide:
- *   void bounds();                         // bracket [lo0,hi0] per pencil
- *   void round(int r);                     // one multisection round
- *   void prepare(int buf);                 // hand brackets to the refinement
- *   void factor(int iter);                 // F pass
- *   void back(int corr_now, int corr_next);// B pass
- *   void check(int allow);                 // convergence marks
- *   void zero_counter(int which);          // which: 0 open brackets (also clears 2), 1 unconverged
- *   int  read_counter(int which);          // blocking read; 2 = open brackets that do not isolate yet
+ *   void bounds();                            // bracket [lo0,hi0] per pencil
+ *   void round(int r, int max_rounds);        // one bracketing round + its bookkeeping
+ *   void prepare();                           // hand brackets to the refinement
+ *   void factor(int iter, int optional);      // F pass (optional: skipped once everything converged)
+ *   void back(int corr_now, int corr_next, int optional);
+ *   void check(int iter);                     // convergence marks + bookkeeping
  */
 #ifndef BSP_DRIVER_H
 #define BSP_DRIVER_H
 
 struct BspSchedule {
-    int max_rounds;  /* multisection rounds cap                       */
-    int min_iters;   /* refinement iterations always done (>= 3)      */
-    int max_iters;   /* cap                                           */
-    int first_check_round; /* first round after which the host polls  */
-    int check_every;       /* ... and then every so many rounds (finished
-                              brackets make a surplus round nearly free) */
-    int open_ok;           /* hand over with this many brackets still open, provided each
-                              isolates its eigenvalue: the refinement keeps bracketing
-                              with the inertia of its own factorisations */
+    int rounds;     /* bracketing rounds enqueued (the flag makes surplus ones free)       */
+    int min_iters;  /* refinement iterations always done (>= 3)                             */
+    int max_iters;  /* iterations enqueued; those beyond min_iters only touch stragglers   */
 };
 
 struct BspRunStats {
     int rounds;
     int iters;
-    int brackets_open; /* brackets not narrowed when the cap was hit  */
-    int unconverged;   /* eigenpairs above conv_tol at the end        */
+    int brackets_open;    /* brackets handed over open (each isolating its eigenvalue)      */
+    int brackets_crowded; /* ... of which not isolating: the chunk must be re-run           */
+    int unconverged;      /* eigenpairs above conv_tol after the last iteration             */
 };
 
 template <class Exec>
-inline BspRunStats bsp_run_chunk(Exec &ex, const BspSchedule &sch)
+inline void bsp_enqueue_chunk(Exec &ex, const BspSchedule &sch)
 {
-    BspRunStats st = {0, 0, 0, 0};
     ex.bounds();
-    int r = 0;
-    for (;;) {
-        ex.zero_counter(0);
-        ex.round(r);
-        ++r;
-        const int ce = sch.check_every > 0 ? sch.check_every : 1;
-        if ((r >= sch.first_check_round && (r - sch.first_check_round) % ce == 0) || r >= sch.max_rounds) {
-            st.brackets_open = ex.read_counter(0);
-            if (st.brackets_open == 0 || r >= sch.max_rounds) break;
-            if (st.brackets_open <= sch.open_ok && ex.read_counter(2) == 0) break;
-        }
-    }
-    st.rounds = r;
-    ex.prepare(r & 1);
+    for (int r = 0; r < sch.rounds; ++r) ex.round(r, sch.rounds);
+    ex.prepare();
     /* iteration t: plain for t < 2, residual-correction form afterwards */
-    int t = 0;
-    for (;;) {
-        const int corr_now = (t >= 2), corr_next = (t + 1 >= 2);
-        ex.factor(t);
-        ex.back(corr_now, corr_next);
-        ++t;
-        if (t >= sch.min_iters || t >= sch.max_iters) {
-            ex.zero_counter(1);
-            ex.check(1);
-            st.unconverged = ex.read_counter(1);
-            if (st.unconverged == 0 || t >= sch.max_iters) break;
-        }
+    for (int t = 0; t < sch.max_iters; ++t) {
+        const int optional = (t >= sch.min_iters);
+        ex.factor(t, optional);
+        ex.back(t >= 2, t + 1 >= 2, optional);
+        if (t + 1 >= sch.min_iters) ex.check(t);
     }
-    st.iters = t;
-    return st;
 }
 
 #endif

@@ -37,15 +37,10 @@ __global__ void __launch_bounds__(BSP_NCAND) bsp_bounds_kernel(BspEigChunk g, do
     bsp_bounds_candidate<B>(g, blockIdx.x, threadIdx.x, cand_s, cand_c);
 }
 
-/* device counter -> host-mapped word with a plain store: the host polls convergence without a D2H
- * memcpy, which would queue behind the multi-hundred-MB result copies on the copy engine */
-__global__ void bsp_publish_counter_kernel(const int *ctr, volatile int *host_word)
+__global__ void bsp_zero_words_kernel(int *w, int n)
 {
-    *host_word = *ctr;
-    __threadfence_system();
+    if ((int)threadIdx.x < n) w[threadIdx.x] = 0;
 }
-
-__global__ void bsp_zero_counter_kernel(int *ctr) { *ctr = 0; }
 
 __global__ void bsp_bounds_pick_kernel(BspEigChunk g, const double *cand_s, const int *cand_c)
 {
@@ -53,44 +48,77 @@ __global__ void bsp_bounds_pick_kernel(BspEigChunk g, const double *cand_s, cons
     if (p < g.npencil) bsp_bounds_pick(g, p, cand_s, cand_c);
 }
 
-template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) bsp_round_kernel(BspEigChunk g, int round)
+/* true in exactly one thread of the grid: thread 0 of the block that finishes last */
+__device__ __forceinline__ bool bsp_last_block(int *arrive)
 {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned t = atomicAdd((unsigned *)arrive, 1u);
+        s_last = (t == total - 1);
+        if (s_last) { *arrive = 0; __threadfence(); }
+    }
+    __syncthreads();
+    return s_last && threadIdx.x == 0;
+}
+
+template <int B>
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) bsp_round_kernel(BspEigChunk g, int round, int max_rounds, int open_ok)
+{
+    if (g.counters[BSP_C_BRACKETED]) return;       /* written by the previous kernel: grid-uniform */
     bsp_multisection_round<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, round);
+    if (bsp_last_block(g.counters + BSP_C_ARRIVE)) bsp_round_ctl(g, round, max_rounds, open_ok);
 }
 
-__global__ void bsp_prepare_kernel(BspEigChunk g, int buf)
+__global__ void bsp_prepare_kernel(BspEigChunk g)
 {
-    bsp_refine_prepare(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, buf);
+    bsp_refine_prepare(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_kernel(BspEigChunk g, int iter)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_kernel(BspEigChunk g, int iter, int optional)
 {
+    if (optional && g.counters[BSP_C_REFINED]) return;
     bsp_factor_forward<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter);
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_back_kernel(BspEigChunk g, int corr_now, int corr_next)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_back_kernel(BspEigChunk g, int corr_now, int corr_next, int optional)
 {
+    if (optional && g.counters[BSP_C_REFINED]) return;
     bsp_back_substitute<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, corr_now, corr_next);
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_ckpt_kernel(BspEigChunk g, int iter)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_ckpt_kernel(BspEigChunk g, int iter, int optional)
 {
+    if (optional && g.counters[BSP_C_REFINED]) return;
     bsp_factor_checkpoint<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter);
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_back_rc_kernel(BspEigChunk g, int corr_now, int corr_next, int iter)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_back_rc_kernel(BspEigChunk g, int corr_now, int corr_next, int iter, int optional)
 {
+    if (optional && g.counters[BSP_C_REFINED]) return;
     bsp_back_recompute<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, corr_now, corr_next, iter);
 }
 
-__global__ void bsp_check_kernel(BspEigChunk g, int allow)
+__global__ void bsp_check_kernel(BspEigChunk g, int iter)
 {
-    bsp_check_converged(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, allow);
+    if (g.counters[BSP_C_REFINED]) return;
+    bsp_check_converged(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, 1);
+    if (bsp_last_block(g.counters + BSP_C_ARRIVE)) bsp_check_ctl(g, iter);
+}
+
+/* copy the chunk's control block into the run report and clear it for the next chunk of this stream */
+__global__ void bsp_report_kernel(BspEigChunk g, int *report)
+{
+    if (threadIdx.x < BSP_C_WORDS) {
+        report[threadIdx.x] = g.counters[threadIdx.x];
+        g.counters[threadIdx.x] = 0;
+    }
 }
 
 __global__ void bsp_finalize_kernel(BspEigChunk g, double *E, double *fac, int *bad, double res_tol)

@@ -410,6 +410,48 @@ def _dipole_chain(self, A_band: np.ndarray, C_blocks) -> np.ndarray:
 BspAtom.dipole_chain = _dipole_chain
 
 
+class BspAtomPipeline:
+    """Throughput mode for sweeps: `depth` handles on one GPU alternate over a list of batches, each from its
+    own host thread (ctypes releases the GIL), so the D2H of one batch's eigenvectors (8 MB per solve at
+    N = 1000, PCIe-bound) overlaps the kernels of the next batch.  Every batch still does its own H2D,
+    kernels and D2H through `bspatom_solve_batch`; results land in the caller's (pinned) buffers."""
+
+    def __init__(self, device: int = 0, depth: int = 2):
+        self.atoms = [BspAtom(device=device) for _ in range(depth)]
+
+    def set_option(self, name: str, value: float):
+        for a in self.atoms:
+            a.set_option(name, value)
+
+    def close(self):
+        for a in self.atoms:
+            a.close()
+
+    def solve_batches(self, batches, outs_E, outs_C, nvec=None):
+        """batches[i]: list of (Problem, l); outs_E[i], outs_C[i]: pinned float64 buffers for batch i.
+        Returns the list of info arrays."""
+        import threading
+
+        infos = [None] * len(batches)
+        errors = []
+
+        def worker(w):
+            try:
+                for i in range(w, len(batches), len(self.atoms)):
+                    _, _, infos[i] = self.atoms[w].solve_batch(batches[i], nvec=nvec, out_E=outs_E[i], out_C=outs_C[i])
+            except Exception as exc:       # surfaced to the caller below
+                errors.append(exc)
+
+        threads = [threading.Thread(target=worker, args=(w,)) for w in range(len(self.atoms))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return infos
+
+
 def pinned_empty(count: int) -> np.ndarray:
     """float64 array in page-locked host memory (bspatom_alloc_host): results written into it by
     solve_batch stream out chunk by chunk while the GPU keeps computing."""

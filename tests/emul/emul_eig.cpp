@@ -14,6 +14,7 @@ struct EmulExec {
     BspEigChunk g;
     std::vector<double> cand_s;
     std::vector<int> cand_c;
+    int recompute = 0, cur_iter = 0, open_ok = 0;
     void bounds() {
         cand_s.assign(g.npencil * BSP_NCAND, 0.0);
         cand_c.assign(g.npencil * BSP_NCAND, 0);
@@ -21,36 +22,39 @@ struct EmulExec {
             for (int l = 0; l < BSP_NCAND; ++l) bsp_bounds_candidate<B>(g, p, l, cand_s.data(), cand_c.data());
         for (int p = 0; p < g.npencil; ++p) bsp_bounds_pick(g, p, cand_s.data(), cand_c.data());
     }
-    void round(int r) {
+    void round(int r, int max_rounds) {
+        if (g.counters[BSP_C_BRACKETED]) return;
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_multisection_round<B>(g, p, e, r);
+        bsp_round_ctl(g, r, max_rounds, open_ok);
     }
-    void prepare(int buf) {
+    void prepare() {
         for (int p = 0; p < g.npencil; ++p)
-            for (int e = 0; e < g.n; ++e) bsp_refine_prepare(g, p, e, buf);
+            for (int e = 0; e < g.n; ++e) bsp_refine_prepare(g, p, e);
     }
-    int recompute = 0, cur_iter = 0;
-    void factor(int it) {
+    void factor(int it, int optional) {
         cur_iter = it;
+        if (optional && g.counters[BSP_C_REFINED]) return;
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) {
                 if (recompute) bsp_factor_checkpoint<B>(g, p, e, it);
                 else bsp_factor_forward<B>(g, p, e, it);
             }
     }
-    void back(int cn, int cx) {
+    void back(int cn, int cx, int optional) {
+        if (optional && g.counters[BSP_C_REFINED]) return;
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) {
                 if (recompute) bsp_back_recompute<B>(g, p, e, cn, cx, cur_iter);
                 else bsp_back_substitute<B>(g, p, e, cn, cx);
             }
     }
-    void check(int allow) {
+    void check(int it) {
+        if (g.counters[BSP_C_REFINED]) return;
         for (int p = 0; p < g.npencil; ++p)
-            for (int e = 0; e < g.n; ++e) bsp_check_converged(g, p, e, allow);
+            for (int e = 0; e < g.n; ++e) bsp_check_converged(g, p, e, 1);
+        bsp_check_ctl(g, it);
     }
-    void zero_counter(int w) { g.counters[w] = 0; if (w == 0) g.counters[2] = 0; }
-    int read_counter(int w) { return g.counters[w]; }
 };
 
 template <int B>
@@ -83,7 +87,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     for (int p = 0; p < npencil; ++p) { inst[p] = p; nvec[p] = nvec_in[p]; }
     std::vector<double> pbound(npencil * 4), lo(2 * per), hi(2 * per), samp_s(2 * per), gap(per), sigma(per),
         rho(per), rho_prev(per), scale(per), res(per);
-    std::vector<int> clo(2 * per), chi(2 * per), samp_c(2 * per), done(per), status(per), counters(4);
+    std::vector<int> clo(2 * per), chi(2 * per), samp_c(2 * per), done(per), status(per), counters(BSP_C_WORDS, 0);
     std::vector<double> samp_fm(2 * per), flm(per), fhm(per), beta(per);
     std::vector<int> samp_fe(2 * per), fle(per), fhe(per), side(per);
     std::vector<double> L((size_t)npencil * g.npad * K1 * g.ldw), X((size_t)npencil * g.xrows * g.ldw, 0.0),
@@ -97,8 +101,10 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     g.res = res.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
     g.counters = counters.data(); g.tau = tau; g.delta_rel = delta_rel; g.conv_tol = conv_tol;
     EmulExec<B> ex; ex.g = g; ex.recompute = getenv("BSP_EMUL_RECOMPUTE") ? atoi(getenv("BSP_EMUL_RECOMPUTE")) : 0;
-    BspSchedule sch = {max_rounds, min_iters, max_iters, 4, 1, 0};
-    BspRunStats st = bsp_run_chunk(ex, sch);
+    BspSchedule sch = {max_rounds, min_iters, max_iters};
+    bsp_enqueue_chunk(ex, sch);
+    BspRunStats st = {counters[BSP_C_ROUNDS], counters[BSP_C_ITERS], counters[BSP_C_OPEN_END], counters[BSP_C_CROWDED_END],
+                      counters[BSP_C_UNCONV_END]};
     std::vector<double> fac(per);
     std::vector<int> bad(npencil, 0);
     for (int p = 0; p < npencil; ++p)

@@ -97,3 +97,25 @@ def test_not_positive_definite_reports_lapack_info(atom):
             h.batch_run()
         finally:
             h.close()
+
+
+def test_pipeline_two_handles_bit_identical_to_single(atom):
+    """BspAtomPipeline (two handles alternating over batches, each through bspatom_solve_batch) returns the
+    same bits as one handle solving the batches one after the other."""
+    from bspatom_b200.host import pinned_empty
+
+    a = host_basis(kind_grid=0, k=7, nfun=120, rb=60.0)
+    p = a.problem()
+    n = a.nfun
+    batches = [[(p, l) for l in range(b, b + 3)] for b in range(4)]
+    pipe = bsp.BspAtomPipeline(device=0, depth=2)
+    oE = [pinned_empty(3 * n) for _ in batches]
+    oC = [pinned_empty(3 * n * n) for _ in batches]
+    infos = pipe.solve_batches(batches, oE, oC)
+    pipe.close()
+    for b, items in enumerate(batches):
+        Es, Cs, info = atom.solve_batch(items)
+        assert not info.any() and not infos[b].any()
+        assert np.array_equal(np.concatenate([np.asarray(e) for e in Es]), oE[b])
+        for j in range(3):      # column-major n x n blocks, one per solve
+            assert np.array_equal(np.asarray(Cs[j]), oC[b][j * n * n:(j + 1) * n * n].reshape((n, n), order="F"))
