@@ -65,6 +65,13 @@
 /* rows are padded to a whole number of segments */
 #define BSP_NPAD(n, B) ((((n) + BSP_SEG_STEPS(B) - 1) / BSP_SEG_STEPS(B)) * BSP_SEG_STEPS(B))
 
+/* The sweeps walk the band rows of a pencil in tiles of BSP_TILE_STEPS(B) steps (whole unrolled groups of
+ * B+1 steps; npad is a whole number of tiles).  A row source hands out one tile at a time: on the host (and
+ * for the bounds ladder) straight from global memory, in the round / factor / back kernels from the
+ * shared-memory stages the block fills with bulk copies (BspRowsStaged in bsp_kernels.cuh). */
+#define BSP_TILE_GROUPS(B) ((B) <= 8 ? 4 : 2)
+#define BSP_TILE_STEPS(B) (BSP_TILE_GROUPS(B) * ((B) + 1))
+
 /* refinement status bits */
 #define BSP_ST_CONVERGED 1
 #define BSP_F_UNKNOWN (-2000000000)
@@ -161,78 +168,152 @@ BSP_HD void bsp_renorm(double &m, int &e)
     e += ex;
 }
 
-template <int B>
-BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restrict__ fbS, int npad,
-                           double sigma, double pivmin, int *first_neg, double *det_m = nullptr,
-                           int *det_e = nullptr)
+/* The sweep is written as "window initialisation" + "group of B+1 steps" so that the same arithmetic runs
+ * from global memory (GL = true: host replay, bounds ladder) and from the shared-memory tiles the round
+ * kernel stages with bulk copies (GL = false).  rows point at band rows of FS doubles. */
+template <bool GL>
+BSP_HD double bsp_ld(const double *p)
+{
+#if defined(__CUDA_ARCH__)
+    if (GL) return __ldg(p);
+#endif
+    return *p;
+}
+
+template <int B, bool GL>
+BSP_HD void bsp_sturm_init(double (&w)[B + 1][B + 1], double (&nh)[B + 1], double (&ns)[B + 1],
+                           const double *__restrict__ rowsH, const double *__restrict__ rowsS, double sigma)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
-    double w[K1][K1];
-    int cnt = 0, first = -1;
-    double fm = 0.5; /* det(H - sigma S) = prod of pivots = fm * 2^fe */
-    int fe = 1;
 #pragma unroll
     for (int r = 0; r < K1; ++r) {
 #pragma unroll
         for (int c = 0; c < K1; ++c) {
             if (c <= r) {
                 const int off = r * FS + (c - r + B);
-                w[r][c] = fma(-sigma, BSP_LDG(fbS + off), BSP_LDG(fbH + off));
+                w[r][c] = fma(-sigma, bsp_ld<GL>(rowsS + off), bsp_ld<GL>(rowsH + off));
             } else {
                 w[r][c] = 0.0;
             }
         }
     }
     /* software pipeline: the band row that enters the window at the end of
-     * step j is loaded during step j-1, so its (L1) latency hides behind the
+     * step j is loaded during step j-1, so its latency hides behind the
      * pivot arithmetic instead of stalling the first FMA that needs it */
-    double nh[K1], ns[K1];
 #pragma unroll
     for (int m = 0; m <= B; ++m) {
-        nh[m] = BSP_LDG(fbH + (size_t)K1 * FS + m);
-        ns[m] = BSP_LDG(fbS + (size_t)K1 * FS + m);
+        nh[m] = bsp_ld<GL>(rowsH + (size_t)K1 * FS + m);
+        ns[m] = bsp_ld<GL>(rowsS + (size_t)K1 * FS + m);
     }
-    for (int j0 = 0; j0 < npad; j0 += K1) {
+}
+
+/* steps j0 .. j0+B; hnext / snext = band row j0 + B + 2 (the row loaded during step j0) */
+template <int B, bool GL>
+BSP_HD void bsp_sturm_group(double (&w)[B + 1][B + 1], double (&nh)[B + 1], double (&ns)[B + 1],
+                            const double *__restrict__ hnext, const double *__restrict__ snext, double sigma,
+                            double pivmin, int j0, int &cnt, int &first, double &fm, int &fe)
+{
+    constexpr int K1 = B + 1;
+    constexpr int FS = 2 * B + 2;
 #pragma unroll
-        for (int t = 0; t < K1; ++t) {
-            const int j = j0 + t;
-            double d = w[t][t];
-            if (fabs(d) < pivmin) d = -pivmin;
-            if (d < 0.0) { ++cnt; if (first < 0) first = j; }
-            fm *= d;
-            bsp_renorm(fm, fe);
-            const double rinv = BSP_RCP(d);
-            double col[K1], l[K1];
+    for (int t = 0; t < K1; ++t) {
+        double d = w[t][t];
+        if (fabs(d) < pivmin) d = -pivmin;
+        if (d < 0.0) { ++cnt; if (first < 0) first = j0 + t; }
+        fm *= d;
+        bsp_renorm(fm, fe);
+        const double rinv = BSP_RCP(d);
+        double col[K1], l[K1];
 #pragma unroll
-            for (int i = 1; i <= B; ++i) {
-                col[i] = w[(t + i) % K1][t];
-                l[i] = col[i] * rinv;
-            }
+        for (int i = 1; i <= B; ++i) {
+            col[i] = w[(t + i) % K1][t];
+            l[i] = col[i] * rinv;
+        }
 #pragma unroll
-            for (int m = 1; m <= B; ++m) {
+        for (int m = 1; m <= B; ++m) {
 #pragma unroll
-                for (int i = m; i <= B; ++i) {
-                    w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
-                }
-            }
-            /* row j retires; its slot takes row j+B+1 (loaded during the previous
-             * step); the registers are refilled at once with row j+B+2 */
-            {
-                const double *hrow = fbH + (size_t)(j + K1 + 1) * FS;
-                const double *srow = fbS + (size_t)(j + K1 + 1) * FS;
-#pragma unroll
-                for (int m = 0; m <= B; ++m) {
-                    w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
-                    nh[m] = BSP_LDG(hrow + m);
-                    ns[m] = BSP_LDG(srow + m);
-                }
+            for (int i = m; i <= B; ++i) {
+                w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
             }
         }
+        /* row j retires; its slot takes row j+B+1 (loaded during the previous
+         * step); the registers are refilled at once with row j+B+2 */
+        {
+            const double *hrow = hnext + (size_t)t * FS;
+            const double *srow = snext + (size_t)t * FS;
+#pragma unroll
+            for (int m = 0; m <= B; ++m) {
+                w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
+                nh[m] = bsp_ld<GL>(hrow + m);
+                ns[m] = bsp_ld<GL>(srow + m);
+            }
+        }
+    }
+}
+
+struct BspTrue { static constexpr bool value = true; };
+struct BspFalse { static constexpr bool value = false; };
+
+/* row source reading global memory.  Forward tiles: pointer to band row t*TR, rows t*TR .. (t+1)*TR+B+1 are
+ * read.  Backward tiles (taken in descending t): same pointer, rows t*TR .. (t+1)*TR-1 are read. */
+template <int B>
+struct BspRowsGlobal {
+    static constexpr bool GL = true;
+    const double *H, *S;
+    BSP_HD void begin_forward(int) {}
+    BSP_HD void acquire_forward(int t, const double *&tH, const double *&tS)
+    {
+        tH = H + (size_t)t * BSP_TILE_STEPS(B) * (2 * B + 2);
+        tS = S + (size_t)t * BSP_TILE_STEPS(B) * (2 * B + 2);
+    }
+    BSP_HD void release_forward(int, int) {}
+    BSP_HD void begin_backward(int) {}
+    BSP_HD void acquire_backward(int t, int, const double *&tH, const double *&tS) { acquire_forward(t, tH, tS); }
+    BSP_HD void release_backward(int, int) {}
+};
+
+/* called by every thread that shares `src` (the staged source synchronises the block);
+ * only `active` threads do arithmetic */
+template <int B, class Src>
+BSP_HD int bsp_sturm_sweep(Src &src, int npad, bool active, double sigma, double pivmin, int *first_neg,
+                           double *det_m, int *det_e)
+{
+    constexpr int K1 = B + 1;
+    constexpr int FS = 2 * B + 2;
+    constexpr int TR = BSP_TILE_STEPS(B);
+    const int ntiles = npad / TR;
+    double w[K1][K1], nh[K1], ns[K1];
+    int cnt = 0, first = -1;
+    double fm = 0.5; /* det(H - sigma S) = prod of pivots = fm * 2^fe */
+    int fe = 1;
+    src.begin_forward(ntiles);
+    for (int t = 0; t < ntiles; ++t) {
+        const double *tH, *tS;
+        src.acquire_forward(t, tH, tS);
+        if (active) {
+            if (t == 0) bsp_sturm_init<B, Src::GL>(w, nh, ns, tH, tS, sigma);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int gq = 0; gq < TR; gq += K1)
+                bsp_sturm_group<B, Src::GL>(w, nh, ns, tH + (size_t)(gq + K1 + 1) * FS, tS + (size_t)(gq + K1 + 1) * FS,
+                                            sigma, pivmin, t * TR + gq, cnt, first, fm, fe);
+        }
+        src.release_forward(t, ntiles);
     }
     if (first_neg) *first_neg = first;
     if (det_m) { *det_m = fm; *det_e = fe; }
     return cnt;
+}
+
+template <int B>
+BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restrict__ fbS, int npad,
+                           double sigma, double pivmin, int *first_neg, double *det_m = nullptr,
+                           int *det_e = nullptr)
+{
+    BspRowsGlobal<B> src{fbH, fbS};
+    return bsp_sturm_sweep<B>(src, npad, true, sigma, pivmin, first_neg, det_m, det_e);
 }
 
 /* ------------------------------------------------------------------------- *
@@ -296,15 +377,21 @@ BSP_HD void bsp_bounds_pick(const BspEigChunk &g, int p, const double *cand_s, c
  * rounds then square the bracket width (order ~1.41 per round) instead of one
  * bit per round.  The inertia of every sample keeps the bracket rigorous.
  * ------------------------------------------------------------------------- */
-template <int B>
-BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round)
+/* state of one eigen index between the phases of a round */
+struct BspRoundState {
+    double lo, hi, flm, fhm, beta, gp, wdt, frac, s, sfm;
+    int clo, chi, fle, fhe, side, done, c, sfe;
+    int want_defl;  /* the regula-falsi step is possible: the deflation sum at the bracket midpoint is needed */
+    int want_count; /* s is a new sample: its inertia is needed                                              */
+};
+
+/* phase 1: load the bracket, tighten it with last round's samples, decide done / kind of step */
+BSP_HD void bsp_round_begin(const BspEigChunk &g, int p, int e, int round, BspRoundState &st)
 {
-    constexpr int FS = 2 * B + 2;
     const int n = g.n;
-    if (e >= n) return;
     const size_t per = (size_t)g.npencil * g.ldw;
     const size_t id = (size_t)p * g.ldw + e;
-    const size_t rd = (size_t)(round & 1) * per, wr = (size_t)((round + 1) & 1) * per;
+    const size_t rd = (size_t)(round & 1) * per;
     double lo, hi, flm = 0.0, fhm = 0.0, beta = 0.0;
     int clo, chi, fle = BSP_F_UNKNOWN, fhe = BSP_F_UNKNOWN, side = 0; /* side: 1 = last sample was an interpolated one */
     if (round == 0) {
@@ -314,7 +401,7 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
         lo = g.lo[rd + id]; hi = g.hi[rd + id]; clo = g.clo[rd + id]; chi = g.chi[rd + id];
         flm = g.flm[id]; fle = g.fle[id]; fhm = g.fhm[id]; fhe = g.fhe[id]; side = g.side[id]; beta = g.beta[id];
     }
-    int was_done = (round == 0) ? 0 : g.done[id];
+    const int was_done = (round == 0) ? 0 : g.done[id];
     if (round > 0 && !was_done) {
         /* tighten with the samples every eigen index of this pencil published
          * last round: s is non-decreasing in the index, c = nu(s) monotone */
@@ -351,8 +438,10 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
         if (wdt <= 4.0 * BSP_EPS * amax + 1e-300) done = 1;
         else if (e < g.nvec[p] && gp > 0.0 && wdt <= g.tau * gp) done = 1;
     }
-    double s = lo, sfm = flm;
-    int c = clo, sfe = fle;
+    st.lo = lo; st.hi = hi; st.flm = flm; st.fhm = fhm; st.beta = beta; st.gp = gp; st.wdt = wdt;
+    st.clo = clo; st.chi = chi; st.fle = fle; st.fhe = fhe; st.side = side; st.done = done;
+    st.s = lo; st.sfm = flm; st.c = clo; st.sfe = fle;
+    st.want_defl = 0; st.want_count = 0; st.frac = 0.5;
     if (!done) {
         int m = chi - clo, rk = e - clo;
         if (m < 1) m = 1;
@@ -360,87 +449,114 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
         if (rk > m - 1) rk = m - 1;
         double frac = ((double)rk + 0.5) / (double)m;
         if (round == 0) frac = frac * frac; /* box states: E_i ~ i^2 */
-        bool secant = false;
+        st.frac = frac;
         /* beta holds the bracket width at the previous interpolated sample: if that sample did not at
          * least halve the bracket, this round bisects (Brent-style safeguard against creeping) */
         const bool stalled = (side == 1) && (wdt > 0.5 * beta);
         if (m == 1 && round > 0 && !stalled && fle != BSP_F_UNKNOWN && fhe != BSP_F_UNKNOWN &&
-            ((flm < 0.0) != (fhm < 0.0))) {
-            /* det(H - sigma S) = prod_k (lambda_k - sigma) varies over the bracket like
-             * (lambda_e - sigma) * exp(beta sigma), beta = sum_{k != e} 1/(sigma - lambda_k) (hundreds of
-             * clustered levels make |beta| w >> 1).  Deflate that factor with the other brackets'
-             * current midpoints (Maehly deflation; float reciprocals are plenty for a slope). */
-            double bsum = 0.0;
-            {
-                const double mid = 0.5 * (lo + hi);
-                const double *Lo = g.lo + rd + (size_t)p * g.ldw, *Hi = g.hi + rd + (size_t)p * g.ldw;
-                float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f; /* independent chains: loads overlap */
-                int k = 0;
-                for (; k + 4 <= n; k += 4) {
-                    const float d0 = (float)(mid - 0.5 * (Lo[k] + Hi[k]));
-                    const float d1 = (float)(mid - 0.5 * (Lo[k + 1] + Hi[k + 1]));
-                    const float d2 = (float)(mid - 0.5 * (Lo[k + 2] + Hi[k + 2]));
-                    const float d3 = (float)(mid - 0.5 * (Lo[k + 3] + Hi[k + 3]));
-                    b0 += (k != e && d0 != 0.0f) ? 1.0f / d0 : 0.0f;
-                    b1 += (k + 1 != e && d1 != 0.0f) ? 1.0f / d1 : 0.0f;
-                    b2 += (k + 2 != e && d2 != 0.0f) ? 1.0f / d2 : 0.0f;
-                    b3 += (k + 3 != e && d3 != 0.0f) ? 1.0f / d3 : 0.0f;
-                }
-                for (; k < n; ++k) {
-                    const float dk = (float)(mid - 0.5 * (Lo[k] + Hi[k]));
-                    b0 += (k != e && dk != 0.0f) ? 1.0f / dk : 0.0f;
-                }
-                bsum = (double)b0 + (double)b1 + (double)b2 + (double)b3;
-            }
-            /* regula falsi on the deflated determinant: root at lo + w / (1 + r),
-             * r = |f(hi)/f(lo)| exp(-beta w) */
-            const double shift = -bsum * wdt * 1.4426950408889634; /* in powers of two */
-            double de = (double)(fhe - fle) + shift;
-            de = de > 1000.0 ? 1000.0 : (de < -1000.0 ? -1000.0 : de);
-            const double dei = floor(de);
-            const double r = ldexp(fabs(fhm / flm) * exp2(de - dei), (int)dei);
-            const double t = 1.0 / (1.0 + r);
-            /* the estimate sits at fraction t; when it hugs one end, sample at twice its distance
-             * from that end: the root then (almost surely) lies between the end and the sample and
-             * the bracket collapses to ~2x the interpolation error instead of creeping one-sidedly */
-            if (t > 0.0 && t < 1.0) {
-                frac = t < 0.25 ? 2.0 * t : (t > 0.75 ? 1.0 - 2.0 * (1.0 - t) : t);
-                secant = true;
-            }
+            ((flm < 0.0) != (fhm < 0.0)))
+            st.want_defl = 1;
+    }
+}
+
+/* phase 2 (plain form; the round kernel computes the same sum from shared-memory tiles):
+ * det(H - sigma S) = prod_k (lambda_k - sigma) varies over the bracket like
+ * (lambda_e - sigma) * exp(beta sigma), beta = sum_{k != e} 1/(sigma - lambda_k) (hundreds of
+ * clustered levels make |beta| w >> 1).  Deflate that factor with the other brackets'
+ * current midpoints (Maehly deflation; float reciprocals are plenty for a slope). */
+BSP_HD double bsp_deflation_sum(const BspEigChunk &g, int p, int e, int round, const BspRoundState &st)
+{
+    const int n = g.n;
+    const size_t rd = (size_t)(round & 1) * (size_t)g.npencil * g.ldw;
+    const double mid = 0.5 * (st.lo + st.hi);
+    const double *Lo = g.lo + rd + (size_t)p * g.ldw, *Hi = g.hi + rd + (size_t)p * g.ldw;
+    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f; /* independent chains: loads overlap */
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {
+        const float d0 = (float)(mid - 0.5 * (Lo[k] + Hi[k]));
+        const float d1 = (float)(mid - 0.5 * (Lo[k + 1] + Hi[k + 1]));
+        const float d2 = (float)(mid - 0.5 * (Lo[k + 2] + Hi[k + 2]));
+        const float d3 = (float)(mid - 0.5 * (Lo[k + 3] + Hi[k + 3]));
+        b0 += (k != e && d0 != 0.0f) ? 1.0f / d0 : 0.0f;
+        b1 += (k + 1 != e && d1 != 0.0f) ? 1.0f / d1 : 0.0f;
+        b2 += (k + 2 != e && d2 != 0.0f) ? 1.0f / d2 : 0.0f;
+        b3 += (k + 3 != e && d3 != 0.0f) ? 1.0f / d3 : 0.0f;
+    }
+    for (; k < n; ++k) {
+        const float dk = (float)(mid - 0.5 * (Lo[k] + Hi[k]));
+        b0 += (k != e && dk != 0.0f) ? 1.0f / dk : 0.0f;
+    }
+    return (double)b0 + (double)b1 + (double)b2 + (double)b3;
+}
+
+/* phase 3: choose the sample */
+BSP_HD void bsp_round_pick(BspRoundState &st, double bsum)
+{
+    if (st.done) return;
+    double frac = st.frac;
+    bool secant = false;
+    if (st.want_defl) {
+        /* regula falsi on the deflated determinant: root at lo + w / (1 + r),
+         * r = |f(hi)/f(lo)| exp(-beta w) */
+        const double shift = -bsum * st.wdt * 1.4426950408889634; /* in powers of two */
+        double de = (double)(st.fhe - st.fle) + shift;
+        de = de > 1000.0 ? 1000.0 : (de < -1000.0 ? -1000.0 : de);
+        const double dei = floor(de);
+        const double r = ldexp(fabs(st.fhm / st.flm) * exp2(de - dei), (int)dei);
+        const double t = 1.0 / (1.0 + r);
+        /* the estimate sits at fraction t; when it hugs one end, sample at twice its distance
+         * from that end: the root then (almost surely) lies between the end and the sample and
+         * the bracket collapses to ~2x the interpolation error instead of creeping one-sidedly */
+        if (t > 0.0 && t < 1.0) {
+            frac = t < 0.25 ? 2.0 * t : (t > 0.75 ? 1.0 - 2.0 * (1.0 - t) : t);
+            secant = true;
         }
-        s = lo + wdt * frac;
-        if (!(s > lo && s < hi)) { s = lo + 0.5 * wdt; secant = false; }
-        side = secant ? 1 : 0;
-        beta = wdt;
-        if (!(s > lo && s < hi)) {
-            done = 1; s = lo; c = clo;
+    }
+    double s = st.lo + st.wdt * frac;
+    if (!(s > st.lo && s < st.hi)) { s = st.lo + 0.5 * st.wdt; secant = false; }
+    st.side = secant ? 1 : 0;
+    st.beta = st.wdt;
+    if (!(s > st.lo && s < st.hi)) {
+        st.done = 1; st.s = st.lo; st.c = st.clo;
+    } else {
+        st.s = s;
+        st.want_count = 1;
+    }
+}
+
+BSP_HD double bsp_round_pivmin(const BspEigChunk &g, int p, double s)
+{
+    return 1e-30 * (g.pbound[p * 4 + 2] + fabs(s) * g.pbound[p * 4 + 3]);
+}
+
+/* phase 5: fold the inertia of the sample (st.c, st.sfm, st.sfe) into the bracket and publish */
+BSP_HD void bsp_round_end(const BspEigChunk &g, int p, int e, int round, BspRoundState &st)
+{
+    const size_t per = (size_t)g.npencil * g.ldw;
+    const size_t id = (size_t)p * g.ldw + e;
+    const size_t wr = (size_t)((round + 1) & 1) * per;
+    if (st.want_count) {
+        if (st.c <= e) {
+            st.lo = st.s; st.clo = st.c; st.flm = st.sfm; st.fle = st.sfe;
         } else {
-            const double *fbH = g.fbH + (size_t)p * g.nrows * FS;
-            const double *fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
-            const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(s) * g.pbound[p * 4 + 3]);
-            c = bsp_sturm_count<B>(fbH, fbS, g.npad, s, pivmin, nullptr, &sfm, &sfe);
-            if (c <= e) {
-                lo = s; clo = c; flm = sfm; fle = sfe;
-            } else {
-                hi = s; chi = c; fhm = sfm; fhe = sfe;
-            }
+            st.hi = st.s; st.chi = st.c; st.fhm = st.sfm; st.fhe = st.sfe;
         }
     }
 #if defined(BSP_TRACE) && !defined(__CUDA_ARCH__)
-    if (round >= BSP_TRACE && !done) printf("r%d e%d lo=%.17g hi=%.17g w=%.3e gp=%.3e clo=%d chi=%d fl=(%g,%d) fh=(%g,%d) s=%.17g c=%d\n", round, e, lo, hi, hi-lo, gp, clo, chi, flm, fle, fhm, fhe, s, c);
+    if (round >= BSP_TRACE && !st.done) printf("r%d e%d lo=%.17g hi=%.17g w=%.3e gp=%.3e clo=%d chi=%d fl=(%g,%d) fh=(%g,%d) s=%.17g c=%d\n", round, e, st.lo, st.hi, st.hi-st.lo, st.gp, st.clo, st.chi, st.flm, st.fle, st.fhm, st.fhe, st.s, st.c);
 #endif
-    g.lo[wr + id] = lo; g.hi[wr + id] = hi; g.clo[wr + id] = clo; g.chi[wr + id] = chi;
-    g.flm[id] = flm; g.fle[id] = fle; g.fhm[id] = fhm; g.fhe[id] = fhe; g.side[id] = side; g.beta[id] = beta;
+    g.lo[wr + id] = st.lo; g.hi[wr + id] = st.hi; g.clo[wr + id] = st.clo; g.chi[wr + id] = st.chi;
+    g.flm[id] = st.flm; g.fle[id] = st.fle; g.fhm[id] = st.fhm; g.fhe[id] = st.fhe; g.side[id] = st.side; g.beta[id] = st.beta;
     const size_t po = (size_t)(round & 1) * per + id;
-    g.samp_s[po] = s;
-    g.samp_c[po] = c;
-    g.samp_fm[po] = sfm;
-    g.samp_fe[po] = sfe;
-    g.gap[id] = gp;
-    g.done[id] = done;
-    if (!done) {
+    g.samp_s[po] = st.s;
+    g.samp_c[po] = st.c;
+    g.samp_fm[po] = st.sfm;
+    g.samp_fe[po] = st.sfe;
+    g.gap[id] = st.gp;
+    g.done[id] = st.done;
+    if (!st.done) {
         /* counters[0]: brackets still open; counters[2]: open AND not yet isolating one eigenvalue */
-        const int crowded = (chi - clo != 1 || !(gp > 0.0)) ? 1 : 0;
+        const int crowded = (st.chi - st.clo != 1 || !(st.gp > 0.0)) ? 1 : 0;
 #if defined(__CUDA_ARCH__)
         atomicAdd(g.counters + BSP_C_OPEN, 1);
         if (crowded) atomicAdd(g.counters + BSP_C_CROWDED, 1);
@@ -449,6 +565,26 @@ BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round
         g.counters[BSP_C_CROWDED] += crowded;
 #endif
     }
+}
+
+/* the whole round of one eigen index from global memory (host replay; the round kernel runs the same
+ * phases with block-cooperative shared-memory staging in phases 2 and 4) */
+template <int B>
+BSP_HD void bsp_multisection_round(const BspEigChunk &g, int p, int e, int round)
+{
+    constexpr int FS = 2 * B + 2;
+    if (e >= g.n) return;
+    BspRoundState st;
+    bsp_round_begin(g, p, e, round, st);
+    double bsum = 0.0;
+    if (st.want_defl) bsum = bsp_deflation_sum(g, p, e, round, st);
+    bsp_round_pick(st, bsum);
+    if (st.want_count) {
+        const double *fbH = g.fbH + (size_t)p * g.nrows * FS;
+        const double *fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
+        st.c = bsp_sturm_count<B>(fbH, fbS, g.npad, st.s, bsp_round_pivmin(g, p, st.s), nullptr, &st.sfm, &st.sfe);
+    }
+    bsp_round_end(g, p, e, round, st);
 }
 
 /* bookkeeping after a bracketing round (one thread, after every eigen index of the chunk has run):
@@ -509,19 +645,17 @@ BSP_HD void bsp_refine_prepare(const BspEigChunk &g, int p, int e)
  *   iter == 0 : rhs = hashed uniform(-1,1)      (plain inverse iteration)
  *   iter  > 0 : rhs = scale * R  (R written by the previous B pass)
  * ------------------------------------------------------------------------- */
-template <int B>
-BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
+template <int B, class Src>
+BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int iter, bool active, Src &src)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
-    if (e >= g.n) return;
-    const size_t id = (size_t)p * g.ldw + e;
-    if (g.status[id] & BSP_ST_CONVERGED) return;
+    constexpr int TR = BSP_TILE_STEPS(B);
     const int n = g.n, npad = g.npad, ldw = g.ldw;
-    const double *__restrict__ fbH = g.fbH + (size_t)p * g.nrows * FS;
-    const double *__restrict__ fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
-    const double sigma = g.sigma[id];
-    const double sc = g.scale[id];
+    const int ntiles = npad / TR;
+    const size_t id = (size_t)p * g.ldw + (active ? e : 0);
+    const double sigma = active ? g.sigma[id] : 0.0;
+    const double sc = active ? g.scale[id] : 1.0;
     const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(sigma) * g.pbound[p * 4 + 3]);
     const double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
     double *__restrict__ Lp = g.L + (size_t)p * npad * K1 * ldw + e;
@@ -535,72 +669,89 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
         if (row >= n) return 0.0;
         return (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)row) : Rp[(size_t)row * ldw];
     };
-#pragma unroll
-    for (int r = 0; r < K1; ++r) {
-#pragma unroll
-        for (int c = 0; c < K1; ++c) {
-            if (c <= r) {
-                const int off = r * FS + (c - r + B);
-                w[r][c] = fma(-sigma, BSP_LDG(fbS + off), BSP_LDG(fbH + off));
-            } else {
-                w[r][c] = 0.0;
-            }
-        }
-        y[r] = scr * rhs(r);
-    }
-    /* software pipelines: next band row (L1) one step ahead, right-hand side
+    /* software pipelines: next band row one step ahead, right-hand side
      * (HBM) a whole unrolled block (B+1 rows) ahead */
     double nh[K1], ns[K1], rq[K1];
+    src.begin_forward(ntiles);
+    for (int tl = 0; tl < ntiles; ++tl) {
+        const double *tH, *tS;
+        src.acquire_forward(tl, tH, tS);
+        if (active) {
+            if (tl == 0) {
+                bsp_sturm_init<B, Src::GL>(w, nh, ns, tH, tS, sigma);
 #pragma unroll
-    for (int m = 0; m <= B; ++m) {
-        nh[m] = BSP_LDG(fbH + (size_t)K1 * FS + m);
-        ns[m] = BSP_LDG(fbS + (size_t)K1 * FS + m);
-        rq[m] = rhs(K1 + m);
-    }
-    for (int j0 = 0; j0 < npad; j0 += K1) {
-#pragma unroll
-        for (int t = 0; t < K1; ++t) {
-            const int j = j0 + t;
-            const double rnew = scr * rq[t];    /* rhs of row j+K1, loaded K1 steps ago */
-            rq[t] = rhs(j + 2 * K1);
-            double d = w[t][t];
-            if (fabs(d) < pivmin) d = -pivmin;
-            if (d < 0.0) ++cnt;
-            const double rinv = BSP_RCP(d);
-            double col[K1], l[K1];
-            const double y0 = y[t];
-            double *Lrow = Lp + (size_t)j * K1 * ldw;
-            Lrow[0] = y0 * rinv;
-#pragma unroll
-            for (int i = 1; i <= B; ++i) {
-                col[i] = w[(t + i) % K1][t];
-                l[i] = col[i] * rinv;
-                Lrow[(size_t)i * ldw] = l[i];
-                y[(t + i) % K1] = fma(-l[i], y0, y[(t + i) % K1]);
-            }
-#pragma unroll
-            for (int m = 1; m <= B; ++m) {
-#pragma unroll
-                for (int i = m; i <= B; ++i) {
-                    w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
+                for (int r = 0; r < K1; ++r) {
+                    y[r] = scr * rhs(r);
+                    rq[r] = rhs(K1 + r);
                 }
             }
-            {
-                const double *hrow = fbH + (size_t)(j + K1 + 1) * FS;
-                const double *srow = fbS + (size_t)(j + K1 + 1) * FS;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int gq = 0; gq < TR; gq += K1) {
+                const int j0 = tl * TR + gq;
+                const double *hnext = tH + (size_t)(gq + K1 + 1) * FS, *snext = tS + (size_t)(gq + K1 + 1) * FS;
 #pragma unroll
-                for (int m = 0; m <= B; ++m) {
-                    w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
-                    nh[m] = BSP_LDG(hrow + m);
-                    ns[m] = BSP_LDG(srow + m);
+                for (int t = 0; t < K1; ++t) {
+                    const int j = j0 + t;
+                    const double rnew = scr * rq[t];    /* rhs of row j+K1, loaded K1 steps ago */
+                    rq[t] = rhs(j + 2 * K1);
+                    double d = w[t][t];
+                    if (fabs(d) < pivmin) d = -pivmin;
+                    if (d < 0.0) ++cnt;
+                    const double rinv = BSP_RCP(d);
+                    double col[K1], l[K1];
+                    const double y0 = y[t];
+                    double *Lrow = Lp + (size_t)j * K1 * ldw;
+                    Lrow[0] = y0 * rinv;
+#pragma unroll
+                    for (int i = 1; i <= B; ++i) {
+                        col[i] = w[(t + i) % K1][t];
+                        l[i] = col[i] * rinv;
+                        Lrow[(size_t)i * ldw] = l[i];
+                        y[(t + i) % K1] = fma(-l[i], y0, y[(t + i) % K1]);
+                    }
+#pragma unroll
+                    for (int m = 1; m <= B; ++m) {
+#pragma unroll
+                        for (int i = m; i <= B; ++i) {
+                            w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
+                        }
+                    }
+                    {
+                        const double *hrow = hnext + (size_t)t * FS;
+                        const double *srow = snext + (size_t)t * FS;
+#pragma unroll
+                        for (int m = 0; m <= B; ++m) {
+                            w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
+                            nh[m] = bsp_ld<Src::GL>(hrow + m);
+                            ns[m] = bsp_ld<Src::GL>(srow + m);
+                        }
+                    }
+                    y[t] = rnew;
                 }
             }
-            y[t] = rnew;
         }
+        src.release_forward(tl, ntiles);
     }
     /* inertia -> bracket (buffer 0) */
-    if (cnt <= e) { if (sigma > g.lo[id]) g.lo[id] = sigma; }
-    else { if (sigma < g.hi[id]) g.hi[id] = sigma; }
+    if (active) {
+        if (cnt <= e) { if (sigma > g.lo[id]) g.lo[id] = sigma; }
+        else { if (sigma < g.hi[id]) g.hi[id] = sigma; }
+    }
+}
+
+BSP_HD bool bsp_refine_active(const BspEigChunk &g, int p, int e)
+{
+    return e < g.n && !(g.status[(size_t)p * g.ldw + e] & BSP_ST_CONVERGED);
+}
+
+template <int B>
+BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
+{
+    if (!bsp_refine_active(g, p, e)) return;
+    BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
+    bsp_factor_forward_rows<B>(g, p, e, iter, true, src);
 }
 
 /* ------------------------------------------------------------------------- *
@@ -616,23 +767,22 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
 #define BSP_BACK_PF 2 /* factor rows in flight per thread in the back sweep */
 #endif
 
-template <int B>
-BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now, int corr_next)
+template <int B, class Src>
+BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int corr_now, int corr_next, bool active, Src &src)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
     constexpr int PF = BSP_BACK_PF;
-    if (e >= g.n) return;
-    const size_t id = (size_t)p * g.ldw + e;
-    if (g.status[id] & BSP_ST_CONVERGED) return;
+    constexpr int TR = BSP_TILE_STEPS(B);
+    static_assert(TR % PF == 0, "tiles hold whole groups of PF steps");
+    const size_t id = (size_t)p * g.ldw + (active ? e : 0);
     const int n = g.n, npad = g.npad, ldw = g.ldw;
-    const double *__restrict__ fbH = g.fbH + (size_t)p * g.nrows * FS;
-    const double *__restrict__ fbS = g.fbS + (size_t)g.inst[p] * g.nrows * FS;
+    const int ntiles = npad / TR;
     const double *__restrict__ Lp = g.L + (size_t)p * npad * K1 * ldw + e;
     double *__restrict__ Xp = g.X + (size_t)p * g.xrows * ldw + e;
     double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
-    const double sc = g.scale[id];
-    const double rho_p = g.rho[id]; /* rho' */
+    const double sc = active ? g.scale[id] : 1.0;
+    const double rho_p = active ? g.rho[id] : 0.0; /* rho' */
     const double cx = corr_now ? sc : 0.0;
 
     /* windows over rows j .. j+B (index 0 = row j after the shift of step j):
@@ -651,88 +801,102 @@ BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now
      * issued, which is what hides the HBM latency of this purely streaming sweep */
     double Lq[PF][K1], xq[PF];
     auto fetch = [&](int q, int row) {
-        if (row >= 0) {
-            const double *Lrow = Lp + (size_t)row * K1 * ldw;
+        /* rows -PF..-1 are asked for by the last steps and never used: row 0 is loaded again instead */
+        const int r = row < 0 ? 0 : row;
+        const double *Lrow = Lp + (size_t)r * K1 * ldw;
 #pragma unroll
-            for (int i = 0; i <= B; ++i) Lq[q][i] = Lrow[(size_t)i * ldw];
-            xq[q] = (corr_now && row < n) ? Xp[(size_t)row * ldw] : 0.0;
+        for (int i = 0; i <= B; ++i) Lq[q][i] = Lrow[(size_t)i * ldw];
+        xq[q] = (corr_now && r < n) ? Xp[(size_t)r * ldw] : 0.0;
+    };
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q) fetch(q, npad - 1 - q);
+    }
+    /* one step; rowH/rowS = band row j (its upper half A(j, j..j+B) is column j of the symmetric band).
+     * The row is read at the top of the step from the staged tile: the shared-memory latency hides behind the
+     * dependent chain of the substitution, and nothing is carried in registers across steps.
+     * TAIL = false: a step of the tiles (0 <= j < npad);
+     * TAIL = true: one of the last B steps (j < 0), which only drain the windows. */
+    auto step = [&](auto tail_c, int j, int q, const double *rowH, const double *rowS) {
+        constexpr bool TAIL = decltype(tail_c)::value;
+        double ah[K1], as[K1];
+        if (!TAIL) {
+#pragma unroll
+            for (int d = 0; d <= B; ++d) {
+                ah[d] = bsp_ld<Src::GL>(rowH + B + d);
+                as[d] = bsp_ld<Src::GL>(rowS + B + d);
+            }
+        }
+        /* shift the windows: index 0 becomes row j */
+#pragma unroll
+        for (int i = B; i >= 1; --i) { yw[i] = yw[i - 1]; xv[i] = xv[i - 1]; hs[i] = hs[i - 1]; ss[i] = ss[i - 1]; }
+        double xn = 0.0;
+        if (!TAIL) {
+            double yj = Lq[q][0];
+#pragma unroll
+            for (int i = B; i >= 1; --i) yj = fma(-Lq[q][i], yw[i], yj);   /* yw[i] = y_{j+i} */
+            yw[0] = yj;
+            if (j < n) {
+                xn = fma(cx, xq[q], -yj);
+                Xp[(size_t)j * ldw] = xn;
+            }
+            fetch(q, j - PF);   /* slot q is free again: row j-PF goes in flight */
         } else {
+            yw[0] = 0.0;
+        }
+        xv[0] = xn;
+        /* column j: A(j+d, j) = A(j, j+d) = ah[d] */
+        double h0 = 0.0, s0 = 0.0;
+        if (!TAIL) {
 #pragma unroll
-            for (int i = 0; i <= B; ++i) Lq[q][i] = 0.0;
-            xq[q] = 0.0;
+            for (int d = 1; d <= B; ++d) {
+                hs[d] = fma(ah[d], xn, hs[d]);
+                ss[d] = fma(as[d], xn, ss[d]);
+            }
+#pragma unroll
+            for (int d = 0; d <= B; ++d) {
+                h0 = fma(ah[d], xv[d], h0);
+                s0 = fma(as[d], xv[d], s0);
+            }
+        }
+        hs[0] = h0;
+        ss[0] = s0;
+        /* row i = j + B is complete */
+        const int i = j + B;
+        if (i < n) {
+            const double h = hs[B], sv = ss[B], xi = xv[B];
+            xSx = fma(xi, sv, xSx);
+            xHx = fma(xi, h, xHx);
+            const double r = fma(-rho_p, sv, h);
+            resmax = fmax(resmax, fabs(r));
+            Rp[(size_t)i * ldw] = corr_next ? r : sv;
         }
     };
+    src.begin_backward(ntiles);
+    for (int tl = ntiles - 1; tl >= 0; --tl) {
+        const double *tH, *tS;   /* band row tl*TR */
+        src.acquire_backward(tl, ntiles, tH, tS);
+        if (active) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int jl = TR - 1; jl >= 0; jl -= PF) {
 #pragma unroll
-    for (int q = 0; q < PF; ++q) fetch(q, npad - 1 - q);
-    /* band column of the row about to be processed, one step ahead (L1 latency) */
-    double ah[K1], as[K1];
-    {
-        const int r0 = npad - 1;
-#pragma unroll
-        for (int d = 0; d <= B; ++d) {
-            ah[d] = BSP_LDG(fbH + (size_t)r0 * FS + B + d);
-            as[d] = BSP_LDG(fbS + (size_t)r0 * FS + B + d);
+                for (int q = 0; q < PF; ++q) {
+                    const int off = (jl - q) * FS;
+                    step(BspFalse(), tl * TR + jl - q, q, tH + off, tS + off);
+                }
+            }
         }
+        src.release_backward(tl, ntiles);
     }
-
-    for (int j0 = npad - 1; j0 >= -B; j0 -= PF) {
+    if (!active) return;
+    /* the last B steps only drain the windows */
+    for (int j0 = -1; j0 >= -B; j0 -= PF) {
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
             const int j = j0 - q;
-            if (j >= -B) {
-                /* shift the windows: index 0 becomes row j */
-#pragma unroll
-                for (int i = B; i >= 1; --i) { yw[i] = yw[i - 1]; xv[i] = xv[i - 1]; hs[i] = hs[i - 1]; ss[i] = ss[i - 1]; }
-                double xn = 0.0;
-                if (j >= 0) {
-                    double yj = Lq[q][0];
-#pragma unroll
-                    for (int i = B; i >= 1; --i) yj = fma(-Lq[q][i], yw[i], yj);   /* yw[i] = y_{j+i} */
-                    yw[0] = yj;
-                    if (j < n) {
-                        xn = fma(cx, xq[q], -yj);
-                        Xp[(size_t)j * ldw] = xn;
-                    }
-                } else {
-                    yw[0] = 0.0;
-                }
-                fetch(q, j - PF);   /* slot q is free again: row j-PF goes in flight */
-                xv[0] = xn;
-                /* column j: A(j+d, j) = A(j, j+d) = ah[d] */
-                double h0 = 0.0, s0 = 0.0;
-                if (j >= 0) {
-#pragma unroll
-                    for (int d = 1; d <= B; ++d) {
-                        hs[d] = fma(ah[d], xn, hs[d]);
-                        ss[d] = fma(as[d], xn, ss[d]);
-                    }
-#pragma unroll
-                    for (int d = 0; d <= B; ++d) {
-                        h0 = fma(ah[d], xv[d], h0);
-                        s0 = fma(as[d], xv[d], s0);
-                    }
-                    /* prefetch the column of row j-1 */
-                    if (j >= 1) {
-#pragma unroll
-                        for (int d = 0; d <= B; ++d) {
-                            ah[d] = BSP_LDG(fbH + (size_t)(j - 1) * FS + B + d);
-                            as[d] = BSP_LDG(fbS + (size_t)(j - 1) * FS + B + d);
-                        }
-                    }
-                }
-                hs[0] = h0;
-                ss[0] = s0;
-                /* row i = j + B is complete */
-                const int i = j + B;
-                if (i < n) {
-                    const double h = hs[B], sv = ss[B], xi = xv[B];
-                    xSx = fma(xi, sv, xSx);
-                    xHx = fma(xi, h, xHx);
-                    const double r = fma(-rho_p, sv, h);
-                    resmax = fmax(resmax, fabs(r));
-                    Rp[(size_t)i * ldw] = corr_next ? r : sv;
-                }
-            }
+            if (j >= -B) step(BspTrue(), j, q, nullptr, nullptr);
         }
     }
     /* bookkeeping + next shift */
@@ -756,6 +920,14 @@ BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now
         if (fabs(sig - rho_p) < delta) sig = (rho_p + delta < hi) ? rho_p + delta : rho_p - delta;
     }
     g.sigma[id] = sig;
+}
+
+template <int B>
+BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now, int corr_next)
+{
+    if (!bsp_refine_active(g, p, e)) return;
+    BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
+    bsp_back_substitute_rows<B>(g, p, e, corr_now, corr_next, true, src);
 }
 
 /* ------------------------------------------------------------------------- *

@@ -64,11 +64,216 @@ __device__ __forceinline__ bool bsp_last_block(int *arrive)
     return s_last && threadIdx.x == 0;
 }
 
+/* ------------------------------------------------------------------------- *
+ * Band-row staging for the sweeps.  Every thread of a block works on the same
+ * pencil and walks its band rows in the same order, so the rows are brought
+ * into shared memory once per block by the bulk-copy engine (cp.async.bulk,
+ * completion on an mbarrier) in tiles of BSP_TILE_GROUPS*(B+1) rows, two tiles
+ * in flight, and the threads read them as shared-memory broadcasts.  A tile
+ * carries B+2 extra rows: step j brings in row j+B+2 (one step of register
+ * prefetch on top of the B+1-row window), so all reads of the steps of tile t
+ * stay inside tile t.  Without the staging the leading warp of an SM pays the
+ * L2 latency on every new row and the other warps queue up behind it.
+ * ------------------------------------------------------------------------- */
+template <int B>
+struct BspTile {
+    static constexpr int K1 = B + 1;
+    static constexpr int FS = 2 * B + 2;
+    static constexpr int TR = BSP_TILE_STEPS(B);  /* steps per tile                         */
+    static constexpr int ROWS = TR + K1 + 1;      /* band rows staged per (forward) tile    */
+    static constexpr int DOUBLES = ROWS * FS;     /* per matrix                             */
+    static constexpr unsigned ROW_BYTES = FS * 8u; /* 16(B+1): bulk copies stay 16-byte aligned */
+    static constexpr int STAGES = 2;
+    static constexpr int SMEM_DOUBLES = STAGES * 2 * DOUBLES;
+};
+static_assert(BSP_SEG_BLOCKS % 4 == 0, "npad must be a whole number of tiles");
+
+__device__ __forceinline__ unsigned bsp_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bsp_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bsp_smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void bsp_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "BSP_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra BSP_DONE_%=;\n\t"
+        "bra BSP_WAIT_%=;\n\t"
+        "BSP_DONE_%=:\n\t}" ::"r"(bsp_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/* one thread: expect `bytes` on the barrier and start the bulk copy global -> shared */
+__device__ __forceinline__ void bsp_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bsp_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(bsp_smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void bsp_mbar_expect(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bsp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+/* row source of the sweeps (see BspRowsGlobal): tiles staged in shared memory.  One object per sweep; every
+ * thread of the block calls the same sequence (the release is a block barrier), thread 0 drives the copies. */
+template <int B>
+struct BspRowsStaged {
+    using T = BspTile<B>;
+    static constexpr bool GL = false;
+    double *sm;
+    uint64_t *bars;   /* two mbarriers, count 1, not used by an earlier sweep of this launch */
+    const double *gH, *gS;
+
+    __device__ __forceinline__ void issue(int seq, const double *srcH, const double *srcS, int rows, int dst_row)
+    {
+        const int stage = seq & 1;
+        double *dH = sm + (size_t)stage * 2 * T::DOUBLES + (size_t)dst_row * T::FS, *dS = dH + T::DOUBLES;
+        const unsigned bytes = (unsigned)rows * T::ROW_BYTES;
+        bsp_mbar_expect(bars + stage, 2u * bytes);
+        bsp_bulk_g2s(dH, srcH, bytes, bars + stage);
+        bsp_bulk_g2s(dS, srcS, bytes, bars + stage);
+    }
+    __device__ __forceinline__ void acquire(int seq, const double *&tH, const double *&tS)
+    {
+        const int stage = seq & 1;
+        bsp_mbar_wait(bars + stage, (unsigned)(seq >> 1) & 1u);
+        tH = sm + (size_t)stage * 2 * T::DOUBLES;
+        tS = tH + T::DOUBLES;
+    }
+    __device__ __forceinline__ void fence_before_first_copy()
+    {
+        /* the stages may alias shared memory the block wrote with ordinary stores before the last barrier */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    /* forward: tile t = rows t*TR .. t*TR + ROWS - 1 */
+    __device__ __forceinline__ void issue_forward(int t)
+    {
+        issue(t, gH + (size_t)t * T::TR * T::FS, gS + (size_t)t * T::TR * T::FS, T::ROWS, 0);
+    }
+    __device__ __forceinline__ void begin_forward(int ntiles)
+    {
+        if (threadIdx.x == 0) {
+            fence_before_first_copy();
+            issue_forward(0);
+            if (ntiles > 1) issue_forward(1);
+        }
+    }
+    __device__ __forceinline__ void acquire_forward(int t, const double *&tH, const double *&tS) { acquire(t, tH, tS); }
+    __device__ __forceinline__ void release_forward(int t, int ntiles)
+    {
+        __syncthreads(); /* every thread is through with this stage: it may be refilled */
+        if (threadIdx.x == 0 && t + 2 < ntiles) issue_forward(t + 2);
+    }
+    /* backward: tile t = rows t*TR .. (t+1)*TR - 1, taken in descending t */
+    __device__ __forceinline__ void issue_backward(int t, int ntiles)
+    {
+        issue(ntiles - 1 - t, gH + (size_t)t * T::TR * T::FS, gS + (size_t)t * T::TR * T::FS, T::TR, 0);
+    }
+    __device__ __forceinline__ void begin_backward(int ntiles)
+    {
+        if (threadIdx.x == 0) {
+            fence_before_first_copy();
+            issue_backward(ntiles - 1, ntiles);
+            if (ntiles > 1) issue_backward(ntiles - 2, ntiles);
+        }
+    }
+    __device__ __forceinline__ void acquire_backward(int t, int ntiles, const double *&tH, const double *&tS)
+    {
+        acquire(ntiles - 1 - t, tH, tS);
+    }
+    __device__ __forceinline__ void release_backward(int t, int ntiles)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0 && t - 2 >= 0) issue_backward(t - 2, ntiles);
+    }
+};
+
+__device__ __forceinline__ void bsp_stage_bars_init(uint64_t *bars)
+{
+    if (threadIdx.x == 0) {
+        bsp_mbar_init(bars, 1);
+        bsp_mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+
+__device__ __forceinline__ float bsp_frcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+/* block-cooperative form of bsp_deflation_sum: the bracket midpoints of the pencil go through shared memory in
+ * tiles of BSP_DEFL_TILE; same four summation chains as the plain form */
+#define BSP_DEFL_TILE 1024
+__device__ __forceinline__ double bsp_deflation_sum_block(const BspEigChunk &g, int p, int e, int round, const BspRoundState &st,
+                                                          bool want, double *sm)
+{
+    const int n = g.n;
+    const size_t rd = (size_t)(round & 1) * (size_t)g.npencil * g.ldw;
+    const double *Lo = g.lo + rd + (size_t)p * g.ldw, *Hi = g.hi + rd + (size_t)p * g.ldw;
+    const double mid = 0.5 * (st.lo + st.hi);
+    float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+    for (int k0 = 0; k0 < n; k0 += BSP_DEFL_TILE) {
+        const int cnt = min(BSP_DEFL_TILE, n - k0), cnt4 = (cnt + 3) & ~3;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt4; i += blockDim.x)
+            sm[i] = (i < cnt) ? 0.5 * (Lo[k0 + i] + Hi[k0 + i]) : INFINITY; /* 1/(mid - inf) = 0 */
+        __syncthreads();
+        if (want) {
+            const int el = e - k0;
+#pragma unroll 2
+            for (int i = 0; i < cnt4; i += 4) {
+                const double2 m01 = *reinterpret_cast<const double2 *>(sm + i);
+                const double2 m23 = *reinterpret_cast<const double2 *>(sm + i + 2);
+                const float d0 = (float)(mid - m01.x), d1 = (float)(mid - m01.y);
+                const float d2 = (float)(mid - m23.x), d3 = (float)(mid - m23.y);
+                const float r0 = bsp_frcp_fast(d0), r1 = bsp_frcp_fast(d1), r2 = bsp_frcp_fast(d2), r3 = bsp_frcp_fast(d3);
+                b0 += (i != el && d0 != 0.0f) ? r0 : 0.0f;
+                b1 += (i + 1 != el && d1 != 0.0f) ? r1 : 0.0f;
+                b2 += (i + 2 != el && d2 != 0.0f) ? r2 : 0.0f;
+                b3 += (i + 3 != el && d3 != 0.0f) ? r3 : 0.0f;
+            }
+        }
+    }
+    __syncthreads();
+    return (double)b0 + (double)b1 + (double)b2 + (double)b3;
+}
+
 template <int B>
 __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) bsp_round_kernel(BspEigChunk g, int round, int max_rounds, int open_ok)
 {
+    using T = BspTile<B>;
+    constexpr int SMD = T::SMEM_DOUBLES > BSP_DEFL_TILE ? T::SMEM_DOUBLES : BSP_DEFL_TILE;
+    __shared__ __align__(128) double sm[SMD];
+    __shared__ __align__(8) uint64_t bars[2];
     if (g.counters[BSP_C_BRACKETED]) return;       /* written by the previous kernel: grid-uniform */
-    bsp_multisection_round<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, round);
+    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < g.n;
+    bsp_stage_bars_init(bars);
+    BspRoundState st;
+    st.want_defl = 0; st.want_count = 0; st.done = 1; st.lo = st.hi = 0.0;
+    if (valid) bsp_round_begin(g, p, e, round, st);
+    /* the barriers below also publish the mbarrier initialisation */
+    double bsum = 0.0;
+    if (__syncthreads_or(st.want_defl)) bsum = bsp_deflation_sum_block(g, p, e, round, st, st.want_defl != 0, sm);
+    if (valid) bsp_round_pick(st, bsum);
+    if (__syncthreads_or(st.want_count)) {
+        constexpr int FS = 2 * B + 2;
+        BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+        double fm;
+        int fe;
+        const double pivmin = st.want_count ? bsp_round_pivmin(g, p, st.s) : 1.0;
+        const int c = bsp_sturm_sweep<B>(src, g.npad, st.want_count != 0, st.s, pivmin, nullptr, &fm, &fe);
+        if (st.want_count) { st.c = c; st.sfm = fm; st.sfe = fe; }
+    }
+    if (valid) bsp_round_end(g, p, e, round, st);
     if (bsp_last_block(g.counters + BSP_C_ARRIVE)) bsp_round_ctl(g, round, max_rounds, open_ok);
 }
 
@@ -80,15 +285,31 @@ __global__ void bsp_prepare_kernel(BspEigChunk g)
 template <int B>
 __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_kernel(BspEigChunk g, int iter, int optional)
 {
+    __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
+    __shared__ __align__(8) uint64_t bars[2];
     if (optional && g.counters[BSP_C_REFINED]) return;
-    bsp_factor_forward<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter);
+    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = bsp_refine_active(g, p, e);
+    bsp_stage_bars_init(bars);
+    if (!__syncthreads_or(active)) return;
+    constexpr int FS = 2 * B + 2;
+    BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    bsp_factor_forward_rows<B>(g, p, e, iter, active, src);
 }
 
 template <int B>
 __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_back_kernel(BspEigChunk g, int corr_now, int corr_next, int optional)
 {
+    __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
+    __shared__ __align__(8) uint64_t bars[2];
     if (optional && g.counters[BSP_C_REFINED]) return;
-    bsp_back_substitute<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, corr_now, corr_next);
+    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = bsp_refine_active(g, p, e);
+    bsp_stage_bars_init(bars);
+    if (!__syncthreads_or(active)) return;
+    constexpr int FS = 2 * B + 2;
+    BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    bsp_back_substitute_rows<B>(g, p, e, corr_now, corr_next, active, src);
 }
 
 template <int B>
