@@ -181,8 +181,8 @@ BSP_HD double bsp_ld(const double *p)
 }
 
 template <int B, bool GL>
-BSP_HD void bsp_sturm_init(double (&w)[B + 1][B + 1], double (&nh)[B + 1], double (&ns)[B + 1],
-                           const double *__restrict__ rowsH, const double *__restrict__ rowsS, double sigma)
+BSP_HD void bsp_sturm_init(double (&w)[B + 1][B + 1], const double *__restrict__ rowsH,
+                           const double *__restrict__ rowsS, double sigma)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
@@ -198,26 +198,26 @@ BSP_HD void bsp_sturm_init(double (&w)[B + 1][B + 1], double (&nh)[B + 1], doubl
             }
         }
     }
-    /* software pipeline: the band row that enters the window at the end of
-     * step j is loaded during step j-1, so its latency hides behind the
-     * pivot arithmetic instead of stalling the first FMA that needs it */
-#pragma unroll
-    for (int m = 0; m <= B; ++m) {
-        nh[m] = bsp_ld<GL>(rowsH + (size_t)K1 * FS + m);
-        ns[m] = bsp_ld<GL>(rowsS + (size_t)K1 * FS + m);
-    }
 }
 
-/* steps j0 .. j0+B; hnext / snext = band row j0 + B + 2 (the row loaded during step j0) */
+/* steps j0 .. j0+B; hnext / snext = band row j0 + B + 1, the row that enters the window at the end of step
+ * j0.  It is read at the top of its step: from a staged tile the shared-memory latency hides behind the pivot
+ * arithmetic of the step, and no row is carried in registers across steps. */
 template <int B, bool GL>
-BSP_HD void bsp_sturm_group(double (&w)[B + 1][B + 1], double (&nh)[B + 1], double (&ns)[B + 1],
-                            const double *__restrict__ hnext, const double *__restrict__ snext, double sigma,
-                            double pivmin, int j0, int &cnt, int &first, double &fm, int &fe)
+BSP_HD void bsp_sturm_group(double (&w)[B + 1][B + 1], const double *__restrict__ hnext,
+                            const double *__restrict__ snext, double sigma, double pivmin, int j0, int &cnt,
+                            int &first, double &fm, int &fe)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
 #pragma unroll
     for (int t = 0; t < K1; ++t) {
+        double nh[K1], ns[K1];
+#pragma unroll
+        for (int m = 0; m <= B; ++m) {
+            nh[m] = bsp_ld<GL>(hnext + (size_t)t * FS + m);
+            ns[m] = bsp_ld<GL>(snext + (size_t)t * FS + m);
+        }
         double d = w[t][t];
         if (fabs(d) < pivmin) d = -pivmin;
         if (d < 0.0) { ++cnt; if (first < 0) first = j0 + t; }
@@ -237,25 +237,16 @@ BSP_HD void bsp_sturm_group(double (&w)[B + 1][B + 1], double (&nh)[B + 1], doub
                 w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
             }
         }
-        /* row j retires; its slot takes row j+B+1 (loaded during the previous
-         * step); the registers are refilled at once with row j+B+2 */
-        {
-            const double *hrow = hnext + (size_t)t * FS;
-            const double *srow = snext + (size_t)t * FS;
+        /* row j retires; its slot takes row j+B+1 */
 #pragma unroll
-            for (int m = 0; m <= B; ++m) {
-                w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
-                nh[m] = bsp_ld<GL>(hrow + m);
-                ns[m] = bsp_ld<GL>(srow + m);
-            }
-        }
+        for (int m = 0; m <= B; ++m) w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
     }
 }
 
 struct BspTrue { static constexpr bool value = true; };
 struct BspFalse { static constexpr bool value = false; };
 
-/* row source reading global memory.  Forward tiles: pointer to band row t*TR, rows t*TR .. (t+1)*TR+B+1 are
+/* row source reading global memory.  Forward tiles: pointer to band row t*TR, rows t*TR .. (t+1)*TR+B are
  * read.  Backward tiles (taken in descending t): same pointer, rows t*TR .. (t+1)*TR-1 are read. */
 template <int B>
 struct BspRowsGlobal {
@@ -283,7 +274,7 @@ BSP_HD int bsp_sturm_sweep(Src &src, int npad, bool active, double sigma, double
     constexpr int FS = 2 * B + 2;
     constexpr int TR = BSP_TILE_STEPS(B);
     const int ntiles = npad / TR;
-    double w[K1][K1], nh[K1], ns[K1];
+    double w[K1][K1];
     int cnt = 0, first = -1;
     double fm = 0.5; /* det(H - sigma S) = prod of pivots = fm * 2^fe */
     int fe = 1;
@@ -292,13 +283,13 @@ BSP_HD int bsp_sturm_sweep(Src &src, int npad, bool active, double sigma, double
         const double *tH, *tS;
         src.acquire_forward(t, tH, tS);
         if (active) {
-            if (t == 0) bsp_sturm_init<B, Src::GL>(w, nh, ns, tH, tS, sigma);
+            if (t == 0) bsp_sturm_init<B, Src::GL>(w, tH, tS, sigma);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
             for (int gq = 0; gq < TR; gq += K1)
-                bsp_sturm_group<B, Src::GL>(w, nh, ns, tH + (size_t)(gq + K1 + 1) * FS, tS + (size_t)(gq + K1 + 1) * FS,
-                                            sigma, pivmin, t * TR + gq, cnt, first, fm, fe);
+                bsp_sturm_group<B, Src::GL>(w, tH + (size_t)(gq + K1) * FS, tS + (size_t)(gq + K1) * FS, sigma, pivmin,
+                                            t * TR + gq, cnt, first, fm, fe);
         }
         src.release_forward(t, ntiles);
     }
@@ -669,16 +660,16 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int iter
         if (row >= n) return 0.0;
         return (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)row) : Rp[(size_t)row * ldw];
     };
-    /* software pipelines: next band row one step ahead, right-hand side
-     * (HBM) a whole unrolled block (B+1 rows) ahead */
-    double nh[K1], ns[K1], rq[K1];
+    /* software pipeline: right-hand side (HBM) a whole unrolled block (B+1 rows) ahead; the band row that
+     * enters the window at the end of a step is read from the tile at the top of the step */
+    double rq[K1];
     src.begin_forward(ntiles);
     for (int tl = 0; tl < ntiles; ++tl) {
         const double *tH, *tS;
         src.acquire_forward(tl, tH, tS);
         if (active) {
             if (tl == 0) {
-                bsp_sturm_init<B, Src::GL>(w, nh, ns, tH, tS, sigma);
+                bsp_sturm_init<B, Src::GL>(w, tH, tS, sigma);
 #pragma unroll
                 for (int r = 0; r < K1; ++r) {
                     y[r] = scr * rhs(r);
@@ -690,10 +681,16 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int iter
 #endif
             for (int gq = 0; gq < TR; gq += K1) {
                 const int j0 = tl * TR + gq;
-                const double *hnext = tH + (size_t)(gq + K1 + 1) * FS, *snext = tS + (size_t)(gq + K1 + 1) * FS;
+                const double *hnext = tH + (size_t)(gq + K1) * FS, *snext = tS + (size_t)(gq + K1) * FS;
 #pragma unroll
                 for (int t = 0; t < K1; ++t) {
                     const int j = j0 + t;
+                    double nh[K1], ns[K1];
+#pragma unroll
+                    for (int m = 0; m <= B; ++m) {
+                        nh[m] = bsp_ld<Src::GL>(hnext + (size_t)t * FS + m);
+                        ns[m] = bsp_ld<Src::GL>(snext + (size_t)t * FS + m);
+                    }
                     const double rnew = scr * rq[t];    /* rhs of row j+K1, loaded K1 steps ago */
                     rq[t] = rhs(j + 2 * K1);
                     double d = w[t][t];
@@ -718,16 +715,8 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int iter
                             w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
                         }
                     }
-                    {
-                        const double *hrow = hnext + (size_t)t * FS;
-                        const double *srow = snext + (size_t)t * FS;
 #pragma unroll
-                        for (int m = 0; m <= B; ++m) {
-                            w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
-                            nh[m] = bsp_ld<Src::GL>(hrow + m);
-                            ns[m] = bsp_ld<Src::GL>(srow + m);
-                        }
-                    }
+                    for (int m = 0; m <= B; ++m) w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
                     y[t] = rnew;
                 }
             }

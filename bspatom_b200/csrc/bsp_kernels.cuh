@@ -69,10 +69,9 @@ __device__ __forceinline__ bool bsp_last_block(int *arrive)
  * pencil and walks its band rows in the same order, so the rows are brought
  * into shared memory once per block by the bulk-copy engine (cp.async.bulk,
  * completion on an mbarrier) in tiles of BSP_TILE_GROUPS*(B+1) rows, two tiles
- * in flight, and the threads read them as shared-memory broadcasts.  A tile
- * carries B+2 extra rows: step j brings in row j+B+2 (one step of register
- * prefetch on top of the B+1-row window), so all reads of the steps of tile t
- * stay inside tile t.  Without the staging the leading warp of an SM pays the
+ * in flight, and the threads read them as shared-memory broadcasts.  A forward
+ * tile carries B+1 extra rows: step j brings row j+B+1 into the window, so all
+ * reads of the steps of tile t stay inside tile t.  Without the staging the leading warp of an SM pays the
  * L2 latency on every new row and the other warps queue up behind it.
  * ------------------------------------------------------------------------- */
 template <int B>
@@ -80,7 +79,7 @@ struct BspTile {
     static constexpr int K1 = B + 1;
     static constexpr int FS = 2 * B + 2;
     static constexpr int TR = BSP_TILE_STEPS(B);  /* steps per tile                         */
-    static constexpr int ROWS = TR + K1 + 1;      /* band rows staged per (forward) tile    */
+    static constexpr int ROWS = TR + K1;          /* band rows staged per (forward) tile    */
     static constexpr int DOUBLES = ROWS * FS;     /* per matrix                             */
     static constexpr unsigned ROW_BYTES = FS * 8u; /* 16(B+1): bulk copies stay 16-byte aligned */
     static constexpr int STAGES = 2;
