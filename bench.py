@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--ref-ls", type=int, default=3, help="l values per reference step")
     ap.add_argument("--workers", type=int, default=0, help="chunk streams (0 = library default)")
     ap.add_argument("--recompute", type=int, default=-1, help="1/0: check-pointed vs stored-factor refinement (-1 = library default)")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (experiments), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -210,6 +211,8 @@ def main():
         atom.set_option("workers", args.workers)
     if args.recompute >= 0:
         atom.set_option("recompute", args.recompute)
+    for kv in args.opt:
+        atom.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     inp, items = workload_items(bsp, rank, args.zrep, args.grid)
     nsolve = len(items)
     n_e = nsolve * NFUN

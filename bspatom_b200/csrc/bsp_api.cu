@@ -41,10 +41,14 @@ struct Options {
     int max_rounds = 90;      /* cap used when a chunk has to be redone */
     int rounds_enqueued = 26; /* bracketing rounds enqueued up front (surplus ones return at once) */
     int min_iters = 3;
+    int trace = 0;        /* diagnostics: print the chunk / copy timeline of every run to stderr */
     int max_iters = 12;
     int chunk = 0; /* 0 = auto */
     int workers = 2; /* concurrent chunk streams (1..4) */
     int stream_chunks = 8; /* chunks per group when results stream to the host */
+#define BSP_MAX_STREAMS 8
+#define BSP_MAIL_INTS (1 << 18)
+#define BSP_MAIL_REPORT_INTS (1 << 14)
     int recompute = 0; /* 1: check-pointed refinement (re-eliminate in the back sweep; measured slower, see
                           DESIGN.md section 12), 0: store the factor */
 };
@@ -53,7 +57,7 @@ struct Group {
     int k = 0, B = 0, n = 0, nkp = 0, ka = 0, npad = 0, nrows = 0, xrows = 0, ldw = 0, FS = 0;
     int ninst = 0, npencil = 0;
     bool any_vtab = false;
-    int chunk_cached = 0; /* pencils per chunk decided on the first run */
+    int budget_pencils = 0; /* pencils whose workspaces fit the memory budget (decided on the first run) */
     std::vector<int> prob_index; /* pencil -> caller's problem index */
     std::vector<int> inst, nvec;
     std::vector<double> cl;
@@ -93,8 +97,12 @@ struct bspatom_handle_s {
      * cudaMalloc/cudaFree of the multi-GB result buffers costs tens of ms per call */
     std::multimap<size_t, void *> pool;
     size_t pool_bytes = 0;
-    int *h_counter = nullptr;     /* pinned + mapped */
+    /* mailbox: pinned host memory mapped into the device.  Kernels write the small per-run outputs (chunk
+     * reports, info flags) straight into it, so the host reads them after a stream synchronise without a
+     * D2H transfer -- which would queue behind the bulk eigenvector copies of this or another handle. */
+    int *h_counter = nullptr;     /* pinned + mapped, BSP_MAIL_INTS ints */
     int *h_counter_dev = nullptr; /* device view of h_counter */
+    bool mail_info = false;       /* the mailbox holds pdinfo / bad of the last run (see run_internal) */
     double stats[24] = {0};
     long long launches = 0;
     /* second chunk stream: an auxiliary context (own stream, workspace, polling word, event pool)
@@ -393,6 +401,11 @@ struct GpuExec {
         note();
         timed_end(h, s);
     }
+    void resid() {
+        const int s = timed_begin(h, 2);
+        bsp_resid_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g); note();
+        timed_end(h, s);
+    }
     void check(int it) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it); note(); }
 };
 
@@ -579,7 +592,7 @@ bspatom_handle new_context(int device_id)
     h->dev = device_id;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaHostAlloc((void **)&h->h_counter, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->h_counter, sizeof(int) * BSP_MAIL_INTS, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void **)&h->h_counter_dev, h->h_counter, 0) != cudaSuccess) {
         cudaGetLastError();
         delete h;
@@ -663,14 +676,15 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "conv_tol") h->opt.conv_tol = v;
     else if (s == "res_tol") h->opt.res_tol = v;
     else if (s == "max_rounds") h->opt.max_rounds = (int)v;
-    else if (s == "min_iters") h->opt.min_iters = std::max(3, (int)v);
+    else if (s == "trace") h->opt.trace = (int)v;
+    else if (s == "min_iters") h->opt.min_iters = std::max(2, (int)v);
     else if (s == "max_iters") h->opt.max_iters = std::max(3, (int)v);
     else if (s == "rounds_enqueued") h->opt.rounds_enqueued = std::max(1, (int)v);
     else if (s == "first_check_round" || s == "check_every") { /* accepted for compatibility: the schedule no longer polls */ }
     else if (s == "chunk") h->opt.chunk = (int)v;
-    else if (s == "recompute") { h->opt.recompute = v != 0.0; for (auto &G : h->groups) G.chunk_cached = 0; }
+    else if (s == "recompute") { h->opt.recompute = v != 0.0; for (auto &G : h->groups) G.budget_pencils = 0; }
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
-    else if (s == "workers") h->opt.workers = std::min(4, std::max(1, (int)v));
+    else if (s == "workers") h->opt.workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
     else return -2;
     return 0;
 }
@@ -806,8 +820,32 @@ bool is_pinned(const void *p)
     return at.type == cudaMemoryTypeHost;
 }
 
-/* enqueue on st_copy the D2H of pencils [p0, p0+np) of group G into the caller's E / C */
-int copy_chunk_out(bspatom_handle h, Group &G, int p0, int np, double *E, double *C)
+/* One result-copy stream per device, shared by every handle of the process.  The D2H of the eigenvectors is
+ * the longest leg of an end-to-end batch (PCIe), so the order in which batches reach the copy engine decides
+ * how well consecutive batches overlap: with one FIFO stream the copies of batch i (all enqueued when batch i
+ * was submitted) run before those of batch i+1, batch i returns as early as it can and its handle's next
+ * batch computes while batch i+1 is being copied.  Per-handle copy streams would share the link instead and
+ * let both batches finish late and together. */
+struct CopyQueue {
+    std::mutex mu;          /* held while one batch enqueues its chunks: keeps its copies contiguous */
+    cudaStream_t st = nullptr;
+};
+CopyQueue *copy_queue(int dev)
+{
+    static std::mutex g_mu;
+    static CopyQueue *g_q[128] = {nullptr};
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (dev < 0 || dev >= 128) return nullptr;
+    if (!g_q[dev]) {
+        CopyQueue *q = new CopyQueue();
+        if (cudaStreamCreateWithFlags(&q->st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete q; return nullptr; }
+        g_q[dev] = q;   /* lives as long as the process */
+    }
+    return g_q[dev];
+}
+
+/* enqueue on `cs` the D2H of pencils [p0, p0+np) of group G into the caller's E / C */
+int copy_chunk_out(bspatom_handle h, Group &G, int p0, int np, double *E, double *C, cudaStream_t cs)
 {
     int p = p0;
     while (p < p0 + np) {
@@ -816,11 +854,11 @@ int copy_chunk_out(bspatom_handle h, Group &G, int p0, int np, double *E, double
         const int i0 = G.prob_index[p];
         const int cnt = q - p + 1;
         if (E) CU(cudaMemcpyAsync(E + h->e_off[i0], G.d_E + (size_t)p * G.n, sizeof(double) * (size_t)cnt * G.n,
-                                  cudaMemcpyDeviceToHost, h->st_copy));
+                                  cudaMemcpyDeviceToHost, cs));
         if (C) {
             const long long nel = (q + 1 < G.npencil ? G.coff[q + 1] : G.c_elems) - G.coff[p];
             if (nel > 0) CU(cudaMemcpyAsync(C + h->c_off[i0], G.d_C + G.coff[p], sizeof(double) * (size_t)nel,
-                                            cudaMemcpyDeviceToHost, h->st_copy));
+                                            cudaMemcpyDeviceToHost, cs));
         }
         p = q + 1;
     }
@@ -871,20 +909,21 @@ BspRunStats stats_from_report(const int *r)
 }
 
 /* enqueue (on the copy stream, after the chunk's own stream reached this point) the D2H of a chunk */
-int stream_chunk_out(bspatom_handle h, bspatom_handle ctx, Group &G, int p0, int np, double *E_out, double *C_out)
+int stream_chunk_out(bspatom_handle h, bspatom_handle ctx, Group &G, int p0, int np, double *E_out, double *C_out,
+                     cudaStream_t cs)
 {
     cudaEvent_t e;
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->chunk_done.push_back(e);
     CU(cudaEventRecord(e, ctx->st));
-    CU(cudaStreamWaitEvent(h->st_copy, e, 0));
-    return copy_chunk_out(h, G, p0, np, E_out, C_out);
+    CU(cudaStreamWaitEvent(cs, e, 0));
+    return copy_chunk_out(h, G, p0, np, E_out, C_out, cs);
 }
 
 /* E_out / C_out: pinned host buffers (or NULL).  Every chunk's whole schedule is enqueued up front on one
  * of `workers` streams (each with its own workspace) -- the host reads nothing back while the batch runs,
  * so the GPU never waits for it and the chunk streams back-fill each other's tail waves.  When E_out / C_out
- * are given, each chunk's results are copied out on st_copy as soon as the chunk is final. */
+ * are given, each chunk's results are copied out on the device's copy queue as soon as the chunk is final. */
 int run_internal(bspatom_handle h, double *E_out, double *C_out)
 {
     int rc = 0;
@@ -898,8 +937,12 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     h->chunk_done.clear();
     double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0;
     int rounds = 0, iters = 0, redone = 0;
-    cudaEvent_t e0, e1, e2;
+    cudaEvent_t e0, e1, e2, copies_done;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
+    CU(cudaEventCreateWithFlags(&copies_done, cudaEventDisableTiming));
+    CopyQueue *cq = (E_out || C_out) ? copy_queue(h->dev) : nullptr;
+    if ((E_out || C_out) && !cq) { h->err = "cannot create the result-copy stream"; return BSPATOM_ECUDA; }
+    if (cq) CU(cudaEventRecord(copies_done, cq->st));
     CU(cudaEventRecord(e0, h->st));
     const BspSchedule sch = {std::min(h->opt.rounds_enqueued, h->opt.max_rounds), h->opt.min_iters,
                              std::min(h->opt.max_iters, h->opt.min_iters + 2)};
@@ -926,51 +969,43 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         const size_t per_pencil = carve_chunk(G, 1, nullptr, c, h->opt.recompute != 0);
         const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
         const int fill_pencils = std::max(1, (148 * 4 + blocks_per_pencil - 1) / blocks_per_pencil); /* one full wave */
+        const bool streaming = (E_out || C_out);
+        /* Chunk streams: `workers` streams (each with its own workspace) run chunks concurrently and
+         * back-fill each other's partial waves and latency-bound kernels (late bracketing rounds); blocks
+         * run a whole sweep (~1 ms), so stream priorities cannot order the chunks -- the chunk sizes do.
+         * Resident batches use `workers` equal chunks.  When results stream to the host the D2H (PCIe,
+         * ~53 GB/s, 57 ms per 408 solves of N = 1000) is the longer leg: the batch is cut into
+         * `stream_chunks` equal chunks so that the first copy starts after 2/stream_chunks of the work and
+         * the copy engine then stays busy.  (Measured: growing or shrinking chunk sizes lose -- a chunk of
+         * less than ~40 pencils takes ~17 ms whatever its size, the kernel chain being latency-bound.) */
         int workers = std::max(1, std::min(h->opt.workers, G.npencil / fill_pencils));
-        int chunk = h->opt.chunk;
-        if (chunk <= 0) chunk = G.chunk_cached;
-        if (chunk <= 0) {
+        if (G.budget_pencils <= 0) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
             size_t have = h->ws.bytes + h->pool_bytes;
             for (auto x : h->aux) have += x->ws.bytes;
             const size_t budget = std::min<size_t>((free_b + have) / 2, (size_t)64 << 30);
-            chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil / workers, 1024));
-            G.chunk_cached = chunk;
+            G.budget_pencils = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil, 1 << 24));
         }
-        chunk = std::min(chunk, G.npencil);
-        int nchunks = (G.npencil + chunk - 1) / chunk;
-        if (h->opt.chunk <= 0) {
-            /* equal chunks; one per stream, and more when results go to the host (if each still fills
-             * the GPU) so that the D2H of a finished chunk hides behind the others */
-            int want = workers;
-            if (E_out || C_out) want = std::max(want, std::min(h->opt.stream_chunks, std::max(1, (2 * G.npencil) / fill_pencils)));
-            nchunks = std::max(nchunks, want);
-        }
-        chunk = (G.npencil + nchunks - 1) / nchunks;
-        nchunks = (G.npencil + chunk - 1) / chunk;
-        workers = std::min(workers, nchunks);
-        /* chunk boundaries.  When results stream to the host the chunks shrink towards the end
-         * (weights n+2, n+1, ... over the same number of chunks): the copies start as early as before,
-         * but the last chunks -- whose copies nothing can hide -- are small. */
+        const int cap = std::max(1, std::min(G.budget_pencils / workers, 1024));   /* workspace per stream */
+        int chunk = h->opt.chunk, nchunks;
         std::vector<int> bounds(1, 0);
-        if ((E_out || C_out) && h->opt.chunk <= 0 && nchunks >= 4) {
-            std::vector<double> wgt(nchunks);
-            double tot = 0.0;
-            for (int i = 0; i < nchunks; ++i) { wgt[i] = (double)(nchunks + 2 - i); tot += wgt[i]; }
-            double accw = 0.0;
-            for (int i = 0; i < nchunks; ++i) {
-                accw += wgt[i];
-                int b = (i + 1 == nchunks) ? G.npencil : (int)(G.npencil * accw / tot + 0.5);
-                b = std::max(b, bounds.back() + 1);
-                b = std::min(b, G.npencil - (nchunks - 1 - i));
-                bounds.push_back(b);
-            }
+        if (chunk > 0) {
+            chunk = std::min(chunk, G.npencil);
+            nchunks = (G.npencil + chunk - 1) / chunk;
+            for (int i = 1; i <= nchunks; ++i) bounds.push_back(std::min(i * chunk, G.npencil));
+        } else {
+            int want = workers;
+            if (streaming) want = std::max(want, std::min(h->opt.stream_chunks, std::max(1, (2 * G.npencil) / fill_pencils)));
+            nchunks = std::max(want, (G.npencil + cap - 1) / cap);
+            nchunks = std::min(nchunks, G.npencil);
+            const int eq = (G.npencil + nchunks - 1) / nchunks;
+            nchunks = (G.npencil + eq - 1) / eq;
+            for (int i = 1; i <= nchunks; ++i) bounds.push_back(std::min(i * eq, G.npencil));
             chunk = 0;
             for (int i = 0; i < nchunks; ++i) chunk = std::max(chunk, bounds[i + 1] - bounds[i]);
-        } else {
-            for (int i = 1; i <= nchunks; ++i) bounds.push_back(std::min(i * chunk, G.npencil));
         }
+        workers = std::min(workers, nchunks);
         const size_t need = carve_chunk(G, chunk, nullptr, c, h->opt.recompute != 0);
         if ((rc = ensure_workspace(h, need))) return rc;
         while ((int)h->aux.size() < workers - 1) {
@@ -986,12 +1021,18 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             ctx.push_back(h->aux[w - 1]);
         }
         /* ---- enqueue every chunk; no host read-back in here ---- */
+        const bool report_mail = (size_t)nchunks * BSP_C_WORDS <= BSP_MAIL_REPORT_INTS;
         int *d_report = nullptr;
-        if ((rc = dev_alloc(h, &d_report, (size_t)nchunks * BSP_C_WORDS))) return rc;
+        if (report_mail) d_report = h->h_counter_dev;
+        else if ((rc = dev_alloc(h, &d_report, (size_t)nchunks * BSP_C_WORDS))) return rc;
         std::vector<ChunkTimes> tms(nchunks);
         for (int ci = 0; ci < nchunks; ++ci)
             for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tms[ci].ev[i]));
+        struct TraceRec { int ci, w, np; cudaEvent_t done, c0, c1; };
+        std::vector<TraceRec> trace;
         std::vector<long long> load(workers, 0);      /* pencils assigned to each stream so far */
+        std::unique_lock<std::mutex> copy_lock;
+        if (streaming) copy_lock = std::unique_lock<std::mutex>(cq->mu);
         for (int ci = 0; ci < nchunks; ++ci) {
             int wsel = 0;
             for (int w = 1; w < workers; ++w) if (load[w] < load[wsel]) wsel = w;
@@ -1004,13 +1045,39 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
                 if (x != h) h->err = x->err;
                 return rc;
             }
-            if (E_out || C_out)
-                if ((rc = stream_chunk_out(h, x, G, p0, np, E_out, C_out))) return rc;
+            if (E_out || C_out) {
+                if (h->opt.trace) {     /* diagnostics: when was the chunk final, when did its copy run */
+                    TraceRec tr = {ci, wsel, np, nullptr, nullptr, nullptr};
+                    CU(cudaEventCreate(&tr.done)); CU(cudaEventCreate(&tr.c0)); CU(cudaEventCreate(&tr.c1));
+                    CU(cudaEventRecord(tr.done, x->st));
+                    CU(cudaStreamWaitEvent(cq->st, tr.done, 0));
+                    CU(cudaEventRecord(tr.c0, cq->st));
+                    if ((rc = copy_chunk_out(h, G, p0, np, E_out, C_out, cq->st))) return rc;
+                    CU(cudaEventRecord(tr.c1, cq->st));
+                    trace.push_back(tr);
+                } else if ((rc = stream_chunk_out(h, x, G, p0, np, E_out, C_out, cq->st))) return rc;
+            }
+        }
+        if (streaming) {
+            CU(cudaEventRecord(copies_done, cq->st));   /* behind this batch's last copy */
+            copy_lock.unlock();
         }
         for (auto x : ctx) CU(cudaStreamSynchronize(x->st));
+        if (!trace.empty()) {
+            CU(cudaEventSynchronize(copies_done));
+            for (auto &tr : trace) {
+                float a = 0, b = 0, c = 0;
+                cudaEventElapsedTime(&a, e0, tr.done); cudaEventElapsedTime(&b, e0, tr.c0); cudaEventElapsedTime(&c, e0, tr.c1);
+                fprintf(stderr, "[bspatom trace %p] chunk %d stream %d pencils %d final at %.2f ms, copy %.2f -> %.2f ms\n", (void *)h,
+                        tr.ci, tr.w, tr.np, a, b, c);
+                cudaEventDestroy(tr.done); cudaEventDestroy(tr.c0); cudaEventDestroy(tr.c1);
+            }
+            trace.clear();
+        }
         /* ---- reports; chunks that ran out of rounds / iterations are redone with the full limits ---- */
         std::vector<int> report((size_t)nchunks * BSP_C_WORDS);
-        CU(cudaMemcpy(report.data(), d_report, report.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        if (report_mail) memcpy(report.data(), h->h_counter, report.size() * sizeof(int));
+        else CU(cudaMemcpy(report.data(), d_report, report.size() * sizeof(int), cudaMemcpyDeviceToHost));
         for (int ci = 0; ci < nchunks; ++ci) {
             BspRunStats st = stats_from_report(&report[(size_t)ci * BSP_C_WORDS]);
             const bool again = (st.brackets_crowded > 0 || st.unconverged > 0) &&
@@ -1022,11 +1089,15 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
                 const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
                 CU(cudaMemsetAsync(G.d_bad + p0, 0, sizeof(int) * np, h->st));
                 if ((rc = enqueue_chunk(h, G, p0, np, cc, sch_redo, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) return rc;
-                if (E_out || C_out)
-                    if ((rc = stream_chunk_out(h, h, G, p0, np, E_out, C_out))) return rc;
+                if (streaming) {
+                    std::lock_guard<std::mutex> lk(cq->mu);
+                    if ((rc = stream_chunk_out(h, h, G, p0, np, E_out, C_out, cq->st))) return rc;
+                    CU(cudaEventRecord(copies_done, cq->st));
+                }
                 CU(cudaStreamSynchronize(h->st));
-                CU(cudaMemcpy(&report[(size_t)ci * BSP_C_WORDS], d_report + (size_t)ci * BSP_C_WORDS, BSP_C_WORDS * sizeof(int),
-                              cudaMemcpyDeviceToHost));
+                if (report_mail) memcpy(&report[(size_t)ci * BSP_C_WORDS], h->h_counter + (size_t)ci * BSP_C_WORDS, BSP_C_WORDS * sizeof(int));
+                else CU(cudaMemcpy(&report[(size_t)ci * BSP_C_WORDS], d_report + (size_t)ci * BSP_C_WORDS, BSP_C_WORDS * sizeof(int),
+                                   cudaMemcpyDeviceToHost));
                 st = stats_from_report(&report[(size_t)ci * BSP_C_WORDS]);
             }
             rounds = std::max(rounds, st.rounds);
@@ -1039,20 +1110,37 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         for (auto x : ctx) timed_collect(x);
         for (int ci = 0; ci < nchunks; ++ci)
             for (int i = 0; i < 4; ++i) cudaEventDestroy(tms[ci].ev[i]);
-        dev_free(h, d_report, (size_t)nchunks * BSP_C_WORDS);
+        if (!report_mail) dev_free(h, d_report, (size_t)nchunks * BSP_C_WORDS);
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, e1, e2)); t_asm += ms;
+    }
+    /* info flags of every group -> mailbox (all chunk streams are drained at this point) */
+    {
+        size_t need = 0;
+        for (auto &G : h->groups) need += (size_t)G.ninst + (size_t)G.npencil;
+        h->mail_info = need <= (size_t)(BSP_MAIL_INTS - BSP_MAIL_REPORT_INTS);
+        if (h->mail_info) {
+            size_t off = BSP_MAIL_REPORT_INTS;
+            for (auto &G : h->groups) {
+                bsp_copy_ints_kernel<<<(G.ninst + 255) / 256, 256, 0, h->st>>>(h->h_counter_dev + off, G.d_pdinfo, G.ninst);
+                off += (size_t)G.ninst;
+                bsp_copy_ints_kernel<<<(G.npencil + 255) / 256, 256, 0, h->st>>>(h->h_counter_dev + off, G.d_bad, G.npencil);
+                off += (size_t)G.npencil;
+                h->launches += 2;
+            }
+            CU(cudaGetLastError());
+        }
     }
     CU(cudaEventRecord(e1, h->st));   /* every chunk stream has been drained */
     CU(cudaStreamSynchronize(h->st));
     {
         auto t0 = std::chrono::steady_clock::now();
-        if (E_out || C_out) CU(cudaStreamSynchronize(h->st_copy));
+        if (E_out || C_out) CU(cudaEventSynchronize(copies_done));
         h->stats[21] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     float total = 0;
     CU(cudaEventElapsedTime(&total, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(copies_done);
     h->stats[0] = (double)(h->launches + aux_launches() - launches0);
     h->stats[1] = rounds; h->stats[2] = iters;
     /* stage times are summed over the chunk streams: with several streams they overlap in wall time */
@@ -1076,11 +1164,19 @@ int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info)
     int rc = check_device(h);
     if (rc) return rc;
     if (!h->ran) { h->err = "batch_download before batch_run"; return BSPATOM_ESTATE; }
+    size_t mail_off = BSP_MAIL_REPORT_INTS;
     for (auto &G : h->groups) {
         G.pdinfo.resize(G.ninst);
         G.bad.resize(G.npencil);
-        CU(cudaMemcpyAsync(G.pdinfo.data(), G.d_pdinfo, sizeof(int) * G.ninst, cudaMemcpyDeviceToHost, h->st));
-        CU(cudaMemcpyAsync(G.bad.data(), G.d_bad, sizeof(int) * G.npencil, cudaMemcpyDeviceToHost, h->st));
+        if (h->mail_info) {
+            memcpy(G.pdinfo.data(), h->h_counter + mail_off, sizeof(int) * G.ninst);
+            mail_off += (size_t)G.ninst;
+            memcpy(G.bad.data(), h->h_counter + mail_off, sizeof(int) * G.npencil);
+            mail_off += (size_t)G.npencil;
+        } else {
+            CU(cudaMemcpyAsync(G.pdinfo.data(), G.d_pdinfo, sizeof(int) * G.ninst, cudaMemcpyDeviceToHost, h->st));
+            CU(cudaMemcpyAsync(G.bad.data(), G.d_bad, sizeof(int) * G.npencil, cudaMemcpyDeviceToHost, h->st));
+        }
         /* pencils of a group are usually contiguous in the caller's order: merge runs */
         int p = 0;
         while (p < G.npencil) {

@@ -756,12 +756,16 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
 #define BSP_BACK_PF 2 /* factor rows in flight per thread in the back sweep */
 #endif
 
-template <int B, class Src>
+/* RESID = true turns the pass into a pure residual evaluation of the vector already in X: nothing is solved and
+ * X is not written; r = (H - rho S) x with the CURRENT Rayleigh quotient goes to R (ready for a correction
+ * step) and its scaled max norm to res.  The plain passes only know the residual against the previous
+ * quotient, so this cheap pass (no factor traffic) is what lets the iteration stop after the second solve. */
+template <int B, bool RESID = false, class Src>
 BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int corr_now, int corr_next, bool active, Src &src)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
-    constexpr int PF = BSP_BACK_PF;
+    constexpr int PF = RESID ? 2 * K1 : BSP_BACK_PF; /* rows in flight per thread */
     constexpr int TR = BSP_TILE_STEPS(B);
     static_assert(TR % PF == 0, "tiles hold whole groups of PF steps");
     const size_t id = (size_t)p * g.ldw + (active ? e : 0);
@@ -792,10 +796,12 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int cor
     auto fetch = [&](int q, int row) {
         /* rows -PF..-1 are asked for by the last steps and never used: row 0 is loaded again instead */
         const int r = row < 0 ? 0 : row;
-        const double *Lrow = Lp + (size_t)r * K1 * ldw;
+        if (!RESID) {
+            const double *Lrow = Lp + (size_t)r * K1 * ldw;
 #pragma unroll
-        for (int i = 0; i <= B; ++i) Lq[q][i] = Lrow[(size_t)i * ldw];
-        xq[q] = (corr_now && r < n) ? Xp[(size_t)r * ldw] : 0.0;
+            for (int i = 0; i <= B; ++i) Lq[q][i] = Lrow[(size_t)i * ldw];
+        }
+        xq[q] = ((RESID || corr_now) && r < n) ? Xp[(size_t)r * ldw] : 0.0;
     };
     if (active) {
 #pragma unroll
@@ -821,13 +827,17 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int cor
         for (int i = B; i >= 1; --i) { yw[i] = yw[i - 1]; xv[i] = xv[i - 1]; hs[i] = hs[i - 1]; ss[i] = ss[i - 1]; }
         double xn = 0.0;
         if (!TAIL) {
-            double yj = Lq[q][0];
+            if (RESID) {
+                xn = xq[q];
+            } else {
+                double yj = Lq[q][0];
 #pragma unroll
-            for (int i = B; i >= 1; --i) yj = fma(-Lq[q][i], yw[i], yj);   /* yw[i] = y_{j+i} */
-            yw[0] = yj;
-            if (j < n) {
-                xn = fma(cx, xq[q], -yj);
-                Xp[(size_t)j * ldw] = xn;
+                for (int i = B; i >= 1; --i) yj = fma(-Lq[q][i], yw[i], yj);   /* yw[i] = y_{j+i} */
+                yw[0] = yj;
+                if (j < n) {
+                    xn = fma(cx, xq[q], -yj);
+                    Xp[(size_t)j * ldw] = xn;
+                }
             }
             fetch(q, j - PF);   /* slot q is free again: row j-PF goes in flight */
         } else {
@@ -858,7 +868,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int cor
             xHx = fma(xi, h, xHx);
             const double r = fma(-rho_p, sv, h);
             resmax = fmax(resmax, fabs(r));
-            Rp[(size_t)i * ldw] = corr_next ? r : sv;
+            Rp[(size_t)i * ldw] = (RESID || corr_next) ? r : sv;
         }
     };
     src.begin_backward(ntiles);
@@ -887,6 +897,10 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int cor
             const int j = j0 - q;
             if (j >= -B) step(BspTrue(), j, q, nullptr, nullptr);
         }
+    }
+    if (RESID) {
+        g.res[id] = (xSx > 0.0 && xSx < INFINITY) ? resmax * sc : INFINITY;
+        return;
     }
     /* bookkeeping + next shift */
     double lo = g.lo[id], hi = g.hi[id];
@@ -917,6 +931,14 @@ BSP_HD void bsp_back_substitute(const BspEigChunk &g, int p, int e, int corr_now
     if (!bsp_refine_active(g, p, e)) return;
     BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
     bsp_back_substitute_rows<B>(g, p, e, corr_now, corr_next, true, src);
+}
+
+template <int B>
+BSP_HD void bsp_residual_pass(const BspEigChunk &g, int p, int e)
+{
+    if (!bsp_refine_active(g, p, e)) return;
+    BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
+    bsp_back_substitute_rows<B, true>(g, p, e, 0, 1, true, src);
 }
 
 /* ------------------------------------------------------------------------- *

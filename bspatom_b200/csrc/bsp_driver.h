@@ -14,6 +14,7 @@
  *   void prepare();                           // hand brackets to the refinement
  *   void factor(int iter, int optional);      // F pass (optional: skipped once everything converged)
  *   void back(int corr_now, int corr_next, int optional);
+ *   void resid();                             // residual of the current vectors against their own Rayleigh quotient
  *   void check(int iter);                     // convergence marks + bookkeeping
  */
 #ifndef BSP_DRIVER_H
@@ -21,7 +22,7 @@
 
 struct BspSchedule {
     int rounds;     /* bracketing rounds enqueued (the flag makes surplus ones free)       */
-    int min_iters;  /* refinement iterations always done (>= 3)                             */
+    int min_iters;  /* refinement iterations always done (>= 2: the two plain solves; default 3) */
     int max_iters;  /* iterations enqueued; those beyond min_iters only touch stragglers   */
 };
 
@@ -39,11 +40,17 @@ inline void bsp_enqueue_chunk(Exec &ex, const BspSchedule &sch)
     ex.bounds();
     for (int r = 0; r < sch.rounds; ++r) ex.round(r, sch.rounds);
     ex.prepare();
-    /* iteration t: plain for t < 2, residual-correction form afterwards */
+    /* iteration t: plain for t < 2, residual-correction form afterwards.  The default schedule always does
+     * the first correction step (min_iters = 3): it is what brings the S-orthogonality of neighbouring
+     * vectors from ~1e-8 to ~1e-12.  With min_iters = 2 ("fast" setting) the check may retire eigenpairs
+     * after the second plain solve; a plain pass only knows its residual against the PREVIOUS Rayleigh
+     * quotient, so one cheap residual pass (no factor traffic) evaluates (H - rho S) x with the current one
+     * first, and the correction iterations then only touch what is left. */
     for (int t = 0; t < sch.max_iters; ++t) {
         const int optional = (t >= sch.min_iters);
         ex.factor(t, optional);
         ex.back(t >= 2, t + 1 >= 2, optional);
+        if (t == 1 && sch.min_iters <= 2) ex.resid();
         if (t + 1 >= sch.min_iters) ex.check(t);
     }
 }

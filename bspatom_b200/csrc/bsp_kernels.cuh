@@ -311,6 +311,21 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) b
     bsp_back_substitute_rows<B>(g, p, e, corr_now, corr_next, active, src);
 }
 
+/* residual of the vectors in X against their own Rayleigh quotient (min_iters = 2 schedule) */
+template <int B>
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_resid_kernel(BspEigChunk g)
+{
+    __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = bsp_refine_active(g, p, e);
+    bsp_stage_bars_init(bars);
+    if (!__syncthreads_or(active)) return;
+    constexpr int FS = 2 * B + 2;
+    BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    bsp_back_substitute_rows<B, true>(g, p, e, 0, 1, active, src);
+}
+
 template <int B>
 __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_ckpt_kernel(BspEigChunk g, int iter, int optional)
 {
@@ -339,6 +354,12 @@ __global__ void bsp_report_kernel(BspEigChunk g, int *report)
         report[threadIdx.x] = g.counters[threadIdx.x];
         g.counters[threadIdx.x] = 0;
     }
+}
+
+__global__ void bsp_copy_ints_kernel(int *dst, const int *src, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
 }
 
 __global__ void bsp_finalize_kernel(BspEigChunk g, double *E, double *fac, int *bad, double res_tol)

@@ -3,6 +3,7 @@
 // that `pytest -m "not gpu"` can check the solver logic (indexing, bracket
 // bookkeeping, iteration schedule) without a GPU.  It is never built into
 // libbspatom.so and nothing in the product imports it.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -26,6 +27,12 @@ struct EmulExec {
         if (g.counters[BSP_C_BRACKETED]) return;
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_multisection_round<B>(g, p, e, r);
+        if (getenv("BSP_EMUL_TRACE")) {   /* per-round census of the brackets (diagnostics) */
+            int secant = 0;
+            for (int p = 0; p < g.npencil; ++p)
+                for (int e = 0; e < g.n; ++e) secant += g.side[(size_t)p * g.ldw + e] && !g.done[(size_t)p * g.ldw + e];
+            fprintf(stderr, "round %2d open %6d crowded %6d interpolating %6d\n", r, g.counters[BSP_C_OPEN], g.counters[BSP_C_CROWDED], secant);
+        }
         bsp_round_ctl(g, r, max_rounds, open_ok);
     }
     void prepare() {
@@ -49,10 +56,15 @@ struct EmulExec {
                 else bsp_back_substitute<B>(g, p, e, cn, cx);
             }
     }
+    void resid() {
+        for (int p = 0; p < g.npencil; ++p)
+            for (int e = 0; e < g.n; ++e) bsp_residual_pass<B>(g, p, e);
+    }
     void check(int it) {
         if (g.counters[BSP_C_REFINED]) return;
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_check_converged(g, p, e, 1);
+        if (getenv("BSP_EMUL_TRACE")) fprintf(stderr, "iteration %d unconverged %d\n", it, g.counters[BSP_C_UNCONV]);
         bsp_check_ctl(g, it);
     }
 };

@@ -258,3 +258,26 @@ def test_check_pointed_refinement_option_is_bit_identical(atom):
         atom.set_option("recompute", 0)
     for x, y in zip(E0 + C0, E1 + C1):
         assert np.array_equal(x, y)
+
+
+def test_fast_schedule_min_iters_2(atom, oracle):
+    """option min_iters = 2: eigenpairs retire after the second solve when the residual pass says so.
+    Eigenvalues and residuals keep the north-star tolerances; only the S-orthogonality of neighbouring
+    vectors is looser than with the default schedule (no correction step)."""
+    a = host_basis(kind_grid=0, k=7, nfun=400, rb=200.0)
+    items = [(a.problem(), l) for l in (0, 3)]
+    E3, C3, info3 = atom.solve_batch(items)
+    atom.set_option("min_iters", 2)
+    try:
+        E2, C2, info2 = atom.solve_batch(items)
+        iters2 = atom.stats()["iters"]
+    finally:
+        atom.set_option("min_iters", 3)
+    assert not info2.any() and not info3.any()
+    assert iters2 <= 3
+    for (p, l), e2, e3, c2 in zip(items, E2, E3, C2):
+        assert np.max(np.abs(e2 - e3) / np.maximum(np.abs(e3), 1e-2)) < 1e-12
+        b, H, S = oracle_pencil(oracle, a, 400, l)
+        R = H @ c2 - (S @ c2) * e2
+        assert (np.abs(R).max(0) / np.maximum(1, np.abs(e2))).max() < 1e-9
+        assert np.abs(c2.T @ S @ c2 - np.eye(a.nfun)).max() < 1e-6
