@@ -45,7 +45,8 @@ struct Options {
     int max_iters = 12;
     int chunk = 0; /* 0 = auto */
     int workers = 2; /* concurrent chunk streams (1..4) */
-    int stream_chunks = 8; /* chunks per group when results stream to the host */
+    int stream_chunks = 6; /* chunks per group when results stream to the host */
+    int stream_workers = 3; /* chunk streams when results stream to the host */
 #define BSP_MAX_STREAMS 8
 #define BSP_MAIL_INTS (1 << 18)
 #define BSP_MAIL_REPORT_INTS (1 << 14)
@@ -102,6 +103,7 @@ struct bspatom_handle_s {
      * D2H transfer -- which would queue behind the bulk eigenvector copies of this or another handle. */
     int *h_counter = nullptr;     /* pinned + mapped, BSP_MAIL_INTS ints */
     int *h_counter_dev = nullptr; /* device view of h_counter */
+    size_t budget_bytes = 0;      /* workspace budget of this handle (decided on the first run) */
     bool mail_info = false;       /* the mailbox holds pdinfo / bad of the last run (see run_internal) */
     double stats[24] = {0};
     long long launches = 0;
@@ -682,8 +684,9 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "rounds_enqueued") h->opt.rounds_enqueued = std::max(1, (int)v);
     else if (s == "first_check_round" || s == "check_every") { /* accepted for compatibility: the schedule no longer polls */ }
     else if (s == "chunk") h->opt.chunk = (int)v;
-    else if (s == "recompute") { h->opt.recompute = v != 0.0; for (auto &G : h->groups) G.budget_pencils = 0; }
+    else if (s == "recompute") { h->opt.recompute = v != 0.0; h->budget_bytes = 0; }
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
+    else if (s == "stream_workers") h->opt.stream_workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
     else if (s == "workers") h->opt.workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
     else return -2;
     return 0;
@@ -828,6 +831,11 @@ bool is_pinned(const void *p)
  * let both batches finish late and together. */
 struct CopyQueue {
     std::mutex mu;          /* held while one batch enqueues its chunks: keeps its copies contiguous */
+    /* "compute turn": held by a streaming batch from its submission until all but its last small chunks are
+     * final.  Two batches computing at the same time only share the SMs -- both become final later, and the
+     * copy engine, which works through them in order, waits.  Taking turns, batch i+1 computes at full speed
+     * while batch i is being copied, and starts exactly when batch i's tail leaves SMs idle. */
+    std::mutex turn;
     cudaStream_t st = nullptr;
 };
 CopyQueue *copy_queue(int dev)
@@ -924,9 +932,15 @@ int stream_chunk_out(bspatom_handle h, bspatom_handle ctx, Group &G, int p0, int
  * of `workers` streams (each with its own workspace) -- the host reads nothing back while the batch runs,
  * so the GPU never waits for it and the chunk streams back-fill each other's tail waves.  When E_out / C_out
  * are given, each chunk's results are copied out on the device's copy queue as soon as the chunk is final. */
+static double host_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int run_internal(bspatom_handle h, double *E_out, double *C_out)
 {
     int rc = 0;
+    const double t_run0 = host_ms();
     if (!h->uploaded) { h->err = "batch_run before batch_upload"; return BSPATOM_ESTATE; }
     auto aux_launches = [&] { long long s = 0; for (auto x : h->aux) s += x->launches; return s; };
     const long long launches0 = h->launches + aux_launches();
@@ -942,6 +956,8 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     CU(cudaEventCreateWithFlags(&copies_done, cudaEventDisableTiming));
     CopyQueue *cq = (E_out || C_out) ? copy_queue(h->dev) : nullptr;
     if ((E_out || C_out) && !cq) { h->err = "cannot create the result-copy stream"; return BSPATOM_ECUDA; }
+    std::unique_lock<std::mutex> turn;
+    if (cq) turn = std::unique_lock<std::mutex>(cq->turn);
     if (cq) CU(cudaEventRecord(copies_done, cq->st));
     CU(cudaEventRecord(e0, h->st));
     const BspSchedule sch = {std::min(h->opt.rounds_enqueued, h->opt.max_rounds), h->opt.min_iters,
@@ -975,18 +991,22 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
          * run a whole sweep (~1 ms), so stream priorities cannot order the chunks -- the chunk sizes do.
          * Resident batches use `workers` equal chunks.  When results stream to the host the D2H (PCIe,
          * ~53 GB/s, 57 ms per 408 solves of N = 1000) is the longer leg: the batch is cut into
-         * `stream_chunks` equal chunks so that the first copy starts after 2/stream_chunks of the work and
-         * the copy engine then stays busy.  (Measured: growing or shrinking chunk sizes lose -- a chunk of
-         * less than ~40 pencils takes ~17 ms whatever its size, the kernel chain being latency-bound.) */
-        int workers = std::max(1, std::min(h->opt.workers, G.npencil / fill_pencils));
-        if (G.budget_pencils <= 0) {
+         * `stream_chunks` chunks whose sizes SHRINK (weights n+2, n+1, ..., 3): the first copies start as
+         * early as with equal chunks and keep the link busy, and the last chunks -- whose copies nothing can
+         * hide -- are small.  (Measured, single handle, 408 solves: shrinking 79.6 ms, equal 84 ms, growing
+         * 95 ms per batch: a chunk below ~40 pencils takes ~17 ms whatever its size, its kernel chain being
+         * latency-bound, so small chunks must not come first.) */
+        int workers = std::max(1, std::min(streaming ? h->opt.stream_workers : h->opt.workers, G.npencil / fill_pencils));
+        if (h->budget_bytes == 0) {
+            /* once per handle: cudaMemGetInfo takes milliseconds and stalls behind whatever else the device is
+             * doing (another handle's batch), which would delay every submission */
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
             size_t have = h->ws.bytes + h->pool_bytes;
             for (auto x : h->aux) have += x->ws.bytes;
-            const size_t budget = std::min<size_t>((free_b + have) / 2, (size_t)64 << 30);
-            G.budget_pencils = (int)std::max<size_t>(1, std::min<size_t>(budget / per_pencil, 1 << 24));
+            h->budget_bytes = std::max<size_t>(std::min<size_t>((free_b + have) / 2, (size_t)64 << 30), 1);
         }
+        G.budget_pencils = (int)std::max<size_t>(1, std::min<size_t>(h->budget_bytes / per_pencil, 1 << 24));
         const int cap = std::max(1, std::min(G.budget_pencils / workers, 1024));   /* workspace per stream */
         int chunk = h->opt.chunk, nchunks;
         std::vector<int> bounds(1, 0);
@@ -999,9 +1019,23 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             if (streaming) want = std::max(want, std::min(h->opt.stream_chunks, std::max(1, (2 * G.npencil) / fill_pencils)));
             nchunks = std::max(want, (G.npencil + cap - 1) / cap);
             nchunks = std::min(nchunks, G.npencil);
-            const int eq = (G.npencil + nchunks - 1) / nchunks;
-            nchunks = (G.npencil + eq - 1) / eq;
-            for (int i = 1; i <= nchunks; ++i) bounds.push_back(std::min(i * eq, G.npencil));
+            const bool shrink = streaming && nchunks >= 4 && (long long)cap * (nchunks + 5) >= 2LL * G.npencil;
+            if (shrink) {
+                /* weights n+2, n+1, ..., 3: the largest chunk is < 2x the mean and must fit the workspace */
+                double tot = 0.0, accw = 0.0;
+                for (int i = 0; i < nchunks; ++i) tot += (double)(nchunks + 2 - i);
+                for (int i = 0; i < nchunks; ++i) {
+                    accw += (double)(nchunks + 2 - i);
+                    int bnd = (i + 1 == nchunks) ? G.npencil : (int)(G.npencil * accw / tot + 0.5);
+                    bnd = std::max(bnd, bounds.back() + 1);
+                    bnd = std::min(bnd, G.npencil - (nchunks - 1 - i));
+                    bounds.push_back(bnd);
+                }
+            } else {
+                const int eq = (G.npencil + nchunks - 1) / nchunks;
+                nchunks = (G.npencil + eq - 1) / eq;
+                for (int i = 1; i <= nchunks; ++i) bounds.push_back(std::min(i * eq, G.npencil));
+            }
             chunk = 0;
             for (int i = 0; i < nchunks; ++i) chunk = std::max(chunk, bounds[i + 1] - bounds[i]);
         }
@@ -1032,7 +1066,9 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         std::vector<TraceRec> trace;
         std::vector<long long> load(workers, 0);      /* pencils assigned to each stream so far */
         std::unique_lock<std::mutex> copy_lock;
+        const double t_lock0 = host_ms();
         if (streaming) copy_lock = std::unique_lock<std::mutex>(cq->mu);
+        const double t_lock1 = host_ms();
         for (int ci = 0; ci < nchunks; ++ci) {
             int wsel = 0;
             for (int w = 1; w < workers; ++w) if (load[w] < load[wsel]) wsel = w;
@@ -1062,7 +1098,18 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             CU(cudaEventRecord(copies_done, cq->st));   /* behind this batch's last copy */
             copy_lock.unlock();
         }
+        const double t_enq = host_ms();
+        if (streaming && &G == &h->groups.back()) {
+            /* pass the compute turn on once only the last (small) chunks are left */
+            const int k = nchunks >= 4 ? nchunks - 3 : nchunks - 1;
+            cudaEvent_t ev = trace.empty() ? h->chunk_done[h->chunk_done.size() - (size_t)nchunks + (size_t)k] : trace[(size_t)k].done;
+            CU(cudaEventSynchronize(ev));
+            turn.unlock();
+        }
         for (auto x : ctx) CU(cudaStreamSynchronize(x->st));
+        if (h->opt.trace)
+            fprintf(stderr, "[bspatom trace %p] host clock %.1f ms: entered run; +%.1f lock wait %.1f; +%.1f enqueued; +%.1f kernels done\n",
+                    (void *)h, t_run0, t_lock0 - t_run0, t_lock1 - t_lock0, t_enq - t_run0, host_ms() - t_run0);
         if (!trace.empty()) {
             CU(cudaEventSynchronize(copies_done));
             for (auto &tr : trace) {

@@ -412,12 +412,17 @@ BspAtom.dipole_chain = _dipole_chain
 
 class BspAtomPipeline:
     """Throughput mode for sweeps: `depth` handles on one GPU alternate over a list of batches, each from its
-    own host thread (ctypes releases the GIL), so the D2H of one batch's eigenvectors (8 MB per solve at
-    N = 1000, PCIe-bound) overlaps the kernels of the next batch.  Every batch still does its own H2D,
-    kernels and D2H through `bspatom_solve_batch`; results land in the caller's (pinned) buffers."""
+    own host thread (ctypes releases the GIL).  Every batch does its own H2D, kernels and D2H through
+    `bspatom_solve_batch`; results land in the caller's (pinned) buffers.  The library sends the result copies
+    of all handles through one FIFO queue per device, so the D2H of batch i (8 MB of eigenvectors per solve at
+    N = 1000: the PCIe link is the longest leg) overlaps the kernels of batch i+1 and the sweep runs at the
+    pace of the slower of the two legs.  Batches also take turns on the SMs (the library's per-device "compute
+    turn"): started together they would only share the GPU and both finish late."""
 
     def __init__(self, device: int = 0, depth: int = 2):
         self.atoms = [BspAtom(device=device) for _ in range(depth)]
+        self.batch_ms = None      # wall time of an undisturbed batch (fastest seen so far)
+        self.timeline = []        # (batch, handle, start ms, end ms) of the last solve_batches call
 
     def set_option(self, name: str, value: float):
         for a in self.atoms:
@@ -431,24 +436,40 @@ class BspAtomPipeline:
         """batches[i]: list of (Problem, l); outs_E[i], outs_C[i]: pinned float64 buffers for batch i.
         Returns the list of info arrays."""
         import threading
+        import time
 
         infos = [None] * len(batches)
         errors = []
+        took = []
+        timeline = []
+        t_origin = time.perf_counter()
+        depth = len(self.atoms)
+        stagger = 0.0   # the library's per-device compute turn orders the handles; no host-side delay needed
 
         def worker(w):
             try:
-                for i in range(w, len(batches), len(self.atoms)):
+                if w and stagger > 0.0 and len(batches) > w:
+                    time.sleep(w * stagger)
+                for i in range(w, len(batches), depth):
+                    t0 = time.perf_counter()
                     _, _, infos[i] = self.atoms[w].solve_batch(batches[i], nvec=nvec, out_E=outs_E[i], out_C=outs_C[i])
+                    t1 = time.perf_counter()
+                    took.append(1e3 * (t1 - t0))
+                    timeline.append((i, w, 1e3 * (t0 - t_origin), 1e3 * (t1 - t_origin)))
             except Exception as exc:       # surfaced to the caller below
                 errors.append(exc)
 
-        threads = [threading.Thread(target=worker, args=(w,)) for w in range(len(self.atoms))]
+        threads = [threading.Thread(target=worker, args=(w,)) for w in range(depth)]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
         if errors:
             raise errors[0]
+        self.timeline = sorted(timeline)
+        if took:
+            m = min(took)         # the least disturbed batch ~ one batch alone
+            self.batch_ms = m if self.batch_ms is None else min(self.batch_ms, m)
         return infos
 
 

@@ -86,8 +86,9 @@ void bspatom_free_host(void *p);
 
 /* tunables: "tau", "delta_rel", "conv_tol", "res_tol", "rounds_enqueued", "max_rounds", "min_iters"
  * (3; 2 = fast schedule: eigenpairs may retire after the second solve, S-orthogonality of neighbouring
- * vectors ~1e-8 instead of ~1e-12), "max_iters", "chunk", "stream_chunks", "workers" (chunk streams,
- * 1..4), "recompute" */
+ * vectors ~1e-8 instead of ~1e-12), "max_iters", "chunk", "workers" (chunk streams of a resident batch,
+ * 1..8), "stream_chunks" / "stream_workers" (chunks and chunk streams when results go to pinned host
+ * buffers), "recompute", "trace" (1: chunk / copy timeline on stderr) */
 int bspatom_set_option(bspatom_handle h, const char *name, double value);
 
 /* ---- assembly: replaces MATRIX_SVT (matrices.f90:1-200) ------------------ *
