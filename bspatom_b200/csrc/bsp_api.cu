@@ -46,7 +46,7 @@ struct Options {
     int chunk = 0; /* 0 = auto */
     int workers = 2; /* concurrent chunk streams (1..4) */
     int stream_chunks = 6; /* chunks per group when results stream to the host */
-    int stream_workers = 3; /* chunk streams when results stream to the host */
+    int stream_workers = 2; /* chunk streams when results stream to the host */
 #define BSP_MAX_STREAMS 8
 #define BSP_MAIL_INTS (1 << 18)
 #define BSP_MAIL_REPORT_INTS (1 << 14)
@@ -430,7 +430,7 @@ struct Carver {
 struct ChunkPtrs {
     double *fbH, *pbound, *lo, *hi, *samp_s, *gap, *sigma, *rho, *rho_prev, *scale, *res, *L, *X, *R, *cand_s, *fac;
     double *samp_fm, *flm, *fhm, *beta;
-    int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c, *samp_fe, *fle, *fhe, *side;
+    int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c, *samp_fe, *fle, *fhe, *side, *olist, *ocount;
 };
 
 size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c, bool recompute = false)
@@ -450,6 +450,7 @@ size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c, bool recomp
     c.scale = cv.take<double>(per); c.res = cv.take<double>(per); c.status = cv.take<int>(per);
     c.fac = cv.take<double>(per);
     c.counters = cv.take<int>(64);
+    c.olist = cv.take<int>(2 * per); c.ocount = cv.take<int>(4 * (size_t)np);
     c.cand_s = cv.take<double>((size_t)np * BSP_NCAND); c.cand_c = cv.take<int>((size_t)np * BSP_NCAND);
     c.L = recompute ? cv.take<double>((size_t)np * (G.npad / BSP_SEG_STEPS(G.B)) * BSP_CK_DOUBLES(G.B) * G.ldw)
                     : cv.take<double>((size_t)np * G.npad * (G.B + 1) * G.ldw);
@@ -481,6 +482,7 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     g.samp_fm = c.samp_fm; g.samp_fe = c.samp_fe; g.flm = c.flm; g.fhm = c.fhm; g.fle = c.fle; g.fhe = c.fhe; g.side = c.side; g.beta = c.beta;
     g.sigma = c.sigma; g.rho = c.rho; g.rho_prev = c.rho_prev; g.scale = c.scale; g.res = c.res;
     g.status = c.status; g.L = c.L; g.X = c.X; g.R = c.R; g.counters = c.counters;
+    g.olist = c.olist; g.ocount = c.ocount;
     g.tau = h->opt.tau; g.delta_rel = h->opt.delta_rel; g.conv_tol = h->opt.conv_tol;
 
     GpuExec<B> ex;
@@ -489,6 +491,7 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     ex.open_ok = (int)((long long)np * G.n / 20000);
     bsp_zero_words_kernel<<<1, 32, 0, h->st>>>(c.counters, BSP_C_WORDS);
     h->launches++;
+    CU(cudaMemsetAsync(c.ocount, 0, sizeof(int) * 4 * (size_t)np, h->st));
     bsp_enqueue_chunk(ex, sch);
     if (ex.first_err != cudaSuccess) {
         h->err = std::string("eigen stage: ") + cudaGetErrorString(ex.first_err);

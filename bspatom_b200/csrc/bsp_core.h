@@ -129,6 +129,10 @@ struct BspEigChunk {
     double *X; /* [npencil][xrows][ldw]                           */
     double *R; /* [npencil][xrows][ldw]                           */
     int *counters; /* control block, BSP_C_* */
+    /* compaction of the bracketing rounds (device only, may be null): olist[buf][p][.] = eigen indices of
+     * pencil p that still have work in the round reading buffer buf -- open brackets from the front,
+     * just-finished ones from the back; ocount[buf][p][2] = how many of each */
+    int *olist, *ocount;
     /* tunables */
     double tau;       /* bracket width / gap at hand-over         */
     double delta_rel; /* shift offset / gap in correction steps   */
@@ -372,6 +376,7 @@ BSP_HD void bsp_bounds_pick(const BspEigChunk &g, int p, const double *cand_s, c
 struct BspRoundState {
     double lo, hi, flm, fhm, beta, gp, wdt, frac, s, sfm;
     int clo, chi, fle, fhe, side, done, c, sfe;
+    int was_done;   /* done before this round started (the round then only re-publishes its state) */
     int want_defl;  /* the regula-falsi step is possible: the deflation sum at the bracket midpoint is needed */
     int want_count; /* s is a new sample: its inertia is needed                                              */
 };
@@ -430,7 +435,7 @@ BSP_HD void bsp_round_begin(const BspEigChunk &g, int p, int e, int round, BspRo
         else if (e < g.nvec[p] && gp > 0.0 && wdt <= g.tau * gp) done = 1;
     }
     st.lo = lo; st.hi = hi; st.flm = flm; st.fhm = fhm; st.beta = beta; st.gp = gp; st.wdt = wdt;
-    st.clo = clo; st.chi = chi; st.fle = fle; st.fhe = fhe; st.side = side; st.done = done;
+    st.clo = clo; st.chi = chi; st.fle = fle; st.fhe = fhe; st.side = side; st.done = done; st.was_done = was_done;
     st.s = lo; st.sfm = flm; st.c = clo; st.sfe = fle;
     st.want_defl = 0; st.want_count = 0; st.frac = 0.5;
     if (!done) {

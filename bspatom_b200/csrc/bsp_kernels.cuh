@@ -245,6 +245,11 @@ __device__ __forceinline__ double bsp_deflation_sum_block(const BspEigChunk &g, 
     return (double)b0 + (double)b1 + (double)b2 + (double)b3;
 }
 
+/* One bracketing round.  Threads are mapped to the eigen indices that still have work through the compaction
+ * list of the pencil (g.olist / g.ocount, built by the previous round): a bracket that is done re-publishes its
+ * state once more (so that both bracket buffers hold it) and then drops out, blocks beyond the list return at
+ * once, and the cost of the late rounds follows the number of open brackets instead of n.  The order of the list
+ * (atomic appends) varies from run to run; the result of an eigen index does not depend on its slot. */
 template <int B>
 __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) bsp_round_kernel(BspEigChunk g, int round, int max_rounds, int open_ok)
 {
@@ -253,27 +258,49 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) 
     __shared__ __align__(128) double sm[SMD];
     __shared__ __align__(8) uint64_t bars[2];
     if (g.counters[BSP_C_BRACKETED]) return;       /* written by the previous kernel: grid-uniform */
-    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = e < g.n;
-    bsp_stage_bars_init(bars);
-    BspRoundState st;
-    st.want_defl = 0; st.want_count = 0; st.done = 1; st.lo = st.hi = 0.0;
-    if (valid) bsp_round_begin(g, p, e, round, st);
-    /* the barriers below also publish the mbarrier initialisation */
-    double bsum = 0.0;
-    if (__syncthreads_or(st.want_defl)) bsum = bsp_deflation_sum_block(g, p, e, round, st, st.want_defl != 0, sm);
-    if (valid) bsp_round_pick(st, bsum);
-    if (__syncthreads_or(st.want_count)) {
-        constexpr int FS = 2 * B + 2;
-        BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
-        double fm;
-        int fe;
-        const double pivmin = st.want_count ? bsp_round_pivmin(g, p, st.s) : 1.0;
-        const int c = bsp_sturm_sweep<B>(src, g.npad, st.want_count != 0, st.s, pivmin, nullptr, &fm, &fe);
-        if (st.want_count) { st.c = c; st.sfm = fm; st.sfe = fe; }
+    const int p = blockIdx.y, slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool compact = g.olist != nullptr;
+    const int rdb = round & 1, wrb = (round + 1) & 1;
+    /* two lists per pencil in one array: open brackets from the front (they sweep: kept dense), brackets that
+     * became done in the previous round from the back (they only re-publish) */
+    const bool listed = compact && round > 0;
+    const int cnt_open = listed ? g.ocount[(rdb * g.npencil + p) * 2] : g.n;
+    const int cnt = listed ? cnt_open + g.ocount[(rdb * g.npencil + p) * 2 + 1] : g.n;
+    if ((int)(blockIdx.x * blockDim.x) < cnt) {     /* block-uniform */
+        const bool valid = slot < cnt;
+        const int *list = g.olist + ((size_t)rdb * g.npencil + p) * g.ldw;
+        const int e = !valid ? g.n : (!listed ? slot : (slot < cnt_open ? list[slot] : list[g.ldw - 1 - (slot - cnt_open)]));
+        bsp_stage_bars_init(bars);
+        BspRoundState st;
+        st.want_defl = 0; st.want_count = 0; st.done = 1; st.was_done = 1; st.lo = st.hi = 0.0;
+        if (valid) bsp_round_begin(g, p, e, round, st);
+        /* the barriers below also publish the mbarrier initialisation */
+        double bsum = 0.0;
+        if (__syncthreads_or(st.want_defl)) bsum = bsp_deflation_sum_block(g, p, e, round, st, st.want_defl != 0, sm);
+        if (valid) bsp_round_pick(st, bsum);
+        if (__syncthreads_or(st.want_count)) {
+            constexpr int FS = 2 * B + 2;
+            BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+            double fm;
+            int fe;
+            const double pivmin = st.want_count ? bsp_round_pivmin(g, p, st.s) : 1.0;
+            const int c = bsp_sturm_sweep<B>(src, g.npad, st.want_count != 0, st.s, pivmin, nullptr, &fm, &fe);
+            if (st.want_count) { st.c = c; st.sfm = fm; st.sfe = fe; }
+        }
+        if (valid) {
+            bsp_round_end(g, p, e, round, st);
+            if (compact && !st.was_done) {
+                int *wl = g.olist + ((size_t)wrb * g.npencil + p) * g.ldw;
+                if (!st.done) wl[atomicAdd(g.ocount + (wrb * g.npencil + p) * 2, 1)] = e;
+                else wl[g.ldw - 1 - atomicAdd(g.ocount + (wrb * g.npencil + p) * 2 + 1, 1)] = e;
+            }
+        }
     }
-    if (valid) bsp_round_end(g, p, e, round, st);
-    if (bsp_last_block(g.counters + BSP_C_ARRIVE)) bsp_round_ctl(g, round, max_rounds, open_ok);
+    if (bsp_last_block(g.counters + BSP_C_ARRIVE)) {
+        bsp_round_ctl(g, round, max_rounds, open_ok);
+        /* the counts this round consumed are the ones the next round appends to */
+        if (compact) for (int q = 0; q < 2 * g.npencil; ++q) g.ocount[rdb * 2 * g.npencil + q] = 0;
+    }
 }
 
 __global__ void bsp_prepare_kernel(BspEigChunk g)
