@@ -267,10 +267,11 @@ def main():
     if not args.no_e2e:
         h2d = sum(8 * (p.nkp + 8) + 64 for p, _ in items)     # knots + parameters per problem struct
         d2h = 8 * (n_e + n_c) + 4 * nsolve
-        bufs = []
-        for _ in range(2):
-            bufs.append((torch.empty(n_e, dtype=torch.float64).pin_memory().numpy(),
-                         torch.empty(n_c, dtype=torch.float64).pin_memory().numpy()))
+        def pinned_pair():
+            return (torch.empty(n_e, dtype=torch.float64).pin_memory().numpy(),
+                    torch.empty(n_c, dtype=torch.float64).pin_memory().numpy())
+
+        bufs = [pinned_pair()]
 
         def gather_E(Eh):
             if world > 1:   # the single gather of the path: eigenvalues to rank 0 over NCCL / NVLink
@@ -298,15 +299,22 @@ def main():
         serial_stats = {k_: atom.stats()[k_] for k_ in ("wall_ms_upload", "wall_ms_run", "wall_ms_download", "wall_ms_copy_tail", "ms_total")}
         bad = int(np.count_nonzero(inf))
         # (b) two alternating handles
-        pipe_s = None
+        pipe_s, pipe, pipe_err = None, None, None
+        nb = args.steps
         try:
+            bufs.append(pinned_pair())      # second result buffer: batch i+1 lands while batch i is in use
             pipe = bsp.BspAtomPipeline(device=local, depth=2)
             if args.workers:
                 pipe.set_option("workers", args.workers)
-            nb = args.steps
             oE = [bufs[i % 2][0] for i in range(max(nb, 2))]
             oC = [bufs[i % 2][1] for i in range(max(nb, 2))]
             pipe.solve_batches([items] * 2, oE[:2], oC[:2])
+        except Exception as exc:      # keep the serial figure if a second handle / buffer does not fit
+            pipe_err = repr(exc)
+        ok = torch.tensor([0 if pipe_err else 1], dtype=torch.int32, device="cuda")
+        if world > 1:                 # every rank takes the same branch (the timed part has barriers)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]):
             barrier()
             t0 = time.perf_counter()
             infos = pipe.solve_batches([items] * nb, oE[:nb], oC[:nb])
@@ -318,10 +326,8 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             pipe_s = float(tt[0])
             bad += sum(int(np.count_nonzero(i_)) for i_ in infos)
+        if pipe is not None:
             pipe.close()
-        except Exception as exc:      # keep the serial figure if a second handle does not fit
-            pipe_s = None
-            pipe_err = repr(exc)
         best_s = min(serial_s, pipe_s) if pipe_s else serial_s
         e2e = {"value": total_solves / best_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * best_s / args.steps,
@@ -331,6 +337,8 @@ def main():
                "serial": {"value": total_solves / serial_s, "ms_per_step": 1e3 * serial_s / args.steps,
                           "ms_each_step": serial_steps, "wall_ms_last_step": serial_stats},
                "bad_info": bad}
+        if pipe_err:
+            e2e["pipelined_unavailable"] = pipe_err
         del bufs
 
     # ---------------- CPU baseline + accuracy, rank 0 only ----------------
@@ -413,7 +421,8 @@ def main():
                         "achieved_GBs": nsolve * NFUN * per_pair[names[3 - dom]] * full_launches
                         / (k1ms[3 - dom] / args.steps * 1e-3) / 1e9, "share_of_step": float(share[3 - dom])},
                     "bsp_round_kernel": {"share_of_step": float(share[0]), "bound": "fp64 pipe (serial pivot recurrence), "
-                                         "sm__pipe_fp64_cycles_active 40 % in profiles/"}},
+                                         "sm__pipe_fp64_cycles_active %s %% in profiles/"
+                                         % ncu.get("bsp_round_kernel", {}).get("fp64_pipe_active_pct", "n/a")}},
                 "single_stream_ms_per_step": one_ms / args.steps}
     b_alg = 8 * ((NFUN + K) + 4 * K * NFUN + NFUN + NFUN * NFUN)       # 8.24 MB per solve
     step_roof = {"bytes_per_solve": b_alg, "achieved_gbs": value / world * b_alg / 1e9,
