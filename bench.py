@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--workers", type=int, default=0, help="chunk streams (0 = library default)")
     ap.add_argument("--recompute", type=int, default=-1, help="1/0: check-pointed vs stored-factor refinement (-1 = library default)")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (experiments), repeatable")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind host memory / CPU affinity to the GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -206,6 +207,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    numa = None
+    if world > 1 and not args.no_numa:
+        # before any pinned allocation: host buffers on the GPU's own NUMA node (N = 1 keeps every core for the
+        # CPU-baseline leg)
+        from bspatom_b200.parallel import bind_host_memory_to_gpu
+        prop = torch.cuda.get_device_properties(local)
+        numa = bind_host_memory_to_gpu("%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id))
     atom = bsp.BspAtom(device=local)
     if args.workers:
         atom.set_option("workers", args.workers)
@@ -441,6 +449,7 @@ def main():
                              "larger than the 126 MB L2", "parallelism": "shard (Z, l) list over %d rank(s), no "
                              "collective on the compute path" % world},
             "clocks": sampler.summary(),
+            "host_numa": numa,
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": roofline,
