@@ -19,7 +19,8 @@ EXPORTS = [
     "bspatom_create", "bspatom_destroy", "bspatom_last_error", "bspatom_version", "bspatom_set_option",
     "bspatom_alloc_host", "bspatom_free_host",
     "bspatom_assemble_band", "bspatom_solve_batch", "bspatom_batch_upload", "bspatom_batch_run",
-    "bspatom_batch_download", "bspatom_dsygv_", "bspatom_dipole", "bspatom_dipole_chain", "bspatom_wavefunction", "bspatom_get_stats",
+    "bspatom_batch_download", "bspatom_dsygv_", "bspatom_dipole", "bspatom_dipole_chain", "bspatom_trans_amp_hermitian",
+    "bspatom_wavefunction", "bspatom_get_stats",
 ]
 
 
@@ -73,6 +74,8 @@ def load():
     L.bspatom_dipole.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                  C.c_void_p]
     L.bspatom_dipole_chain.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.bspatom_trans_amp_hermitian.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p]
     L.bspatom_wavefunction.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bspatom_get_stats.argtypes = [H, _dp, C.c_int]

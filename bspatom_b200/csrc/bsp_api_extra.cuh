@@ -190,6 +190,76 @@ int bspatom_dipole_chain(bspatom_handle h, int n, int kd, const double *A_band, 
     return 0;
 }
 
+/* General (structured-light) branch of TRANS_AMP, PhotoIon.f90:218-232: for one angular block (il, jl, component)
+ * the reference loops over every (bra, ket) pair and calls ZHVMV = ZHEMV('U') + ZDOTU (Modules.f90:398-425) on the
+ * N x N complex block zAij(:,:,il,jl,i) with the REAL eigenvectors as zx, zy.  ZHEMV('U') reads the upper triangle
+ * only, takes the lower one as its conjugate and ignores the imaginary part of the diagonal, so
+ *   T = Cf^T Re(A_h) Ci + i Cf^T Im(A_h) Ci,  Re(A_h) symmetric, Im(A_h) antisymmetric (zero diagonal),
+ * two real banded-operator contractions that share Cf and Ci: two band x dense launches and one batched DMMA GEMM
+ * give all (bra, ket) pairs of the block at once. */
+int bspatom_trans_amp_hermitian(bspatom_handle h, int n, int kd, const double *zA_upper, int nf, const double *Cf,
+                                int ni, const double *Ci, double *T)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (n < 1) return -2;
+    if (kd < 0 || kd >= n) return -3;
+    if (!zA_upper) return -4;
+    if (nf < 1) return -5;
+    if (!Cf) return -6;
+    if (ni < 1) return -7;
+    if (!Ci) return -8;
+    if (!T) return -9;
+    const int ld = 2 * kd + 1, ldu = kd + 1;
+    const size_t abytes = (size_t)ld * n;
+    std::vector<double> ab(2 * abytes, 0.0);   /* [0]: Re(A_h), [1]: Im(A_h), general band AB(kd+i-j, j) = A(i,j) */
+    double *ar = ab.data(), *ai = ab.data() + abytes;
+    for (int j = 0; j < n; ++j)
+        for (int i = std::max(0, j - kd); i <= j; ++i) {
+            const double re = zA_upper[2 * ((size_t)j * ldu + (kd + i - j))], im = zA_upper[2 * ((size_t)j * ldu + (kd + i - j)) + 1];
+            ar[(size_t)j * ld + (kd + i - j)] = re;                 /* A(i,j) */
+            ar[(size_t)i * ld + (kd + j - i)] = re;                 /* A(j,i) */
+            if (i != j) {
+                ai[(size_t)j * ld + (kd + i - j)] = im;
+                ai[(size_t)i * ld + (kd + j - i)] = -im;
+            }
+        }
+    const size_t yblk = (size_t)n * ni, dblk = (size_t)nf * ni;
+    double *d_A = nullptr, *d_Cf = nullptr, *d_Ci = nullptr, *d_Y = nullptr, *d_D = nullptr;
+    if ((rc = dev_alloc(h, &d_A, 2 * abytes))) return rc;
+    if ((rc = dev_alloc(h, &d_Ci, yblk))) return rc;
+    if ((rc = dev_alloc(h, &d_Y, 2 * yblk))) return rc;
+    if ((rc = dev_alloc(h, &d_D, 2 * dblk))) return rc;
+    const bool same = (Cf == Ci && nf == ni);
+    if (same) d_Cf = d_Ci;
+    else if ((rc = dev_alloc(h, &d_Cf, (size_t)n * nf))) return rc;
+    CU(cudaMemcpyAsync(d_A, ab.data(), sizeof(double) * 2 * abytes, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(d_Ci, Ci, sizeof(double) * yblk, cudaMemcpyHostToDevice, h->st));
+    if (!same) CU(cudaMemcpyAsync(d_Cf, Cf, sizeof(double) * (size_t)n * nf, cudaMemcpyHostToDevice, h->st));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, h->st));
+    for (int part = 0; part < 2; ++part) {
+        bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, ni), 128, 0, h->st>>>(n, kd, d_A + part * abytes, ni, d_Ci, d_Y + part * yblk);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(bsp_launch_dgemm_tn(h->st, nf, ni, n, d_Cf, n, d_Y, n, d_D, nf, 2, 0, (long long)yblk, (long long)dblk));
+    h->launches++;
+    CU(cudaEventRecord(e1, h->st));
+    std::vector<double> d(2 * dblk);
+    CU(cudaMemcpyAsync(d.data(), d_D, sizeof(double) * 2 * dblk, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    for (size_t q = 0; q < dblk; ++q) { T[2 * q] = d[q]; T[2 * q + 1] = d[dblk + q]; }
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    h->stats[0] = 3; h->stats[7] = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dev_free(h, d_A, 2 * abytes); dev_free(h, d_Ci, yblk); dev_free(h, d_Y, 2 * yblk); dev_free(h, d_D, 2 * dblk);
+    if (!same) dev_free(h, d_Cf, (size_t)n * nf);
+    return 0;
+}
+
 /*
  * DSYGV-shaped entry.  Accepts the dense pencil exactly as matrices.f90:244-248
  * hands it to LAPACK, finds the half bandwidth from the zero pattern and runs

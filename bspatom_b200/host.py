@@ -390,6 +390,26 @@ class BspAtom(BspInputs):
         return D
 
 
+def _trans_amp_hermitian(self, zA_upper: np.ndarray, Cf: np.ndarray, Ci: np.ndarray) -> np.ndarray:
+    """General (structured-light) branch of TRANS_AMP, PhotoIon.f90:218-232, for one angular block and all (bra, ket)
+    pairs at once: T = Cf^T ZHEMV_U(zA) Ci (complex nf x ni), ZHEMV('U') semantics of ZHVMV (Modules.f90:398-425).
+    zA_upper: complex upper band (kd+1, n), AB[kd+i-j, j] = zA[i, j]."""
+    zA_upper = np.asfortranarray(zA_upper, dtype=np.complex128)
+    Cf = np.asfortranarray(Cf, dtype=np.float64)
+    Ci = np.asfortranarray(Ci, dtype=np.float64)
+    n = Cf.shape[0]
+    kd = zA_upper.shape[0] - 1
+    T = np.empty((Cf.shape[1], Ci.shape[1]), dtype=np.complex128, order="F")
+    rc = self.lib.bspatom_trans_amp_hermitian(self._h, n, kd, zA_upper.ctypes.data_as(C.c_void_p), Cf.shape[1],
+                                              Cf.ctypes.data_as(C.c_void_p), Ci.shape[1],
+                                              Ci.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p))
+    _lib.check(self.lib, self._h, rc, "bspatom_trans_amp_hermitian")
+    return T
+
+
+BspAtom.trans_amp_hermitian = _trans_amp_hermitian
+
+
 def _dipole_chain(self, A_band: np.ndarray, C_blocks) -> np.ndarray:
     """D[l] = C[l+1]^T A C[l] for all neighbouring l in two launches (cfg5).  C_blocks: sequence of
     (n, nvec) arrays (e.g. BspAtom.cinl); returns (nl-1, nvec, nvec) with D[l] Fortran-ordered blocks."""

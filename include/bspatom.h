@@ -141,6 +141,15 @@ int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf
 int bspatom_dipole_chain(bspatom_handle h, int n, int kd, const double *A_band, int nl, int nvec,
                          const double *C_all, double *D_all);
 
+/* ---- general branch of TRANS_AMP (structured light), PhotoIon.f90:218-232 ------ *
+ * One angular block zAij(:,:,il,jl,i) against all (bra, ket) pairs at once:
+ *   T(nf,ni) = Cf^T * ZHEMV_U(zA) * Ci   (what ZHVMV = ZHEMV('U') + ZDOTU, Modules.f90:398-425, gives pair by pair:
+ *   upper triangle read, lower = its conjugate, imaginary part of the diagonal ignored; Cf, Ci real).
+ * zA_upper: COMPLEX*16 upper band AB(kd+1, n), AB(kd+1+i-j, j) = zA(i,j) (re,im interleaved);
+ * T: COMPLEX*16 nf x ni column-major.  The scalar ciall(i) and the B_0 term (ciall(5)*mi*Sij) are the caller's. */
+int bspatom_trans_amp_hermitian(bspatom_handle h, int n, int kd, const double *zA_upper, int nf, const double *Cf,
+                                int ni, const double *Ci, double *T);
+
 /* ---- wavefunction synthesis: WRITE_WF (Bsp_Atom.f90:101-152) --------------- *
  * psi(ip, iv) = sum_j C(j,iv) B_j(r_ip), r_ip = ra + ip (rb-ra)/npts, ip=0..npts */
 int bspatom_wavefunction(bspatom_handle h, int k, int nfun, int nkp, const double *rt, double ra,

@@ -106,3 +106,32 @@ def solve_system_bookkeeping(Enl, kind_pi, l_ini, l_fin, emax_fin):
         n1_max = min(n1_max, nfun)
     return dict(n0_fin=n0_fin, n1_fin=n1_fin, Emax_fin=emax_fin, n1_max=n1_max, nbds=nbds, n01=n01, rEki=rEki,
                 ntemp=ntemps, E_ini=E_ini, E_fin=E_fin)
+
+
+def zhvmv(zA, zx, zy):
+    """ZHVMV of the reference (Modules.f90:398-425): zv = ZHEMV('U', zA) zx, zf = ZDOTU(zy, zv), written out as
+    the BLAS reference loops do it: only the upper triangle of zA is read, the lower one is its conjugate and the
+    imaginary part of the diagonal is ignored.  Plain loops: test infrastructure for small cases."""
+    import numpy as np
+
+    n = zA.shape[0]
+    v = np.zeros(n, dtype=np.complex128)
+    for j in range(n):
+        t1 = zx[j]
+        t2 = 0.0 + 0.0j
+        for i in range(j):
+            v[i] += t1 * zA[i, j]
+            t2 += np.conj(zA[i, j]) * zx[i]
+        v[j] += t1 * zA[j, j].real + t2
+    return np.sum(np.asarray(zy) * v)      # ZDOTU: no conjugation
+
+
+def trans_amp_block(zA, Cf, Ci):
+    """All (bra, ket) pairs of one angular block of TRANS_AMP's general branch (PhotoIon.f90:218-232):
+    T[f, i] = ZHVMV(zA, Ci[:, i], Cf[:, f]) -- vectorised form of `zhvmv` (Hermitian completion of the upper
+    triangle), used where the loops would be too slow."""
+    import numpy as np
+
+    U = np.triu(zA, 1)
+    Ah = U + np.conj(U).T + np.diag(np.real(np.diag(zA)))
+    return np.asarray(Cf).T @ (Ah @ np.asarray(Ci))

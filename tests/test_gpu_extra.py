@@ -119,3 +119,33 @@ def test_pipeline_two_handles_bit_identical_to_single(atom):
         assert np.array_equal(np.concatenate([np.asarray(e) for e in Es]), oE[b])
         for j in range(3):      # column-major n x n blocks, one per solve
             assert np.array_equal(np.asarray(Cs[j]), oC[b][j * n * n:(j + 1) * n * n].reshape((n, n), order="F"))
+
+
+def test_trans_amp_hermitian_block_matches_zhvmv(atom, oracle):
+    """general branch of TRANS_AMP (PhotoIon.f90:218-232): one complex banded angular block against all
+    (bra, ket) pairs, ZHEMV('U') semantics (lower triangle and imaginary diagonal of the input are ignored)."""
+    from oracle import postproc_oracle as po
+
+    a = host_basis(kind_grid=0, k=7, nfun=150, rb=75.0)
+    p = a.problem()
+    n, kd = a.nfun, a.k - 1
+    Es, Cs, info = atom.solve_batch([(p, 1), (p, 2)])
+    assert not info.any()
+    rng = np.random.default_rng(11)
+    zA = np.zeros((n, n), dtype=np.complex128)
+    for i in range(n):
+        for j in range(max(0, i - kd), min(n, i + kd + 1)):
+            zA[i, j] = rng.standard_normal() + 1j * rng.standard_normal()     # not Hermitian, complex diagonal
+    zab = np.zeros((kd + 1, n), dtype=np.complex128, order="F")
+    for j in range(n):
+        for i in range(max(0, j - kd), j + 1):
+            zab[kd + i - j, j] = zA[i, j]
+    Cf, Ci = np.asarray(Cs[1])[:, :37], np.asarray(Cs[0])[:, :50]
+    T = atom.trans_amp_hermitian(zab, Cf, Ci)
+    ref = po.trans_amp_block(zA, Cf, Ci)
+    scale = np.linalg.norm(Cf, axis=0)[:, None] * np.linalg.norm(Ci, axis=0)[None, :] * np.abs(zA).max() * (2 * kd + 1)
+    assert np.max(np.abs(T - ref) / scale) < 1e-13
+    # a few pairs through the literal BLAS-loop restatement
+    for f, i in ((0, 0), (5, 17), (36, 49)):
+        z = po.zhvmv(zA, Ci[:, i].astype(np.complex128), Cf[:, f].astype(np.complex128))
+        assert abs(T[f, i] - z) < 1e-12 * scale[f, i]

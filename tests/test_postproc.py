@@ -85,3 +85,27 @@ def test_writers_round_trip(tmp_path, oracle):
     assert int(lines[1]) == 0 and len(lines[2]) == 5 + 20 * 30            # I5,5000G20.10
     row = np.array([float(lines[2][5 + 20 * i: 25 + 20 * i]) for i in range(30)])
     assert np.allclose(row, cinl[:, 0, 0], rtol=1e-9, atol=1e-99)
+
+
+def test_zhvmv_restatement_matches_blas_zhemv():
+    """oracle.zhvmv / trans_amp_block (general branch of TRANS_AMP, PhotoIon.f90:218-232) against the BLAS the
+    reference calls: ZHEMV('U') + ZDOTU on a NON-Hermitian complex matrix with a complex diagonal."""
+    import numpy as np
+    from scipy.linalg import blas
+
+    from oracle import postproc_oracle as po
+
+    rng = np.random.default_rng(5)
+    n = 23
+    zA = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Cf = rng.standard_normal((n, 4))
+    Ci = rng.standard_normal((n, 3))
+    T = po.trans_amp_block(zA, Cf, Ci)
+    for f in range(4):
+        for i in range(3):
+            zx = Ci[:, i].astype(np.complex128)
+            zy = Cf[:, f].astype(np.complex128)
+            v = blas.zhemv(1.0, np.asfortranarray(zA), zx, lower=0)
+            ref = blas.zdotu(zy, v)
+            assert abs(po.zhvmv(zA, zx, zy) - ref) < 1e-12 * (1 + abs(ref))
+            assert abs(T[f, i] - ref) < 1e-12 * (1 + abs(ref))
