@@ -255,6 +255,7 @@ struct BspFalse { static constexpr bool value = false; };
 template <int B>
 struct BspRowsGlobal {
     static constexpr bool GL = true;
+    static constexpr int RHS_RING = 0;   /* no shared-memory ring for the right-hand side */
     const double *H, *S;
     BSP_HD void begin_forward(int) {}
     BSP_HD void acquire_forward(int t, const double *&tH, const double *&tS)
@@ -668,6 +669,23 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int iter
     /* software pipeline: right-hand side (HBM) a whole unrolled block (B+1 rows) ahead; the band row that
      * enters the window at the end of a step is read from the tile at the top of the step */
     double rq[K1];
+    /* staged sources keep the right-hand side of the following groups in flight through a per-thread ring in
+     * shared memory (asynchronous copies, no registers): the reads sit behind the kernel's own write stream in
+     * the memory controller and take several microseconds, more than one group of look-ahead hides.  Only the
+     * passes that read R use it (iteration 0 computes its start vector). */
+    const bool ring = (Src::RHS_RING > 0) && iter > 0;
+    auto ring_issue = [&](int gi) {
+        if constexpr (Src::RHS_RING > 0) {
+            const int slot = (gi % (Src::RHS_RING + 1)) * K1;
+#pragma unroll
+            for (int t = 0; t < K1; ++t) {
+                const int row = gi * K1 + t;
+                if (row < n) src.rhs_issue(slot + t, Rp + (size_t)row * ldw);
+                else src.rhs_zero(slot + t);
+            }
+            src.rhs_commit();
+        }
+    };
     src.begin_forward(ntiles);
     for (int tl = 0; tl < ntiles; ++tl) {
         const double *tH, *tS;
@@ -676,9 +694,18 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int iter
             if (tl == 0) {
                 bsp_sturm_init<B, Src::GL>(w, tH, tS, sigma);
 #pragma unroll
-                for (int r = 0; r < K1; ++r) {
-                    y[r] = scr * rhs(r);
-                    rq[r] = rhs(K1 + r);
+                for (int r = 0; r < K1; ++r) y[r] = scr * rhs(r);
+                if constexpr (Src::RHS_RING > 0) {
+                    /* groups 1 .. RHS_RING of the right-hand side go in flight through the shared-memory ring */
+                    if (ring) {
+                        for (int gi = 1; gi <= Src::RHS_RING; ++gi) ring_issue(gi);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < K1; ++r) rq[r] = rhs(K1 + r);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < K1; ++r) rq[r] = rhs(K1 + r);
                 }
             }
 #if defined(__CUDA_ARCH__)
@@ -687,6 +714,17 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int iter
             for (int gq = 0; gq < TR; gq += K1) {
                 const int j0 = tl * TR + gq;
                 const double *hnext = tH + (size_t)(gq + K1) * FS, *snext = tS + (size_t)(gq + K1) * FS;
+                if constexpr (Src::RHS_RING > 0) {
+                    if (ring) {
+                        /* this group consumes the rows of group gi+1; group gi+1+RHS_RING takes the slot that
+                         * the previous group emptied */
+                        const int gi = j0 / K1;
+                        ring_issue(gi + 1 + Src::RHS_RING);
+                        src.template rhs_wait<Src::RHS_RING>();
+#pragma unroll
+                        for (int t = 0; t < K1; ++t) rq[t] = src.rhs_read(((gi + 1) % (Src::RHS_RING + 1)) * K1 + t);
+                    }
+                }
 #pragma unroll
                 for (int t = 0; t < K1; ++t) {
                     const int j = j0 + t;
@@ -697,7 +735,7 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int iter
                         ns[m] = bsp_ld<Src::GL>(snext + (size_t)t * FS + m);
                     }
                     const double rnew = scr * rq[t];    /* rhs of row j+K1, loaded K1 steps ago */
-                    rq[t] = rhs(j + 2 * K1);
+                    if (!ring) rq[t] = rhs(j + 2 * K1);
                     double d = w[t][t];
                     if (fabs(d) < pivmin) d = -pivmin;
                     if (d < 0.0) ++cnt;

@@ -120,13 +120,25 @@ __device__ __forceinline__ void bsp_mbar_expect(uint64_t *bar, unsigned bytes)
 
 /* row source of the sweeps (see BspRowsGlobal): tiles staged in shared memory.  One object per sweep; every
  * thread of the block calls the same sequence (the release is a block barrier), thread 0 drives the copies. */
-template <int B>
+template <int B, int RING = 0>
 struct BspRowsStaged {
     using T = BspTile<B>;
     static constexpr bool GL = false;
+    static constexpr int RHS_RING = RING;   /* groups of the right-hand side in flight (factor kernel) */
     double *sm;
     uint64_t *bars;   /* two mbarriers, count 1, not used by an earlier sweep of this launch */
     const double *gH, *gS;
+    double *rq = nullptr;   /* this thread's column of the right-hand-side ring: rq[slot_row * blockDim.x] */
+
+    __device__ __forceinline__ void rhs_issue(int slot_row, const double *src)
+    {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(bsp_smem_u32(rq + (size_t)slot_row * blockDim.x)), "l"(src) : "memory");
+    }
+    __device__ __forceinline__ void rhs_zero(int slot_row) { rq[(size_t)slot_row * blockDim.x] = 0.0; }
+    __device__ __forceinline__ void rhs_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    template <int N>
+    __device__ __forceinline__ void rhs_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+    __device__ __forceinline__ double rhs_read(int slot_row) { return rq[(size_t)slot_row * blockDim.x]; }
 
     __device__ __forceinline__ void issue(int seq, const double *srcH, const double *srcS, int rows, int dst_row)
     {
@@ -308,10 +320,17 @@ __global__ void bsp_prepare_kernel(BspEigChunk g)
     bsp_refine_prepare(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+#ifndef BSP_RHS_RING
+#define BSP_RHS_RING 3   /* groups of B+1 right-hand-side rows in flight per thread in the factor kernel */
+#endif
+/* wide bands: fewer groups, so that tiles + ring stay within the 48 KB of static shared memory */
+__host__ __device__ constexpr int bsp_rhs_ring(int B) { return B <= 6 ? BSP_RHS_RING : (B == 7 ? (BSP_RHS_RING < 2 ? BSP_RHS_RING : 2) : 1); }
 template <int B>
 __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_kernel(BspEigChunk g, int iter, int optional)
 {
     __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
+    constexpr int RING = bsp_rhs_ring(B);
+    __shared__ __align__(16) double ring[(RING + 1) * (B + 1) * BSP_EIG_THREADS];
     __shared__ __align__(8) uint64_t bars[2];
     if (optional && g.counters[BSP_C_REFINED]) return;
     const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,7 +338,8 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B))
     bsp_stage_bars_init(bars);
     if (!__syncthreads_or(active)) return;
     constexpr int FS = 2 * B + 2;
-    BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    BspRowsStaged<B, RING> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    src.rq = ring + threadIdx.x;
     bsp_factor_forward_rows<B>(g, p, e, iter, active, src);
 }
 
