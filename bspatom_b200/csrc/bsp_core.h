@@ -378,6 +378,7 @@ struct BspRoundState {
     double lo, hi, flm, fhm, beta, gp, wdt, frac, s, sfm;
     int clo, chi, fle, fhe, side, done, c, sfe;
     int was_done;   /* done before this round started (the round then only re-publishes its state) */
+    int nfail;      /* interpolated samples in a row that did not halve the bracket */
     int want_defl;  /* the regula-falsi step is possible: the deflation sum at the bracket midpoint is needed */
     int want_count; /* s is a new sample: its inertia is needed                                              */
 };
@@ -390,7 +391,7 @@ BSP_HD void bsp_round_begin(const BspEigChunk &g, int p, int e, int round, BspRo
     const size_t id = (size_t)p * g.ldw + e;
     const size_t rd = (size_t)(round & 1) * per;
     double lo, hi, flm = 0.0, fhm = 0.0, beta = 0.0;
-    int clo, chi, fle = BSP_F_UNKNOWN, fhe = BSP_F_UNKNOWN, side = 0; /* side: 1 = last sample was an interpolated one */
+    int clo, chi, fle = BSP_F_UNKNOWN, fhe = BSP_F_UNKNOWN, side = 0; /* side >= 1: last sample was an interpolated one */
     if (round == 0) {
         lo = g.pbound[p * 4 + 0]; hi = g.pbound[p * 4 + 1]; clo = 0; chi = n;
         if (lo > hi) { const double t_ = lo; lo = hi; hi = t_; } /* unbracketed: flagged in finalize */
@@ -438,7 +439,7 @@ BSP_HD void bsp_round_begin(const BspEigChunk &g, int p, int e, int round, BspRo
     st.lo = lo; st.hi = hi; st.flm = flm; st.fhm = fhm; st.beta = beta; st.gp = gp; st.wdt = wdt;
     st.clo = clo; st.chi = chi; st.fle = fle; st.fhe = fhe; st.side = side; st.done = done; st.was_done = was_done;
     st.s = lo; st.sfm = flm; st.c = clo; st.sfe = fle;
-    st.want_defl = 0; st.want_count = 0; st.frac = 0.5;
+    st.want_defl = 0; st.want_count = 0; st.frac = 0.5; st.nfail = 0;
     if (!done) {
         int m = chi - clo, rk = e - clo;
         if (m < 1) m = 1;
@@ -447,9 +448,14 @@ BSP_HD void bsp_round_begin(const BspEigChunk &g, int p, int e, int round, BspRo
         double frac = ((double)rk + 0.5) / (double)m;
         if (round == 0) frac = frac * frac; /* box states: E_i ~ i^2 */
         st.frac = frac;
-        /* beta holds the bracket width at the previous interpolated sample: if that sample did not at
-         * least halve the bracket, this round bisects (Brent-style safeguard against creeping) */
-        const bool stalled = (side == 1) && (wdt > 0.5 * beta);
+        /* beta holds the bracket width at the previous interpolated sample, side - 1 the number of
+         * interpolated samples in a row before it that did not halve the bracket.  One such sample is
+         * normal -- an estimate in the middle of the bracket lands on one side of the root and leaves the far
+         * end where it was, and the next (overshooting) sample closes it from the other side; after two in a
+         * row this round bisects (Brent-style safeguard against creeping). */
+        const int nfail = (side >= 1 && wdt > 0.5 * beta) ? side : 0;
+        const bool stalled = nfail >= 2;
+        st.nfail = nfail;
         if (m == 1 && round > 0 && !stalled && fle != BSP_F_UNKNOWN && fhe != BSP_F_UNKNOWN &&
             ((flm < 0.0) != (fhm < 0.0)))
             st.want_defl = 1;
@@ -511,7 +517,7 @@ BSP_HD void bsp_round_pick(BspRoundState &st, double bsum)
     }
     double s = st.lo + st.wdt * frac;
     if (!(s > st.lo && s < st.hi)) { s = st.lo + 0.5 * st.wdt; secant = false; }
-    st.side = secant ? 1 : 0;
+    st.side = secant ? st.nfail + 1 : 0;
     st.beta = st.wdt;
     if (!(s > st.lo && s < st.hi)) {
         st.done = 1; st.s = st.lo; st.c = st.clo;
