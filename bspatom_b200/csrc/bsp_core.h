@@ -378,7 +378,7 @@ struct BspRoundState {
     double lo, hi, flm, fhm, beta, gp, wdt, frac, s, sfm;
     int clo, chi, fle, fhe, side, done, c, sfe;
     int was_done;   /* done before this round started (the round then only re-publishes its state) */
-    int nfail;      /* interpolated samples in a row that did not halve the bracket */
+    int nfail;      /* 1: the previous sample was a middle estimate that did not halve the bracket */
     int want_defl;  /* the regula-falsi step is possible: the deflation sum at the bracket midpoint is needed */
     int want_count; /* s is a new sample: its inertia is needed                                              */
 };
@@ -448,14 +448,16 @@ BSP_HD void bsp_round_begin(const BspEigChunk &g, int p, int e, int round, BspRo
         double frac = ((double)rk + 0.5) / (double)m;
         if (round == 0) frac = frac * frac; /* box states: E_i ~ i^2 */
         st.frac = frac;
-        /* beta holds the bracket width at the previous interpolated sample, side - 1 the number of
-         * interpolated samples in a row before it that did not halve the bracket.  One such sample is
-         * normal -- an estimate in the middle of the bracket lands on one side of the root and leaves the far
-         * end where it was, and the next (overshooting) sample closes it from the other side; after two in a
-         * row this round bisects (Brent-style safeguard against creeping). */
-        const int nfail = (side >= 1 && wdt > 0.5 * beta) ? side : 0;
-        const bool stalled = nfail >= 2;
-        st.nfail = nfail;
+        /* beta holds the bracket width at the previous interpolated sample; side says what kind it was:
+         * 1 = an overshooting sample (the estimate hugged one end and the sample was put at twice its distance:
+         * the bracket is expected to collapse), 2 = the estimate itself, somewhere in the middle (it lands on
+         * one side of the root and leaves the far end where it was: the bracket halves at best, and the next,
+         * overshooting, sample closes it from the other side).  An overshooting sample that did not halve the
+         * bracket means the model is off: this round bisects (Brent-style safeguard against creeping).  After a
+         * middle sample that did not halve it, only an overshooting sample is accepted (see bsp_round_pick). */
+        const bool failed = (side >= 1) && (wdt > 0.5 * beta);
+        const bool stalled = failed && side == 1;
+        st.nfail = (failed && side == 2) ? 1 : 0;
         if (m == 1 && round > 0 && !stalled && fle != BSP_F_UNKNOWN && fhe != BSP_F_UNKNOWN &&
             ((flm < 0.0) != (fhm < 0.0)))
             st.want_defl = 1;
@@ -498,6 +500,7 @@ BSP_HD void bsp_round_pick(BspRoundState &st, double bsum)
     if (st.done) return;
     double frac = st.frac;
     bool secant = false;
+    int kind = 0;
     if (st.want_defl) {
         /* regula falsi on the deflated determinant: root at lo + w / (1 + r),
          * r = |f(hi)/f(lo)| exp(-beta w) */
@@ -511,13 +514,20 @@ BSP_HD void bsp_round_pick(BspRoundState &st, double bsum)
          * from that end: the root then (almost surely) lies between the end and the sample and
          * the bracket collapses to ~2x the interpolation error instead of creeping one-sidedly */
         if (t > 0.0 && t < 1.0) {
-            frac = t < 0.25 ? 2.0 * t : (t > 0.75 ? 1.0 - 2.0 * (1.0 - t) : t);
-            secant = true;
+            if (t < 0.25 || t > 0.75) {
+                frac = t < 0.25 ? 2.0 * t : 1.0 - 2.0 * (1.0 - t);
+                secant = true;
+                kind = 1;
+            } else if (!st.nfail) {
+                frac = t;
+                secant = true;
+                kind = 2;
+            }   /* else: a second middle estimate in a row after a poor one: bisect */
         }
     }
     double s = st.lo + st.wdt * frac;
     if (!(s > st.lo && s < st.hi)) { s = st.lo + 0.5 * st.wdt; secant = false; }
-    st.side = secant ? st.nfail + 1 : 0;
+    st.side = secant ? kind : 0;
     st.beta = st.wdt;
     if (!(s > st.lo && s < st.hi)) {
         st.done = 1; st.s = st.lo; st.c = st.clo;
