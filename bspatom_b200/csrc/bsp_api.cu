@@ -429,7 +429,7 @@ struct Carver {
 
 struct ChunkPtrs {
     double *fbH, *pbound, *lo, *hi, *samp_s, *gap, *sigma, *rho, *rho_prev, *scale, *res, *L, *X, *R, *cand_s, *fac;
-    double *samp_fm, *flm, *fhm, *beta;
+    double *samp_fm, *flm, *fhm, *beta, *xmax;
     int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c, *samp_fe, *fle, *fhe, *side, *olist, *ocount;
 };
 
@@ -448,6 +448,7 @@ size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c, bool recomp
     c.gap = cv.take<double>(per); c.done = cv.take<int>(per);
     c.sigma = cv.take<double>(per); c.rho = cv.take<double>(per); c.rho_prev = cv.take<double>(per);
     c.scale = cv.take<double>(per); c.res = cv.take<double>(per); c.status = cv.take<int>(per);
+    c.xmax = cv.take<double>(per);
     c.fac = cv.take<double>(per);
     c.counters = cv.take<int>(64);
     c.olist = cv.take<int>(2 * per); c.ocount = cv.take<int>(4 * (size_t)np);
@@ -480,7 +481,7 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     g.pbound = c.pbound; g.lo = c.lo; g.hi = c.hi; g.clo = c.clo; g.chi = c.chi;
     g.samp_s = c.samp_s; g.samp_c = c.samp_c; g.gap = c.gap; g.done = c.done;
     g.samp_fm = c.samp_fm; g.samp_fe = c.samp_fe; g.flm = c.flm; g.fhm = c.fhm; g.fle = c.fle; g.fhe = c.fhe; g.side = c.side; g.beta = c.beta;
-    g.sigma = c.sigma; g.rho = c.rho; g.rho_prev = c.rho_prev; g.scale = c.scale; g.res = c.res;
+    g.sigma = c.sigma; g.rho = c.rho; g.rho_prev = c.rho_prev; g.scale = c.scale; g.res = c.res; g.xmax = c.xmax;
     g.status = c.status; g.L = c.L; g.X = c.X; g.R = c.R; g.counters = c.counters;
     g.olist = c.olist; g.ocount = c.ocount;
     g.tau = h->opt.tau; g.delta_rel = h->opt.delta_rel; g.conv_tol = h->opt.conv_tol;

@@ -122,6 +122,7 @@ struct BspEigChunk {
     int *done;      /* [npencil][ldw]                             */
     /* refinement state [npencil][ldw] */
     double *sigma, *rho, *rho_prev, *scale, *res;
+    double *xmax;   /* max |x_j| of the vector in X (tracked by the back sweep; the sign convention needs it) */
     int *status;
     /* workspaces */
     double *L; /* [npencil][npad][B+1][ldw]  (zd, l_1..l_B), or, check-pointed:
@@ -319,8 +320,9 @@ BSP_HD int bsp_sturm_count(const double *__restrict__ fbH, const double *__restr
  * pbound[4p..4p+3] = lo0, hi0, hmax, smax ; lo0 > hi0 flags "not bracketed".
  * ------------------------------------------------------------------------- */
 #define BSP_NCAND 64
+/* shift of candidate `lane` of pencil p (and the pencil's scale figures, stored by lane 0) */
 template <int B>
-BSP_HD void bsp_bounds_candidate(const BspEigChunk &g, int p, int lane, double *cand_s, int *cand_c)
+BSP_HD void bsp_bounds_shift(const BspEigChunk &g, int p, int lane, double &sig, double &pivmin)
 {
     constexpr int FS = 2 * B + 2;
     const double *fbH = g.fbH + (size_t)p * g.nrows * FS;
@@ -335,16 +337,24 @@ BSP_HD void bsp_bounds_candidate(const BspEigChunk &g, int p, int lane, double *
         if (q > s0) s0 = q;
     }
     if (!(s0 > 0.0) || !(s0 < INFINITY)) s0 = 1.0;
-    double sig;
     if (lane < 32) sig = ldexp(s0, lane - 8);
     else sig = -ldexp(s0, lane - 32 - 16);
-    const double pivmin = 1e-30 * (hmax + fabs(sig) * smax);
-    cand_s[p * BSP_NCAND + lane] = sig;
-    cand_c[p * BSP_NCAND + lane] = bsp_sturm_count<B>(fbH, fbS, g.npad, sig, pivmin, nullptr);
+    pivmin = 1e-30 * (hmax + fabs(sig) * smax);
     if (lane == 0) {
         g.pbound[p * 4 + 2] = hmax;
         g.pbound[p * 4 + 3] = smax;
     }
+}
+
+template <int B>
+BSP_HD void bsp_bounds_candidate(const BspEigChunk &g, int p, int lane, double *cand_s, int *cand_c)
+{
+    constexpr int FS = 2 * B + 2;
+    double sig, pivmin;
+    bsp_bounds_shift<B>(g, p, lane, sig, pivmin);
+    cand_s[p * BSP_NCAND + lane] = sig;
+    cand_c[p * BSP_NCAND + lane] = bsp_sturm_count<B>(g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS,
+                                                      g.npad, sig, pivmin, nullptr);
 }
 
 BSP_HD void bsp_bounds_pick(const BspEigChunk &g, int p, const double *cand_s, const int *cand_c)
@@ -847,7 +857,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int cor
     double yw[K1], xv[K1], hs[K1], ss[K1];
 #pragma unroll
     for (int i = 0; i < K1; ++i) { yw[i] = 0.0; xv[i] = 0.0; hs[i] = 0.0; ss[i] = 0.0; }
-    double xSx = 0.0, xHx = 0.0, resmax = 0.0;
+    double xSx = 0.0, xHx = 0.0, resmax = 0.0, xabs = 0.0;
 
     /* ring of PF factor rows (+ x_old) in flight: row j is consumed PF steps after its loads were
      * issued, which is what hides the HBM latency of this purely streaming sweep */
@@ -896,6 +906,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int cor
                 if (j < n) {
                     xn = fma(cx, xq[q], -yj);
                     Xp[(size_t)j * ldw] = xn;
+                    xabs = fmax(xabs, fabs(xn));
                 }
             }
             fetch(q, j - PF);   /* slot q is free again: row j-PF goes in flight */
@@ -970,6 +981,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int cor
         scn = 1.0 / sqrt(xSx);
         res = resmax * scn;
     }
+    g.xmax[id] = xabs;
     g.rho_prev[id] = rho_p;
     g.rho[id] = rho_new;
     g.scale[id] = scn;
@@ -1149,7 +1161,7 @@ BSP_HD void bsp_back_recompute(const BspEigChunk &g, int p, int e, int corr_now,
     double yw[K1], xv[K1], hs[K1], ss[K1];
 #pragma unroll
     for (int i = 0; i < K1; ++i) { yw[i] = 0.0; xv[i] = 0.0; hs[i] = 0.0; ss[i] = 0.0; }
-    double xSx = 0.0, xHx = 0.0, resmax = 0.0;
+    double xSx = 0.0, xHx = 0.0, resmax = 0.0, xabs = 0.0;
     double scratch[T][K1]; /* (zd, l_1..l_B) of the rows of the current segment */
     double xold[T];        /* x_old of the segment, fetched during the re-elimination (HBM latency hidden) */
     double ah[K1], as[K1]; /* band column of the row about to be processed, one step ahead */
@@ -1172,6 +1184,7 @@ BSP_HD void bsp_back_recompute(const BspEigChunk &g, int p, int e, int corr_now,
             if (j < n) {
                 xn = fma(cx, xo, -yj);
                 Xp[(size_t)j * ldw] = xn;
+                xabs = fmax(xabs, fabs(xn));
             }
         } else {
             yw[0] = 0.0;
@@ -1296,6 +1309,7 @@ BSP_HD void bsp_back_recompute(const BspEigChunk &g, int p, int e, int corr_now,
         scn = 1.0 / sqrt(xSx);
         res = resmax * scn;
     }
+    g.xmax[id] = xabs;
     g.rho_prev[id] = rho_p;
     g.rho[id] = rho_new;
     g.scale[id] = scn;
@@ -1347,8 +1361,7 @@ BSP_HD void bsp_finalize_eigen(const BspEigChunk &g, int p, int e, double *E, do
     const double rho = g.rho[id];
     E[(size_t)p * g.n + e] = rho;
     const double *Xp = g.X + (size_t)p * g.xrows * g.ldw + e;
-    double amax = 0.0;
-    for (int j = 0; j < g.n; ++j) amax = fmax(amax, fabs(Xp[(size_t)j * g.ldw]));
+    const double amax = g.xmax[id];   /* = max_j |X(j,e)|, from the back sweep that wrote the vector */
     double sgn = 1.0;
     const double thr = 1e-6 * amax;
     for (int j = 0; j < g.n; ++j) {

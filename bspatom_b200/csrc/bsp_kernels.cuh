@@ -31,12 +31,6 @@ constexpr int bsp_minb_128(int base, int B) { return B <= 6 ? base : (B == 7 ? (
 /* `base` counts blocks of 128 threads; larger blocks keep the same number of resident warps */
 constexpr int bsp_minb(int base, int B) { return (bsp_minb_128(base, B) * 128) / BSP_EIG_THREADS > 0 ? (bsp_minb_128(base, B) * 128) / BSP_EIG_THREADS : 1; }
 
-template <int B>
-__global__ void __launch_bounds__(BSP_NCAND) bsp_bounds_kernel(BspEigChunk g, double *cand_s, int *cand_c)
-{
-    bsp_bounds_candidate<B>(g, blockIdx.x, threadIdx.x, cand_s, cand_c);
-}
-
 __global__ void bsp_zero_words_kernel(int *w, int n)
 {
     if ((int)threadIdx.x < n) w[threadIdx.x] = 0;
@@ -211,6 +205,23 @@ __device__ __forceinline__ void bsp_stage_bars_init(uint64_t *bars)
         bsp_mbar_init(bars + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+}
+
+/* spectrum bounds: the BSP_NCAND shifts of the ladder, one thread each, band rows staged like in the sweeps */
+template <int B>
+__global__ void __launch_bounds__(BSP_NCAND) bsp_bounds_kernel(BspEigChunk g, double *cand_s, int *cand_c)
+{
+    __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int p = blockIdx.x, lane = threadIdx.x;
+    constexpr int FS = 2 * B + 2;
+    bsp_stage_bars_init(bars);
+    double sig, pivmin;
+    bsp_bounds_shift<B>(g, p, lane, sig, pivmin);
+    __syncthreads();    /* publishes the mbarrier initialisation */
+    BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    cand_s[p * BSP_NCAND + lane] = sig;
+    cand_c[p * BSP_NCAND + lane] = bsp_sturm_sweep<B>(src, g.npad, true, sig, pivmin, nullptr, nullptr, nullptr);
 }
 
 __device__ __forceinline__ float bsp_frcp_fast(float x)

@@ -98,7 +98,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     std::vector<int> inst(npencil), nvec(npencil);
     for (int p = 0; p < npencil; ++p) { inst[p] = p; nvec[p] = nvec_in[p]; }
     std::vector<double> pbound(npencil * 4), lo(2 * per), hi(2 * per), samp_s(2 * per), gap(per), sigma(per),
-        rho(per), rho_prev(per), scale(per), res(per);
+        rho(per), rho_prev(per), scale(per), res(per), xmax(per);
     std::vector<int> clo(2 * per), chi(2 * per), samp_c(2 * per), done(per), status(per), counters(BSP_C_WORDS, 0);
     std::vector<double> samp_fm(2 * per), flm(per), fhm(per), beta(per);
     std::vector<int> samp_fe(2 * per), fle(per), fhe(per), side(per);
@@ -110,7 +110,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     g.samp_fm = samp_fm.data(); g.samp_fe = samp_fe.data(); g.flm = flm.data(); g.fhm = fhm.data();
     g.fle = fle.data(); g.fhe = fhe.data(); g.side = side.data(); g.beta = beta.data();
     g.sigma = sigma.data(); g.rho = rho.data(); g.rho_prev = rho_prev.data(); g.scale = scale.data();
-    g.res = res.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
+    g.res = res.data(); g.xmax = xmax.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
     g.counters = counters.data(); g.tau = tau; g.delta_rel = delta_rel; g.conv_tol = conv_tol;
     EmulExec<B> ex; ex.g = g; ex.recompute = getenv("BSP_EMUL_RECOMPUTE") ? atoi(getenv("BSP_EMUL_RECOMPUTE")) : 0;
     BspSchedule sch = {max_rounds, min_iters, max_iters};
