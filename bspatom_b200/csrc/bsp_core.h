@@ -39,7 +39,20 @@
 
 #if defined(__CUDA_ARCH__)
 #define BSP_LDG(p) __ldg(p)
-#define BSP_RCP(x) __drcp_rn(x)
+/* reciprocal of a pivot: the arguments are finite, normal and bounded away from zero (|d| >= pivmin), so the
+ * special-case path of __drcp_rn (a branch + call per row of every sweep) is not needed: hardware seed
+ * (MUFU.RCP64H, ~20 bits), one cubic and one linear correction, the same arithmetic as the library's fast path */
+__device__ __forceinline__ double bsp_drcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+#define BSP_RCP(x) bsp_drcp(x)
 #else
 #define BSP_LDG(p) (*(p))
 #define BSP_RCP(x) (1.0 / (x))
@@ -226,8 +239,10 @@ BSP_HD void bsp_sturm_group(double (&w)[B + 1][B + 1], const double *__restrict_
         double d = w[t][t];
         if (fabs(d) < pivmin) d = -pivmin;
         if (d < 0.0) { ++cnt; if (first < 0) first = j0 + t; }
+        /* det = product of the pivots, kept as mantissa * 2^fe; |d| >= pivmin and a huge pivot only follows a
+         * tiny one, so the mantissa may run over four rows before it is brought back to [0.5, 1) */
         fm *= d;
-        bsp_renorm(fm, fe);
+        if ((t & 3) == 3 || t == K1 - 1) bsp_renorm(fm, fe);
         const double rinv = BSP_RCP(d);
         double col[K1], l[K1];
 #pragma unroll
