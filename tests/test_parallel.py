@@ -68,3 +68,15 @@ def test_gather_single_process():
     E = np.arange(12.0).reshape(3, 4)
     Eg, Cg = gather_eigenpairs(E, [0, 1, 2], 3, 4)
     assert np.array_equal(Eg, E) and Cg is None
+
+
+def test_numa_binding_helper_is_best_effort():
+    """bind_host_memory_to_gpu never raises: unknown devices / single-node hosts leave everything as it is."""
+    import os
+
+    from bspatom_b200.parallel import bind_host_memory_to_gpu
+
+    before = os.sched_getaffinity(0)
+    out = bind_host_memory_to_gpu("0000:ff:1f.0")          # no such device here
+    assert out["node"] is None and out["mempolicy"] is False
+    assert os.sched_getaffinity(0) == before
