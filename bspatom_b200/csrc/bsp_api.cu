@@ -507,7 +507,7 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
         int maxnv = 0;
         for (int p = 0; p < np; ++p) maxnv = std::max(maxnv, G.nvec[p0 + p]);
         if (maxnv > 0) {
-            dim3 tg((maxnv + 31) / 32, (G.n + 31) / 32, np), tb(32, 8);
+            dim3 tg((maxnv + 31) / 32, (G.n + 32 * BSP_TR_TILES - 1) / (32 * BSP_TR_TILES), np), tb(32, 8);
             bsp_transpose_kernel<<<tg, tb, 0, h->st>>>(g, c.fac, G.d_C, G.d_coff + p0);
             h->launches++;
             CU(cudaGetLastError());
@@ -891,25 +891,25 @@ extern "C" int bspatom_batch_run(bspatom_handle h)
 namespace {
 
 template <int B>
-int launch_pdcheck_b(bspatom_handle h, Group &G)
+int launch_pdcheck_b(bspatom_handle h, Group &G, cudaStream_t st)
 {
-    bsp_pdcheck_fast_kernel<B><<<(G.ninst + 31) / 32, 32, 0, h->st>>>(G.d_fbS, G.n, G.npad, G.nrows, G.ninst, G.d_pdinfo);
+    bsp_pdcheck_fast_kernel<B><<<(G.ninst + 31) / 32, 32, 0, st>>>(G.d_fbS, G.n, G.npad, G.nrows, G.ninst, G.d_pdinfo);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
-int launch_pdcheck(bspatom_handle h, Group &G)
+int launch_pdcheck(bspatom_handle h, Group &G, cudaStream_t st)
 {
     switch (G.B) {
-    case 2: return launch_pdcheck_b<2>(h, G);
-    case 3: return launch_pdcheck_b<3>(h, G);
-    case 4: return launch_pdcheck_b<4>(h, G);
-    case 5: return launch_pdcheck_b<5>(h, G);
-    case 6: return launch_pdcheck_b<6>(h, G);
-    case 7: return launch_pdcheck_b<7>(h, G);
-    case 8: return launch_pdcheck_b<8>(h, G);
-    case 9: return launch_pdcheck_b<9>(h, G);
+    case 2: return launch_pdcheck_b<2>(h, G, st);
+    case 3: return launch_pdcheck_b<3>(h, G, st);
+    case 4: return launch_pdcheck_b<4>(h, G, st);
+    case 5: return launch_pdcheck_b<5>(h, G, st);
+    case 6: return launch_pdcheck_b<6>(h, G, st);
+    case 7: return launch_pdcheck_b<7>(h, G, st);
+    case 8: return launch_pdcheck_b<8>(h, G, st);
+    case 9: return launch_pdcheck_b<9>(h, G, st);
     default: return BSPATOM_EUNSUPPORTED;
     }
 }
@@ -958,6 +958,9 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     cudaEvent_t e0, e1, e2, copies_done;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
     CU(cudaEventCreateWithFlags(&copies_done, cudaEventDisableTiming));
+    cudaEvent_t pd_done;
+    CU(cudaEventCreateWithFlags(&pd_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(pd_done, h->st_copy));
     CopyQueue *cq = (E_out || C_out) ? copy_queue(h->dev) : nullptr;
     if ((E_out || C_out) && !cq) { h->err = "cannot create the result-copy stream"; return BSPATOM_ECUDA; }
     std::unique_lock<std::mutex> turn;
@@ -981,9 +984,13 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             timed_end(h, s);
             if (rc) return rc;
         }
-        if ((rc = launch_pdcheck(h, G))) return rc;
         CU(cudaMemsetAsync(G.d_bad, 0, sizeof(int) * G.npencil, h->st));
         CU(cudaEventRecord(e2, h->st));
+        /* positive definiteness of S: one thread per instance walks a whole Cholesky-like sweep (~0.7 ms of pure
+         * latency), needed only when the info flags are assembled -- on the side stream, off the critical path */
+        CU(cudaStreamWaitEvent(h->st_copy, e2, 0));
+        if ((rc = launch_pdcheck(h, G, h->st_copy))) return rc;
+        CU(cudaEventRecord(pd_done, h->st_copy));
         /* ---- chunking ---- */
         ChunkPtrs c;
         const size_t per_pencil = carve_chunk(G, 1, nullptr, c, h->opt.recompute != 0);
@@ -1165,6 +1172,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, e1, e2)); t_asm += ms;
     }
+    CU(cudaStreamWaitEvent(h->st, pd_done, 0));
     /* info flags of every group -> mailbox (all chunk streams are drained at this point) */
     {
         size_t need = 0;
@@ -1191,7 +1199,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     }
     float total = 0;
     CU(cudaEventElapsedTime(&total, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(copies_done);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(copies_done); cudaEventDestroy(pd_done);
     h->stats[0] = (double)(h->launches + aux_launches() - launches0);
     h->stats[1] = rounds; h->stats[2] = iters;
     /* stage times are summed over the chunk streams: with several streams they overlap in wall time */

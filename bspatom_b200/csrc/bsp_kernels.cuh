@@ -426,26 +426,38 @@ __global__ void bsp_finalize_kernel(BspEigChunk g, double *E, double *fac, int *
 }
 
 /* C[p] (n x nvec_p, column-major, column e = eigenvector e) = fac[e] * X[p][row][e]
- * 32x32 shared-memory transpose; coff[p] = offset of pencil p's block in C. */
+ * shared-memory transpose of BSP_TR_TILES tiles of 32x32 per block (all loads of a block in flight before its
+ * barrier); coff[p] = offset of pencil p's block in C. */
+#define BSP_TR_TILES 4
 __global__ void bsp_transpose_kernel(BspEigChunk g, const double *fac, double *C, const long long *coff)
 {
-    __shared__ double tile[32][33];
+    __shared__ double tile[BSP_TR_TILES][32][33];
     const int p = blockIdx.z;
     const int nv = g.nvec[p];
-    const int e0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int e0 = blockIdx.x * 32, r00 = blockIdx.y * 32 * BSP_TR_TILES;
     if (e0 >= nv) return;
     const double *X = g.X + (size_t)p * g.xrows * g.ldw;
-    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
-        const int r = r0 + rr, e = e0 + threadIdx.x;
-        double v = 0.0;
-        if (r < g.n && e < nv) v = X[(size_t)r * g.ldw + e] * fac[(size_t)p * g.ldw + e];
-        tile[rr][threadIdx.x] = v;
+    const int e_in = e0 + threadIdx.x;
+    const double f = e_in < nv ? fac[(size_t)p * g.ldw + e_in] : 0.0;
+#pragma unroll
+    for (int t = 0; t < BSP_TR_TILES; ++t) {
+#pragma unroll
+        for (int rr = threadIdx.y; rr < 32; rr += 8) {
+            const int r = r00 + t * 32 + rr;
+            double v = 0.0;
+            if (r < g.n && e_in < nv) v = X[(size_t)r * g.ldw + e_in] * f;
+            tile[t][rr][threadIdx.x] = v;
+        }
     }
     __syncthreads();
     double *Cp = C + coff[p];
-    for (int ee = threadIdx.y; ee < 32; ee += blockDim.y) {
-        const int e = e0 + ee, r = r0 + threadIdx.x;
-        if (e < nv && r < g.n) Cp[(size_t)e * g.n + r] = tile[threadIdx.x][ee];
+#pragma unroll
+    for (int t = 0; t < BSP_TR_TILES; ++t) {
+#pragma unroll
+        for (int ee = threadIdx.y; ee < 32; ee += 8) {
+            const int e = e0 + ee, r = r00 + t * 32 + threadIdx.x;
+            if (e < nv && r < g.n) Cp[(size_t)e * g.n + r] = tile[t][threadIdx.x][ee];
+        }
     }
 }
 
