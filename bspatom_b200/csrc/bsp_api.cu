@@ -107,9 +107,9 @@ struct bspatom_handle_s {
     bool mail_info = false;       /* the mailbox holds pdinfo / bad of the last run (see run_internal) */
     double stats[24] = {0};
     long long launches = 0;
-    /* second chunk stream: an auxiliary context (own stream, workspace, polling word, event pool)
-     * driven by a helper thread, so two chunks are in flight and the GPU back-fills the tail
-     * waves / polling bubbles of one with blocks of the other */
+    /* further chunk streams: auxiliary contexts (own stream, workspace, event pool) that the same host
+     * thread enqueues on, so several chunks are in flight and the GPU back-fills the tail waves and the
+     * latency-bound kernels of one with blocks of the others */
     std::vector<bspatom_handle_s *> aux; /* helper contexts 1..workers-1 */
     std::mutex mu;
     /* per-kernel-class device timing (CUDA events on the launching stream) */
@@ -686,7 +686,7 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "min_iters") h->opt.min_iters = std::max(2, (int)v);
     else if (s == "max_iters") h->opt.max_iters = std::max(3, (int)v);
     else if (s == "rounds_enqueued") h->opt.rounds_enqueued = std::max(1, (int)v);
-    else if (s == "first_check_round" || s == "check_every") { /* accepted for compatibility: the schedule no longer polls */ }
+    else if (s == "first_check_round" || s == "check_every") { /* accepted and ignored: the schedule is static */ }
     else if (s == "chunk") h->opt.chunk = (int)v;
     else if (s == "recompute") { h->opt.recompute = v != 0.0; h->budget_bytes = 0; }
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);

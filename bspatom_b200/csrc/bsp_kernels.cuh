@@ -4,7 +4,8 @@
  * Thread mapping everywhere: blockIdx.y = pencil, blockIdx.x*blockDim.x +
  * threadIdx.x = eigen index e, so a warp streams 32 consecutive e of one
  * pencil: every workspace access X/R/L[row][e] is a fully coalesced 256 B
- * line and every band-row read is a warp-uniform broadcast that stays in L1.
+ * line.  The band rows of the pencil, which every thread of a block walks in the
+ * same order, come through shared-memory tiles filled by bulk copies (BspRowsStaged).
  */
 #ifndef BSP_KERNELS_CUH
 #define BSP_KERNELS_CUH
