@@ -156,3 +156,21 @@ def test_fast_schedule_two_solves_plus_residual_pass(emul, oracle):
     R = H @ C2 - (m["S"] @ C2) * E2
     assert (np.abs(R).max(0) / np.maximum(1, np.abs(E2))).max() < 1e-10
     assert np.abs(C2.T @ m["S"] @ C2 - np.eye(b.nfun)).max() < 1e-6
+
+
+@pytest.mark.parametrize("kw,lmax,max_rounds", [
+    (dict(kind_grid=0, k=7, nfun=300, rb=150.0), 2, 13),
+    (dict(kind_grid=2, k=7, nfun=300, rb=500.0, rmax=60.0), 2, 16),
+    (dict(kind_grid=0, k=8, nfun=240, rb=120.0), 1, 13),
+])
+def test_schedule_budget(emul, oracle, kw, lmax, max_rounds):
+    """Guards the tuning of the bracketing safeguards: every bracket closes within the rounds the static
+    schedule enqueues (26) with room to spare, and three solves converge every eigenpair (a straggler that
+    creeps shows up here as extra rounds / iterations long before it shows up as a wrong answer)."""
+    b = oracle.make_basis(**kw)
+    m = oracle.matrix_svt(b, lmax=lmax)
+    for l in range(lmax + 1):
+        H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+        E, Cm, st = solve(emul, H, m["S"], b.k - 1)
+        assert st[0] <= max_rounds, (l, st[0])
+        assert st[1] == 3 and st[2] == 0 and st[3] == 0 and st[5] == 0, (l, list(st))
