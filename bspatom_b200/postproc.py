@@ -171,3 +171,97 @@ def collect_cinl(C_per_l: List[np.ndarray], sel: StateSelection) -> np.ndarray:
         keep = min(sel.ntemp[l], sel.n1_max, C_per_l[l].shape[1])
         cinl[:, :keep, l] = C_per_l[l][:, :keep]
     return cinl
+
+
+# ---- plane-wave photo-ionisation (KIND_PI = 1, 2): TRANS_AMP factors and CROSS_SECTIONS -------------
+# SURVEY.md 8(f) row f-4, dipole branch: what the reference does with the matrix elements
+# <n_f l_f | A | n_0 l_0> = ci_fin^T A ci_ini (bspatom_dipole) before it writes CSs/CrossSection_*.dat.
+C_AU = 137.03599913815          # Modules.f90:12
+A_AU = 5.29177249e-9            # Modules.f90:12  (cm)
+
+
+def three_j(j1: int, j2: int, j3: int, m1: int, m2: int, m3: int) -> float:
+    """Wigner 3j symbol for integer arguments (what THREE_J, Funs_WignerSymbols.for:1-60, evaluates with
+    log-factorials); Racah's formula in exact rational arithmetic, one square root at the end."""
+    from fractions import Fraction
+    from math import factorial as f, sqrt
+
+    if m1 + m2 + m3 != 0 or j3 > j1 + j2 or j3 < abs(j1 - j2):
+        return 0.0
+    if abs(m1) > j1 or abs(m2) > j2 or abs(m3) > j3:
+        return 0.0
+    tmin = max(0, j2 - j3 - m1, j1 + m2 - j3)
+    tmax = min(j1 + j2 - j3, j1 - m1, j2 + m2)
+    if tmax < tmin:
+        return 0.0
+    acc = Fraction(0)
+    for t in range(tmin, tmax + 1):
+        den = f(t) * f(j1 + j2 - j3 - t) * f(j1 - m1 - t) * f(j2 + m2 - t) * f(j3 - j2 + m1 + t) * f(j3 - j1 - m2 + t)
+        acc += Fraction((-1) ** t, den)
+    delta = Fraction(f(j1 + j2 - j3) * f(j1 - j2 + j3) * f(-j1 + j2 + j3), f(j1 + j2 + j3 + 1))
+    pref = delta * f(j1 + m1) * f(j1 - m1) * f(j2 + m2) * f(j2 - m2) * f(j3 + m3) * f(j3 - m3)
+    val = acc * acc * pref                       # square of the symbol, exact
+    sign = (-1) ** (j1 - j2 - m3) * (1 if acc >= 0 else -1)
+    return sign * sqrt(val.numerator / val.denominator) if val.denominator < 2 ** 1000 and val.numerator < 2 ** 1000 \
+        else sign * sqrt(float(val))
+
+
+def dipole_angular_factors(kind_pi: int, l0: int, m0: int, lf: int, mf: int, mph: int):
+    """(c0, c1, c2) of TRANS_AMP's plane-wave branch (PhotoIon.f90:67-85): the radial operator is
+    A = c1*rij(:,:,1) + c2*rij(:,:,2) and the amplitude c0 * An * <f|A|i>.
+    KIND_PI = 1 (length): rij1 = <B_i|r|B_j>;  KIND_PI = 2 (velocity): rij1 = <B_i|1/r|B_j>, rij2 = <B_i|B_j'>."""
+    t3a = three_j(lf, 1, l0, -mf, mph, m0)
+    if kind_pi == 1:
+        t3b = three_j(lf, 1, l0, 0, 0, 0)
+        c1 = (-1.0) ** (lf + l0 + mf) * np.sqrt(float((2 * lf + 1) * (2 * l0 + 1))) * t3a * t3b
+        return 1.0, c1, 0.0
+    c0 = np.sqrt(float(l0 + 1)) * t3a
+    c1 = c2 = 0.0
+    if lf == l0 + 1:
+        c1, c2 = float(l0 + 1), -1.0
+    elif lf == l0 - 1:
+        c1, c2 = float(l0), 1.0
+    return c0, c1, c2
+
+
+def trans_amp_dipole(D: np.ndarray, E_fin: np.ndarray, n0_fin: int, n1_fin: int, c0: float) -> np.ndarray:
+    """T_fi(ni) = An * c0 * <ci_fin(:,ni)| A |ci_ini>, ni = n0_fin..n1_fin (1-based, PhotoIon.f90:96-106), with the
+    density-of-states normalisation An = sqrt(2 / (E_fin(ni+1) - E_fin(ni-1))).  D[ni-1] is the matrix element of
+    final state ni (one column of bspatom_dipole's result).  Returns the array T_fi(n0_fin:n1_fin)."""
+    ni = np.arange(n0_fin, n1_fin + 1)                 # 1-based
+    An = np.sqrt(2.0 / (E_fin[ni] - E_fin[ni - 2]))    # E_fin(ni+1) - E_fin(ni-1)
+    return An * c0 * np.asarray(D, dtype=np.float64)[ni - 1]
+
+
+def cross_sections_dipole(kind_pi: int, E0: float, E_fin: np.ndarray, T_fi: np.ndarray, n0_fin: int, n1_fin: int,
+                          l0: int):
+    """(Ef, sigma in Mb) of CROSS_SECTIONS for KIND_PI = 1, 2 (PhotoIon.f90:300-318, 395-414):
+    sigma = M_au * (4 pi^2 / c) * 1/(2 l0 + 1) * d1 * T_fi^2, d1 = Ef - E0 (length) or 1/(Ef - E0) (velocity)."""
+    ni = np.arange(n0_fin, n1_fin + 1)
+    Ef = E_fin[ni - 1]
+    M_au = (A_AU ** 2) * 1.0e18
+    c0 = 4.0 * (np.pi ** 2) / C_AU
+    c1 = 1.0 / float(2 * l0 + 1)
+    d1 = (Ef - E0) if kind_pi == 1 else 1.0 / (Ef - E0)
+    return Ef, M_au * c0 * c1 * d1 * np.asarray(T_fi, dtype=np.float64) ** 2
+
+
+def fortran_g_e3(v: float, w: int, d: int) -> str:
+    """Gw.dE3 (three exponent digits): the F sub-format is followed by e + 2 = 5 blanks."""
+    n = abs(v)
+    if n == 0.0:
+        return ("%.*f" % (d - 1, 0.0)).rjust(w - 5) + "     "
+    ex10 = int(("%.*E" % (d - 1, n)).split("E")[1]) + 1
+    if 0 <= ex10 <= d:
+        s = "%.*f" % (d - ex10, v)
+        return (s.rjust(w - 5) if len(s) <= w - 5 else "*" * (w - 5)) + "     "
+    m, _ = ("%.*E" % (d - 1, n)).split("E")
+    body = ("-" if v < 0 else "") + "0." + m.replace(".", "") + "E%+04d" % ex10
+    return body.rjust(w) if len(body) <= w else "*" * w
+
+
+def write_cross_section(path: str, Ef: np.ndarray, sigma: np.ndarray) -> None:
+    """CSs/CrossSection_Len.dat / _Vel.dat: one `FORMAT(2G20.10E3)` record per final state (PhotoIon.f90:417,461)."""
+    with open(path, "w") as fh:
+        for e, s in zip(Ef, sigma):
+            fh.write(fortran_g_e3(float(e), 20, 10) + fortran_g_e3(float(s), 20, 10) + "\n")

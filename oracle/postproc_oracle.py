@@ -135,3 +135,76 @@ def trans_amp_block(zA, Cf, Ci):
     U = np.triu(zA, 1)
     Ah = U + np.conj(U).T + np.diag(np.real(np.diag(zA)))
     return np.asarray(Cf).T @ (Ah @ np.asarray(Ci))
+
+
+def three_j_ref(i1, i2, i3, m1, m2, m3):
+    """THREE_J as the reference evaluates it (Funs_WignerSymbols.for:1-57): log-factorial table, terms scaled by
+    the smallest one, alternating sum.  Returns 0 where the reference's selection rules fail."""
+    import math
+
+    fac = [0.0] * 141                                    # FAC(I) = log((I-1)!), 1-based
+    for i in range(2, 141):
+        fac[i] = fac[i - 1] + math.log(float(i - 1))
+    l4 = i1 + i2 + i3 + 2
+    if l4 > 140 or m1 + m2 + m3 != 0:
+        return 0.0
+    izmax = min(i1 + i2 - i3, i1 - m1, i2 + m2) + 1
+    izmin = max(0, i2 - i3 - m1, i1 + m2 - i3) + 1
+    if izmax - izmin < 0:
+        return 0.0
+    l1, l2, l3 = i1 + i2 - i3 + 1, i3 + i1 - i2 + 1, i3 + i2 - i1 + 1
+    l5, l6, l7, l8, l9, l10 = i1 + m1 + 1, i1 - m1 + 1, i2 + m2 + 1, i2 - m2 + 1, i3 + m3 + 1, i3 - m3 + 1
+    if min(l1, l2, l3, l5, l6, l7, l8, l9, l10) < 1:
+        return 0.0                                       # outside the triangle / |m| > j: the reference indexes FAC(0)
+    abra = 0.5 * (fac[l1] + fac[l2] + fac[l3] - fac[l4] + fac[l5] + fac[l6] + fac[l7] + fac[l8] + fac[l9] + fac[l10])
+    k1, k2 = i3 - i2 + m1 + 1, i3 - i1 - m2 + 1
+    gros = 250.0
+    ac = {}
+    for ii in range(izmin, izmax + 1):
+        i = ii - 1
+        ac[ii] = fac[i + 1] + fac[l1 - i] + fac[l6 - i] + fac[l7 - i] + fac[k1 + i] + fac[k2 + i]
+        if ac[ii] < gros:
+            gros = ac[ii]
+    accu = 0.0
+    sig = (-1.0) ** izmin
+    for ii in range(izmin, izmax + 1):
+        sig = -sig
+        accu += sig * math.exp(-(ac[ii] - gros))
+    return (-1.0) ** (i1 - i2 - m3) * math.exp(abra - gros) * accu
+
+
+def photoion_dipole_ref(kind_pi, A, ci_ini, ci_fin, E_ini_n0, E_fin, n0_fin, n1_fin, l0, m0, lf, mf, mph):
+    """TRANS_AMP (PhotoIon.f90:50-107) + CROSS_SECTIONS (:300-318, :395-417) for KIND_PI = 1, 2, loop by loop.
+    A: (rij1, rij2) dense operators (rij2 None for the length gauge); ci_fin: (nfun, nfun) all final vectors;
+    indices 1-based as in the reference.  Returns (Ef list, T_fi list, sigma list) over ni = n0_fin..n1_fin."""
+    import math
+
+    n = len(ci_ini)
+    t3a = three_j_ref(lf, 1, l0, -mf, mph, m0)
+    if kind_pi == 1:
+        t3b = three_j_ref(lf, 1, l0, 0, 0, 0)
+        c1 = (-1.0) ** (lf + l0 + mf) * math.sqrt(float((2 * lf + 1) * (2 * l0 + 1))) * t3a * t3b
+        c0 = 1.0
+        Am = [[c1 * A[0][i][j] for j in range(n)] for i in range(n)]
+    else:
+        c0 = math.sqrt(float(l0 + 1)) * t3a
+        c1 = c2 = 0.0
+        if lf == l0 + 1:
+            c1, c2 = float(l0 + 1), -1.0
+        elif lf == l0 - 1:
+            c1, c2 = float(l0), 1.0
+        Am = [[c1 * A[0][i][j] + c2 * A[1][i][j] for j in range(n)] for i in range(n)]
+    v = [sum(Am[i][j] * ci_ini[j] for j in range(n)) for i in range(n)]          # DGEMV
+    M_au = (5.29177249e-9 ** 2) * 1.0e18
+    cc0 = 4.0 * (math.pi ** 2) / 137.03599913815
+    cc1 = 1.0 / float(2 * l0 + 1)
+    Ef, T, sig = [], [], []
+    for ni in range(n0_fin, n1_fin + 1):
+        An = math.sqrt(2.0 / (E_fin[ni] - E_fin[ni - 2]))                         # E_fin(ni+1) - E_fin(ni-1)
+        t = An * c0 * sum(ci_fin[i][ni - 1] * v[i] for i in range(n))            # DDOT
+        e = E_fin[ni - 1]
+        d1 = (e - E_ini_n0) if kind_pi == 1 else 1.0 / (e - E_ini_n0)
+        Ef.append(e)
+        T.append(t)
+        sig.append(M_au * cc0 * cc1 * d1 * t * t)
+    return Ef, T, sig

@@ -109,3 +109,76 @@ def test_zhvmv_restatement_matches_blas_zhemv():
             ref = blas.zdotu(zy, v)
             assert abs(po.zhvmv(zA, zx, zy) - ref) < 1e-12 * (1 + abs(ref))
             assert abs(T[f, i] - ref) < 1e-12 * (1 + abs(ref))
+
+
+def test_three_j_exact_vs_reference_restatement_and_closed_forms():
+    import numpy as np
+
+    from bspatom_b200 import postproc as pp
+    from oracle import postproc_oracle as po
+
+    # closed forms: (l+1 1 l; 0 0 0) = (-1)^(l+1) sqrt((l+1) / ((2l+1)(2l+3)))
+    for l in range(0, 12):
+        exact = (-1) ** (l + 1) * np.sqrt((l + 1) / ((2 * l + 1) * (2 * l + 3)))
+        assert abs(pp.three_j(l + 1, 1, l, 0, 0, 0) - exact) < 1e-15
+    assert abs(pp.three_j(1, 1, 0, 0, 0, 0) + 1 / np.sqrt(3)) < 1e-15
+    assert pp.three_j(2, 1, 0, 0, 0, 0) == 0.0 and pp.three_j(1, 1, 1, 0, 0, 0) == 0.0
+    # the reference's log-factorial evaluation on a sweep of arguments
+    for j1 in range(0, 7):
+        for j3 in range(abs(j1 - 1), j1 + 2):
+            for m1 in range(-j1, j1 + 1):
+                for m2 in (-1, 0, 1):
+                    m3 = -m1 - m2
+                    if abs(m3) > j3:
+                        continue
+                    a, b = pp.three_j(j1, 1, j3, m1, m2, m3), po.three_j_ref(j1, 1, j3, m1, m2, m3)
+                    assert abs(a - b) < 1e-13, (j1, j3, m1, m2, a, b)
+
+
+def test_plane_wave_cross_sections_match_the_loop_restatement(tmp_path):
+    """TRANS_AMP factors + CROSS_SECTIONS of the dipole branch (PhotoIon.f90:50-107, 300-318, 395-417) on a real
+    hydrogen pencil from the oracle: vectorised host code vs the loop-by-loop restatement, both gauges."""
+    import numpy as np
+
+    from bspatom_b200 import postproc as pp
+    from oracle import oracle as O
+    from oracle import postproc_oracle as po
+
+    b = O.make_basis(kind_grid=0, k=7, nfun=60, rb=40.0)
+    m = O.matrix_svt(b, lmax=1)
+    E0v, C0 = O.solve_system(m, 0)
+    E1v, C1 = O.solve_system(m, 1)
+    Enl = np.stack([E0v, E1v], axis=1)
+    for kind_pi in (1, 2):
+        sel = pp.select_states(Enl, kind_pi, 0, 1, 1.5)
+        assert 1 <= sel.n0_fin <= sel.n1_fin < b.nfun
+        ops = (m["R"], None) if kind_pi == 1 else (m["Ri"], m["D"])
+        c0, c1, c2 = pp.dipole_angular_factors(kind_pi, 0, 0, 1, 0, 0)
+        A = c1 * ops[0] + (c2 * ops[1] if ops[1] is not None else 0.0)
+        D = C1.T @ (A @ C0[:, 0])                                   # what bspatom_dipole returns, column n0 = 1
+        T = pp.trans_amp_dipole(D, sel.E_fin, sel.n0_fin, sel.n1_fin, c0)
+        Ef, sig = pp.cross_sections_dipole(kind_pi, float(sel.E_ini[0]), sel.E_fin, T, sel.n0_fin, sel.n1_fin, 0)
+        rEf, rT, rsig = po.photoion_dipole_ref(kind_pi, [o.tolist() if o is not None else None for o in ops],
+                                               C0[:, 0].tolist(), C1.tolist(), float(sel.E_ini[0]), sel.E_fin.tolist(),
+                                               sel.n0_fin, sel.n1_fin, 0, 0, 1, 0, 0)
+        assert np.array_equal(Ef, np.array(rEf))
+        assert np.allclose(T, rT, rtol=1e-11, atol=1e-13 * np.abs(rT).max())
+        assert np.allclose(sig, rsig, rtol=1e-11, atol=1e-13 * np.abs(rsig).max())
+        assert np.all(sig >= 0.0) and sig.max() > 0.0
+        path = tmp_path / ("cs%d.dat" % kind_pi)
+        pp.write_cross_section(str(path), Ef, sig)
+        lines = path.read_text().splitlines()
+        assert len(lines) == len(Ef) and all(len(ln) == 40 for ln in lines)
+        back = np.array([[float(x) for x in ln.split()] for ln in lines])
+        assert np.allclose(back[:, 0], Ef, rtol=1e-9) and np.allclose(back[:, 1], sig, rtol=1e-9)
+
+
+def test_g20_10e3_edit_descriptor():
+    from bspatom_b200.postproc import fortran_g_e3
+
+    assert fortran_g_e3(1.0, 20, 10) == "    1.000000000     "
+    assert fortran_g_e3(0.0, 20, 10) == "    0.000000000     "
+    assert fortran_g_e3(-123.456, 20, 10) == "   -123.4560000     "
+    assert fortran_g_e3(1.5e-7, 20, 10) == "   0.1500000000E-006"
+    assert fortran_g_e3(-2.5e123, 20, 10) == "  -0.2500000000E+124"
+    assert all(len(fortran_g_e3(v, 20, 10)) == 20 for v in (3.14159, 1e10, 9.9999999999e9, 0.1, 0.0999))
