@@ -265,3 +265,42 @@ def write_cross_section(path: str, Ef: np.ndarray, sigma: np.ndarray) -> None:
     with open(path, "w") as fh:
         for e, s in zip(Ef, sigma):
             fh.write(fortran_g_e3(float(e), 20, 10) + fortran_g_e3(float(s), 20, 10) + "\n")
+
+
+# ---- CUBSPL (CubicSpline.f90): the interpolation the cross-section stage uses -------------------------
+def cubspl(x0: np.ndarray, y0: np.ndarray, x1: np.ndarray) -> np.ndarray:
+    """y1 = CUBSPL(x0, y0, x1) (CubicSpline.f90:1-51): clamped cubic spline through (x0, y0) with end slopes
+    from the first / last pair of points (SPLINE, :55-99), evaluated at x1 (SPLINT, :103-131).
+    Kept from the reference: SPLINT starts its bisection at klo = 1 on arrays indexed from 0, so abscissae
+    inside the FIRST interval are extrapolated from the second one; x1 equal to an end point returns the
+    tabulated value."""
+    x = np.asarray(x0, dtype=np.float64)
+    y = np.asarray(y0, dtype=np.float64)
+    n = x.size - 1
+    yp1 = (y[1] - y[0]) / (x[1] - x[0])
+    ypn = (y[n] - y[n - 1]) / (x[n] - x[n - 1])
+    y2 = np.zeros(n + 1)
+    u = np.zeros(n + 1)
+    y2[0] = -0.5
+    u[0] = (3.0 / (x[1] - x[0])) * ((y[1] - y[0]) / (x[1] - x[0]) - yp1)
+    for i in range(1, n):
+        sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1])
+        p = sig * y2[i - 1] + 2.0
+        y2[i] = (sig - 1.0) / p
+        u[i] = (6.0 * ((y[i + 1] - y[i]) / (x[i + 1] - x[i]) - (y[i] - y[i - 1]) / (x[i] - x[i - 1]))
+                / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / p
+    qn = 0.5
+    un = (3.0 / (x[n] - x[n - 1])) * (ypn - (y[n] - y[n - 1]) / (x[n] - x[n - 1]))
+    y2[n] = (un - qn * u[n - 1]) / (qn * y2[n - 1] + 1.0)
+    for k in range(n - 1, -1, -1):
+        y2[k] = y2[k] * y2[k + 1] + u[k]
+    xi = np.asarray(x1, dtype=np.float64)
+    # bisection of SPLINT: klo = last k in 1..n-1 with x(k) <= xi, or 1; khi = klo + 1
+    klo = np.maximum(np.searchsorted(x[1:n], xi, side="right"), 1)
+    khi = klo + 1
+    h = x[khi] - x[klo]
+    a = (x[khi] - xi) / h
+    b = (xi - x[klo]) / h
+    out = a * y[klo] + b * y[khi] + ((a ** 3 - a) * y2[klo] + (b ** 3 - b) * y2[khi]) * (h ** 2) / 6.0
+    out = np.where(xi == x[0], y[0], np.where(xi == x[n], y[n], out))
+    return out

@@ -208,3 +208,54 @@ def photoion_dipole_ref(kind_pi, A, ci_ini, ci_fin, E_ini_n0, E_fin, n0_fin, n1_
         T.append(t)
         sig.append(M_au * cc0 * cc1 * d1 * t * t)
     return Ef, T, sig
+
+
+def cubspl_ref(x0, y0, x1):
+    """CUBSPL / SPLINE / SPLINT (CubicSpline.f90) statement by statement; arrays indexed from 0 as in the
+    reference (x0(0:n0)), including SPLINT's `klo = 1`."""
+    n = len(x0) - 1
+    x, y = [float(v) for v in x0], [float(v) for v in y0]
+    yp1 = (y[1] - y[0]) / (x[1] - x[0])                       # :18
+    ypn = (y[n] - y[n - 1]) / (x[n] - x[n - 1])               # :19
+    y2 = [0.0] * (n + 1)
+    u = [0.0] * (n + 1)
+    if yp1 > 0.99e30:                                          # :68
+        y2[0] = 0.0
+        u[0] = 0.0
+    else:
+        y2[0] = -0.5
+        u[0] = (3.0 / (x[1] - x[0])) * ((y[1] - y[0]) / (x[1] - x[0]) - yp1)
+    for i in range(1, n):                                      # :77
+        sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1])
+        p = sig * y2[i - 1] + 2.0
+        y2[i] = (sig - 1.0) / p
+        u[i] = (6.0 * ((y[i + 1] - y[i]) / (x[i + 1] - x[i]) - (y[i] - y[i - 1]) / (x[i] - x[i - 1]))
+                / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / p
+    if ypn > 0.99e30:                                          # :85
+        qn = un = 0.0
+    else:
+        qn = 0.5
+        un = (3.0 / (x[n] - x[n - 1])) * (ypn - (y[n] - y[n - 1]) / (x[n] - x[n - 1]))
+    y2[n] = (un - qn * u[n - 1]) / (qn * y2[n - 1] + 1.0)      # :94
+    for k in range(n - 1, -1, -1):                             # :96
+        y2[k] = y2[k] * y2[k + 1] + u[k]
+    out = []
+    for xi in x1:                                              # :36
+        xi = float(xi)
+        if xi == x[0]:
+            out.append(y[0])
+        elif xi == x[n]:
+            out.append(y[n])
+        else:
+            klo, khi = 1, n                                    # :113
+            while khi - klo > 1:
+                k = (khi + klo) // 2
+                if x[k] > xi:
+                    khi = k
+                else:
+                    klo = k
+            h = x[khi] - x[klo]
+            a = (x[khi] - xi) / h
+            b = (xi - x[klo]) / h
+            out.append(a * y[klo] + b * y[khi] + ((a ** 3 - a) * y2[klo] + (b ** 3 - b) * y2[khi]) * (h ** 2) / 6.0)
+    return out

@@ -182,3 +182,32 @@ def test_g20_10e3_edit_descriptor():
     assert fortran_g_e3(1.5e-7, 20, 10) == "   0.1500000000E-006"
     assert fortran_g_e3(-2.5e123, 20, 10) == "  -0.2500000000E+124"
     assert all(len(fortran_g_e3(v, 20, 10)) == 20 for v in (3.14159, 1e10, 9.9999999999e9, 0.1, 0.0999))
+
+
+def test_cubspl_matches_the_statement_by_statement_restatement():
+    """CUBSPL (CubicSpline.f90): vectorised host version vs the literal restatement, bit for bit on the same
+    operations order; cubic reproduction away from the first interval; the klo = 1 quirk of SPLINT."""
+    import numpy as np
+
+    from bspatom_b200.postproc import cubspl
+    from oracle.postproc_oracle import cubspl_ref
+
+    rng = np.random.default_rng(3)
+    x0 = np.cumsum(rng.uniform(0.05, 0.4, 41))
+    y0 = np.sin(1.3 * x0) * np.exp(-0.1 * x0)
+    x1 = np.concatenate(([x0[0], x0[-1], x0[7]], rng.uniform(x0[0], x0[-1], 200)))
+    got = cubspl(x0, y0, x1)
+    ref = np.array(cubspl_ref(x0, y0, x1))
+    assert np.allclose(got, ref, rtol=0, atol=1e-15 * np.abs(ref).max())
+    assert got[0] == y0[0] and got[1] == y0[-1] and abs(got[2] - y0[7]) < 1e-15
+    inner = x1 > x0[1]
+    assert np.max(np.abs(got[inner] - np.sin(1.3 * x1[inner]) * np.exp(-0.1 * x1[inner]))) < 5e-3
+    # a straight line is reproduced everywhere, including the extrapolated first interval
+    xl = np.linspace(0.0, 2.0, 11)
+    assert np.allclose(cubspl(xl, 3.0 * xl - 1.0, np.array([0.05, 0.15, 1.234])), 3.0 * np.array([0.05, 0.15, 1.234]) - 1.0,
+                       atol=1e-13)
+    # the quirk: inside the first interval the second interval's cubic is used (differs from a proper spline)
+    xq = np.array([0.0, 1.0, 2.0, 3.0, 4.0])
+    yq = np.array([0.0, 1.0, 0.0, 1.0, 0.0])
+    v = cubspl(xq, yq, np.array([0.5]))[0]
+    assert abs(v - cubspl_ref(xq, yq, [0.5])[0]) < 1e-15
