@@ -483,3 +483,88 @@ void bsp_dipole_dots(int n, const double *A, const double *x, int nfin,
     }
     free(v);
 }
+
+/* ------------------------------------------------------------------------- *
+ * Third comparator ("a third, independent comparator at N=1000"):
+ * eigenvalues of the symmetric banded pencil H c = E S c by Sturm bisection in
+ * EXTENDED precision (x87 long double, eps = 1.1e-19), straight on the band --
+ * no reduction to standard or tridiagonal form, hence none of the eps*|E_max|
+ * backward error DSYGV (matrices.f90:248: dpotrf/dsygst/dsytrd/dsteqr) carries.
+ * nu(sigma) = number of negative pivots of the banded LDL^T of H - sigma S
+ * (Sylvester's law of inertia, S positive definite) = number of eigenvalues
+ * below sigma.  The result is the spectrum of the pencil *as stored in double*
+ * to about 1e-18 |E_max|, the same definition as the 40-digit table of
+ * tests/golden/make_golden.py, at sizes where mpmath takes hours.
+ *
+ * hb, sb: lower bands, hb[d*n + i] = H(i+d, i), d = 0..kd  (row-major (kd+1, n)).
+ * idx[0..nidx): 0-based eigenvalue indices wanted; lo_hint/hi_hint (may be NULL):
+ * a guess of a bracket per index (verified with two counts, widened if wrong).
+ * ------------------------------------------------------------------------- */
+static int band_count_ld(int n, int kd, const double *hb, const double *sb, long double sigma, long double pivmin)
+{
+    /* window w[r][c], r >= c: Schur complement of rows j..j+kd */
+    long double w[ORACLE_MAXK][ORACLE_MAXK];
+    int cnt = 0;
+    for (int r = 0; r <= kd; ++r)
+        for (int c = 0; c <= r; ++c) {
+            /* entry (row r, col c), r - c = d */
+            const int d = r - c;
+            w[r][c] = (r < n) ? (long double)hb[(size_t)d * n + c] - sigma * (long double)sb[(size_t)d * n + c] : (r == c ? 1.0L : 0.0L);
+        }
+    for (int j = 0; j < n; ++j) {
+        long double d = w[0][0];
+        if (fabsl(d) < pivmin) d = -pivmin;
+        if (d < 0.0L) ++cnt;
+        long double l[ORACLE_MAXK], col0[ORACLE_MAXK];
+        for (int i = 1; i <= kd; ++i) { col0[i] = w[i][0]; l[i] = col0[i] / d; }
+        /* eliminate row/col j, shift the window up-left by one */
+        for (int r = 1; r <= kd; ++r)
+            for (int c = 1; c <= r; ++c) w[r - 1][c - 1] = w[r][c] - l[r] * col0[c];
+        /* new last row: row j+kd+1 of the band, columns j+1 .. j+kd+1 */
+        const int rn = j + kd + 1;
+        for (int c = 0; c <= kd; ++c) {
+            const int col = j + 1 + c, dd = rn - col;
+            if (rn < n) w[kd][c] = (long double)hb[(size_t)dd * n + col] - sigma * (long double)sb[(size_t)dd * n + col];
+            else w[kd][c] = (c == kd) ? 1.0L : 0.0L;
+        }
+    }
+    return cnt;
+}
+
+int bsp_band_bisect_ld(int n, int kd, const double *hb, const double *sb, int nidx, const int *idx,
+                       const double *lo_hint, const double *hi_hint, double *out)
+{
+    if (kd + 1 > ORACLE_MAXK) return -1;
+    long double hmax = 0.0L, smax = 0.0L, s0 = 0.0L;
+    for (int i = 0; i < n; ++i) {
+        const long double h = fabsl((long double)hb[i]), s = (long double)sb[i];
+        if (h > hmax) hmax = h;
+        if (s > smax) smax = s;
+        if (s > 0.0L && h / s > s0) s0 = h / s;
+    }
+    if (!(s0 > 0.0L)) s0 = 1.0L;
+    /* global bounds by doubling */
+    long double glo = -s0, ghi = s0;
+    for (int t = 0; t < 80 && band_count_ld(n, kd, hb, sb, glo, 1e-4000L) > 0; ++t) glo *= 2.0L;
+    for (int t = 0; t < 80 && band_count_ld(n, kd, hb, sb, ghi, 1e-4000L) < n; ++t) ghi *= 2.0L;
+    for (int q = 0; q < nidx; ++q) {
+        const int e = idx[q];
+        if (e < 0 || e >= n) return -2;
+        long double lo = glo, hi = ghi;
+        if (lo_hint && hi_hint && lo_hint[q] < hi_hint[q]) {
+            const long double a = lo_hint[q], b = hi_hint[q];
+            if (band_count_ld(n, kd, hb, sb, a, 1e-4000L) <= e) lo = a;
+            if (band_count_ld(n, kd, hb, sb, b, 1e-4000L) > e) hi = b;
+        }
+        /* invariant: nu(lo) <= e < nu(hi) */
+        for (int it = 0; it < 200; ++it) {
+            const long double mid = 0.5L * (lo + hi);
+            if (!(mid > lo && mid < hi)) break;
+            if (hi - lo <= 1e-19L * (fabsl(lo) + fabsl(hi))) break;
+            const long double pm = 1e-4000L;
+            if (band_count_ld(n, kd, hb, sb, mid, pm) <= e) lo = mid; else hi = mid;
+        }
+        out[q] = (double)(0.5L * (lo + hi));
+    }
+    return 0;
+}

@@ -59,6 +59,8 @@ def lib():
         L.bsp_write_wf.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, _dp, C.c_int, _dp, _dp]
         L.bsp_write_wf.restype = C.c_int
         L.bsp_dipole_dots.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, _dp]
+        L.bsp_band_bisect_ld.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, _ip, _dp, _dp, _dp]
+        L.bsp_band_bisect_ld.restype = C.c_int
         _lib = L
     return _lib
 
@@ -215,6 +217,41 @@ def dsygv(H, S):
     w, v, info = lapack.dsygv(np.asfortranarray(H), np.asfortranarray(S), itype=1, jobz="V", uplo="U",
                               overwrite_a=False, overwrite_b=False)
     return w, v, info
+
+
+def lower_band(A, kd):
+    """row-major (kd+1, n) lower band: ab[d, i] = A[i+d, i]."""
+    n = A.shape[0]
+    ab = np.zeros((kd + 1, n))
+    for d in range(kd + 1):
+        ab[d, :n - d] = np.diagonal(A, -d)
+    return np.ascontiguousarray(ab)
+
+
+def band_bisect_truth(H, S, kd, idx=None, guess=None, rel_window=1e-6):
+    """Third comparator: eigenvalues of the banded pencil by Sturm bisection in x87 extended precision
+    straight on the band (no reduction, no eps*|E_max| floor; bsp_band_bisect_ld).  ``guess``: approximate
+    eigenvalues (e.g. dsygv's) used only to start the brackets -- every bracket is verified by two counts."""
+    n = H.shape[0]
+    hb, sb = lower_band(np.asarray(H), kd), lower_band(np.asarray(S), kd)
+    idx = np.arange(n, dtype=np.int32) if idx is None else np.ascontiguousarray(idx, dtype=np.int32)
+    out = np.zeros(len(idx))
+    lo = hi = None
+    if guess is not None:
+        g = np.asarray(guess, dtype=np.float64)[idx]
+        wdt = rel_window * np.maximum(np.abs(g), np.abs(np.asarray(guess)).max() * 1e-9) + 1e-12
+        lo, hi = np.ascontiguousarray(g - wdt), np.ascontiguousarray(g + wdt)
+    rc = lib().bsp_band_bisect_ld(n, kd, _p(hb), _p(sb), len(idx), idx.ctypes.data_as(_ip), _p(lo), _p(hi), _p(out))
+    if rc:
+        raise ValueError("bsp_band_bisect_ld rc=%d" % rc)
+    return out
+
+
+def dsygvx(H, S):
+    """LAPACK's own bisection driver (dsygvx: dstebz + dstein after the dense reduction), all eigenvalues."""
+    from scipy.linalg import eigh
+
+    return eigh(np.asarray(H), np.asarray(S), eigvals_only=True, driver="gvx")
 
 
 def solve_system(m, l):

@@ -149,3 +149,27 @@ def test_trans_amp_hermitian_block_matches_zhvmv(atom, oracle):
     for f, i in ((0, 0), (5, 17), (36, 49)):
         z = po.zhvmv(zA, Ci[:, i].astype(np.complex128), Cf[:, f].astype(np.complex128))
         assert abs(T[f, i] - z) < 1e-12 * scale[f, i]
+
+
+@pytest.mark.parametrize("l0", [0, 49])
+def test_cfg5_full_size_n1000_against_oracle_loop(atom, oracle, l0):
+    """BASELINE cfg5 at full size: D = C_{l0+1}^T R C_{l0} for ALL 1000 x 1000 state pairs of the N=1000 spectra,
+    GPU eigenvectors in, against the oracle's literal DGEMV + DDOT loop (PhotoIon.f90:90-105) on the same
+    vectors; bar 1e-12 relative to |row| |col|."""
+    a = host_basis(kind_grid=0, k=7, nfun=1000, rb=500.0)
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=1000, rb=500.0)
+    m = oracle.matrix_svt(b, lmax=0, want_u=False)
+    Es, Cs, info = atom.solve_batch([(a.problem(), l0), (a.problem(), l0 + 1)])
+    assert not info.any()
+    Ci, Cf = np.asarray(Cs[0]), np.asarray(Cs[1])
+    D = atom.dipole(general_band(m["R"], 6), Cf, Ci)
+    assert D.shape == (1000, 1000)
+    RCi = m["R"] @ Ci
+    scale = np.linalg.norm(Cf, axis=0)[:, None] * np.linalg.norm(RCi, axis=0)[None, :]
+    worst = 0.0
+    for j in range(1000):
+        ref = oracle.dipole_dots(m["R"], Ci[:, j], Cf)
+        worst = max(worst, float(np.max(np.abs(D[:, j] - ref) / scale[:, j])))
+    assert worst < 1e-12, worst
+    if l0 == 0:   # <2p|r|1s> of hydrogen = 128 sqrt(6) / 243 (basis-limited at h = 0.5)
+        assert abs(abs(D[0, 0]) - 128 * np.sqrt(6) / 243) < 1e-5

@@ -120,6 +120,25 @@ def test_golden_spectrum_shipped_input(oracle):
         assert np.abs(v.T @ m["S"] @ v - np.eye(b.nfun)).max() < 1e-12     # C^T S C = I (ITYPE=1)
 
 
+def test_extended_precision_bisection_is_pinned_to_the_40_digit_table(oracle):
+    """The third comparator used by the strict GPU parity tests (oracle.band_bisect_truth: Sturm bisection on
+    the band in x87 extended precision) reproduces the mpmath spectrum of the shipped input to double rounding,
+    for every level of l = 0, 1, 2; LAPACK's own bisection driver dsygvx is inside the strict north-star bar too."""
+    gold = json.load(open(os.path.join(GOLD, "shipped_truth.json")))
+    b = oracle.shipped_basis()
+    m = oracle.matrix_svt(b, lmax=2)
+    for l in range(3):
+        truth = np.array([float(s) for s in gold["levels"][str(l)]])
+        H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+        w = oracle.band_bisect_truth(H, m["S"], b.k - 1)
+        assert np.max(np.abs(w - truth) / np.abs(truth)) < 2e-15
+        wd, _, _ = oracle.dsygv(H, m["S"])
+        w2 = oracle.band_bisect_truth(H, m["S"], b.k - 1, idx=[0, 7, 123], guess=wd)     # hinted brackets, subset
+        assert np.array_equal(w2, w[[0, 7, 123]])
+        strict = np.maximum(1e-12 * np.abs(truth), 1e-10)
+        assert np.all(np.abs(oracle.dsygvx(H, m["S"]) - truth) <= strict)
+
+
 def test_golden_band_fixture(oracle):
     z = np.load(os.path.join(GOLD, "shipped_band.npz"))
     b = oracle.shipped_basis()
@@ -162,3 +181,28 @@ def test_write_wf_and_dipole_restatements(oracle):
     assert np.allclose(out, v1[:, :5].T @ (m["R"] @ v0[:, 0]), rtol=1e-12, atol=1e-14)
     # <2p|r|1s> = 128 sqrt(6)/243 = 1.2902663...
     assert abs(abs(out[0]) - 128 * np.sqrt(6) / 243) < 1e-6
+
+
+def test_reference_enl_dat_if_built(oracle, tmp_path):
+    """When oracle/_ref/Bsp_Atom_ref.x exists (oracle/build_ref.sh: needs gfortran + LAPACK, absent from the build
+    image and from the pool's GPU boxes), run the REAL reference on the shipped input and pin the oracle
+    restatement to its Enl.dat (matrices.f90:239-265: `nfun`, then `i, En(i)` for l = 0..lmax)."""
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "Bsp_Atom_ref.x")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built: no Fortran compiler here (oracle/build_ref.sh exits 3)")
+    inp = open(os.path.join(GOLD, "cfg1_shipped.inp")).read()
+    subprocess.run([os.path.abspath(exe)], input=inp, text=True, cwd=tmp_path, check=True, timeout=600,
+                   capture_output=True)
+    toks = open(tmp_path / "Enl.dat").read().replace("D", "E").split()
+    nfun = int(toks[0])
+    vals = np.array([float(t) for t in toks[2::2]]).reshape(-1, nfun)      # (lmax+1, nfun)
+    b = oracle.shipped_basis()
+    assert nfun == b.nfun and vals.shape[0] == 3
+    m = oracle.matrix_svt(b, lmax=2)
+    eps = np.finfo(float).eps
+    for l in range(3):
+        w, _ = oracle.solve_system(m, l)
+        # two LAPACK builds (MKL/reference LAPACK there, OpenBLAS here) agree within dsygv's backward error
+        assert np.max(np.abs(vals[l] - w)) <= 64 * eps * np.abs(w).max() + 1e-13 * np.abs(w).max()
