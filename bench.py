@@ -179,7 +179,6 @@ def main():
     ap.add_argument("--zrep", type=int, default=ZREP_DEFAULT, help="nuclear charges per GPU per step")
     ap.add_argument("--ref-ls", type=int, default=3, help="l values per reference step")
     ap.add_argument("--workers", type=int, default=0, help="chunk streams (0 = library default)")
-    ap.add_argument("--recompute", type=int, default=-1, help="1/0: check-pointed vs stored-factor refinement (-1 = library default)")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (experiments), repeatable")
     ap.add_argument("--no-numa", action="store_true", help="do not bind host memory / CPU affinity to the GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -217,8 +216,6 @@ def main():
     atom = bsp.BspAtom(device=local)
     if args.workers:
         atom.set_option("workers", args.workers)
-    if args.recompute >= 0:
-        atom.set_option("recompute", args.recompute)
     for kv in args.opt:
         atom.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     inp, items = workload_items(bsp, rank, args.zrep, args.grid)
@@ -247,7 +244,7 @@ def main():
         kms += [st["ms_k_round"], st["ms_k_factor"], st["ms_k_back"], st["ms_k_assembly"]]
         kcnt += [st["n_k_round"], st["n_k_factor"], st["n_k_back"], st["n_k_assembly"]]
         stage_ms += [st["ms_assembly"], st["ms_eigenvalues"], st["ms_eigenvectors"], st["ms_finalize"]]
-        gaps.append((st["ms_total"], st["ms_gap_before_chunk"], st["ms_gap_after_last_chunk"]))
+        gaps.append(st["ms_total"])
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     sampler.stop_flag = True
@@ -468,7 +465,7 @@ def main():
             "stage_ms_per_step": dict(zip(("assembly", "eigenvalues", "eigenvectors", "finalize"),
                                           (stage_ms / args.steps).tolist())),
             "rounds": int(last_stats["rounds"]), "iters": int(last_stats["iters"]),
-            "per_step_total_gap_pre_post_ms": gaps,
+            "ms_each_step": gaps, "selected_third_solve_per_step": int(last_stats["selected_third_solve"]),
             "wall_ms_per_step": wall_ms_max / args.steps,
         }
         print(json.dumps(line))

@@ -19,7 +19,7 @@ EXPORTS = [
     "bspatom_create", "bspatom_destroy", "bspatom_last_error", "bspatom_version", "bspatom_set_option",
     "bspatom_alloc_host", "bspatom_free_host",
     "bspatom_assemble_band", "bspatom_solve_batch", "bspatom_batch_upload", "bspatom_batch_run",
-    "bspatom_batch_download", "bspatom_dsygv_", "bspatom_dipole", "bspatom_dipole_chain", "bspatom_trans_amp_hermitian",
+    "bspatom_batch_download", "bspatom_batch_verify", "bspatom_dsygv_", "bspatom_dipole", "bspatom_dipole_chain", "bspatom_trans_amp_hermitian",
     "bspatom_wavefunction", "bspatom_get_stats",
 ]
 
@@ -68,6 +68,7 @@ def load():
     L.bspatom_batch_upload.argtypes = [H, C.c_int, C.POINTER(BspProblem)]
     L.bspatom_batch_run.argtypes = [H]
     L.bspatom_batch_download.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bspatom_batch_verify.argtypes = [H, _dp]
     L.bspatom_dsygv_.argtypes = [_ip, C.c_char_p, C.c_char_p, _ip, C.c_void_p, _ip, C.c_void_p, _ip,
                                  C.c_void_p, C.c_void_p, _ip, _ip]
     L.bspatom_dsygv_.restype = None

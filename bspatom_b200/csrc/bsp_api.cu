@@ -40,7 +40,8 @@ struct Options {
     double res_tol = 1e-9;
     int max_rounds = 90;      /* cap used when a chunk has to be redone */
     int rounds_enqueued = 26; /* bracketing rounds enqueued up front (surplus ones return at once) */
-    int min_iters = 3;
+    double vec_tol = 1e-12;   /* ||r||_2 / gap above which an eigenpair gets the correction pass after its second solve */
+    int min_iters = 2;        /* solves every eigenpair gets (3 = round-1 schedule: everybody gets the correction pass) */
     int trace = 0;        /* diagnostics: print the chunk / copy timeline of every run to stderr */
     int max_iters = 12;
     int chunk = 0; /* 0 = auto */
@@ -50,8 +51,6 @@ struct Options {
 #define BSP_MAX_STREAMS 8
 #define BSP_MAIL_INTS (1 << 18)
 #define BSP_MAIL_REPORT_INTS (1 << 14)
-    int recompute = 0; /* 1: check-pointed refinement (re-eliminate in the back sweep; measured slower, see
-                          DESIGN.md section 12), 0: store the factor */
 };
 
 struct Group {
@@ -391,15 +390,13 @@ struct GpuExec {
     void factor(int it, int optional) {
         cur_iter = it;
         const int s = timed_begin(h, 1);
-        if (h->opt.recompute) bsp_factor_ckpt_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional);
-        else bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional);
+        bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional);
         note();
         timed_end(h, s);
     }
-    void back(int cn, int cx, int optional) {
+    void back(int it, int cn, int cx, int optional) {
         const int s = timed_begin(h, 2);
-        if (h->opt.recompute) bsp_back_rc_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx, cur_iter, optional);
-        else bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, cn, cx, optional);
+        bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, cn, cx, optional);
         note();
         timed_end(h, s);
     }
@@ -408,7 +405,7 @@ struct GpuExec {
         bsp_resid_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g); note();
         timed_end(h, s);
     }
-    void check(int it) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it); note(); }
+    void check(int it, int select) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, select); note(); }
 };
 
 struct ChunkTimes {
@@ -429,11 +426,11 @@ struct Carver {
 
 struct ChunkPtrs {
     double *fbH, *pbound, *lo, *hi, *samp_s, *gap, *sigma, *rho, *rho_prev, *scale, *res, *L, *X, *R, *cand_s, *fac;
-    double *samp_fm, *flm, *fhm, *beta, *xmax;
-    int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c, *samp_fe, *fle, *fhe, *side, *olist, *ocount;
+    double *samp_fm, *flm, *fhm, *beta, *xmax, *res2;
+    int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c, *samp_fe, *fle, *fhe, *side, *olist, *ocount, *rlist, *rcount;
 };
 
-size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c, bool recompute = false)
+size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
 {
     Carver cv{base};
     const size_t per = (size_t)np * G.ldw;
@@ -448,13 +445,13 @@ size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c, bool recomp
     c.gap = cv.take<double>(per); c.done = cv.take<int>(per);
     c.sigma = cv.take<double>(per); c.rho = cv.take<double>(per); c.rho_prev = cv.take<double>(per);
     c.scale = cv.take<double>(per); c.res = cv.take<double>(per); c.status = cv.take<int>(per);
-    c.xmax = cv.take<double>(per);
+    c.xmax = cv.take<double>(per); c.res2 = cv.take<double>(per);
     c.fac = cv.take<double>(per);
     c.counters = cv.take<int>(64);
     c.olist = cv.take<int>(2 * per); c.ocount = cv.take<int>(4 * (size_t)np);
+    c.rlist = cv.take<int>(2 * per); c.rcount = cv.take<int>(2 * (size_t)np);
     c.cand_s = cv.take<double>((size_t)np * BSP_NCAND); c.cand_c = cv.take<int>((size_t)np * BSP_NCAND);
-    c.L = recompute ? cv.take<double>((size_t)np * (G.npad / BSP_SEG_STEPS(G.B)) * BSP_CK_DOUBLES(G.B) * G.ldw)
-                    : cv.take<double>((size_t)np * G.npad * (G.B + 1) * G.ldw);
+    c.L = cv.take<double>((size_t)np * G.npad * (G.B + 1) * G.ldw);
     c.X = cv.take<double>((size_t)np * G.xrows * G.ldw);
     c.R = cv.take<double>((size_t)np * G.xrows * G.ldw);
     return cv.used;
@@ -483,8 +480,8 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     g.samp_fm = c.samp_fm; g.samp_fe = c.samp_fe; g.flm = c.flm; g.fhm = c.fhm; g.fle = c.fle; g.fhe = c.fhe; g.side = c.side; g.beta = c.beta;
     g.sigma = c.sigma; g.rho = c.rho; g.rho_prev = c.rho_prev; g.scale = c.scale; g.res = c.res; g.xmax = c.xmax;
     g.status = c.status; g.L = c.L; g.X = c.X; g.R = c.R; g.counters = c.counters;
-    g.olist = c.olist; g.ocount = c.ocount;
-    g.tau = h->opt.tau; g.delta_rel = h->opt.delta_rel; g.conv_tol = h->opt.conv_tol;
+    g.olist = c.olist; g.ocount = c.ocount; g.res2 = c.res2; g.rlist = c.rlist; g.rcount = c.rcount;
+    g.tau = h->opt.tau; g.delta_rel = h->opt.delta_rel; g.conv_tol = h->opt.conv_tol; g.vec_tol = h->opt.vec_tol;
 
     GpuExec<B> ex;
     ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.ev_refine = tm.ev[1];
@@ -493,6 +490,7 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     bsp_zero_words_kernel<<<1, 32, 0, h->st>>>(c.counters, BSP_C_WORDS);
     h->launches++;
     CU(cudaMemsetAsync(c.ocount, 0, sizeof(int) * 4 * (size_t)np, h->st));
+    CU(cudaMemsetAsync(c.rcount, 0, sizeof(int) * 2 * (size_t)np, h->st));
     bsp_enqueue_chunk(ex, sch);
     if (ex.first_err != cudaSuccess) {
         h->err = std::string("eigen stage: ") + cudaGetErrorString(ex.first_err);
@@ -688,7 +686,7 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "rounds_enqueued") h->opt.rounds_enqueued = std::max(1, (int)v);
     else if (s == "first_check_round" || s == "check_every") { /* accepted and ignored: the schedule is static */ }
     else if (s == "chunk") h->opt.chunk = (int)v;
-    else if (s == "recompute") { h->opt.recompute = v != 0.0; h->budget_bytes = 0; }
+    else if (s == "vec_tol") h->opt.vec_tol = v;
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
     else if (s == "stream_workers") h->opt.stream_workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
     else if (s == "workers") h->opt.workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
@@ -955,6 +953,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     h->chunk_done.clear();
     double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0;
     int rounds = 0, iters = 0, redone = 0;
+    long long selected = 0;
     cudaEvent_t e0, e1, e2, copies_done;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
     CU(cudaEventCreateWithFlags(&copies_done, cudaEventDisableTiming));
@@ -968,7 +967,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     if (cq) CU(cudaEventRecord(copies_done, cq->st));
     CU(cudaEventRecord(e0, h->st));
     const BspSchedule sch = {std::min(h->opt.rounds_enqueued, h->opt.max_rounds), h->opt.min_iters,
-                             std::min(h->opt.max_iters, h->opt.min_iters + 2)};
+                             std::min(h->opt.max_iters, h->opt.min_iters + 3)};
     const BspSchedule sch_redo = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters};
     for (auto &G : h->groups) {
         /* ---- assembly, once per instance ---- */
@@ -993,7 +992,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         CU(cudaEventRecord(pd_done, h->st_copy));
         /* ---- chunking ---- */
         ChunkPtrs c;
-        const size_t per_pencil = carve_chunk(G, 1, nullptr, c, h->opt.recompute != 0);
+        const size_t per_pencil = carve_chunk(G, 1, nullptr, c);
         const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
         const int fill_pencils = std::max(1, (148 * 4 + blocks_per_pencil - 1) / blocks_per_pencil); /* one full wave */
         const bool streaming = (E_out || C_out);
@@ -1051,7 +1050,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             for (int i = 0; i < nchunks; ++i) chunk = std::max(chunk, bounds[i + 1] - bounds[i]);
         }
         workers = std::min(workers, nchunks);
-        const size_t need = carve_chunk(G, chunk, nullptr, c, h->opt.recompute != 0);
+        const size_t need = carve_chunk(G, chunk, nullptr, c);
         if ((rc = ensure_workspace(h, need))) return rc;
         while ((int)h->aux.size() < workers - 1) {
             bspatom_handle x = new_context(h->dev);
@@ -1086,7 +1085,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             load[wsel] += bounds[ci + 1] - bounds[ci];
             bspatom_handle x = ctx[wsel];
             ChunkPtrs cc;
-            carve_chunk(G, chunk, x->ws.base, cc, h->opt.recompute != 0);
+            carve_chunk(G, chunk, x->ws.base, cc);
             const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
             if ((rc = enqueue_chunk(x, G, p0, np, cc, sch, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) {
                 if (x != h) h->err = x->err;
@@ -1143,7 +1142,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             if (again) {
                 ++redone;
                 ChunkPtrs cc;
-                carve_chunk(G, chunk, h->ws.base, cc, h->opt.recompute != 0);
+                carve_chunk(G, chunk, h->ws.base, cc);
                 const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
                 CU(cudaMemsetAsync(G.d_bad + p0, 0, sizeof(int) * np, h->st));
                 if ((rc = enqueue_chunk(h, G, p0, np, cc, sch_redo, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) return rc;
@@ -1160,6 +1159,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             }
             rounds = std::max(rounds, st.rounds);
             iters = std::max(iters, st.iters);
+            selected += report[(size_t)ci * BSP_C_WORDS + BSP_C_SELECTED];
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, tms[ci].ev[0], tms[ci].ev[1])); t_val += ms;
             CU(cudaEventElapsedTime(&ms, tms[ci].ev[1], tms[ci].ev[2])); t_vec += ms;
@@ -1209,7 +1209,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         h->stats[12 + i] = (double)h->k_cnt[i];
         for (auto x : h->aux) { h->stats[8 + i] += x->k_ms[i]; h->stats[12 + i] += (double)x->k_cnt[i]; }
     }
-    h->stats[19] = redone; h->stats[20] = 0;
+    h->stats[19] = redone; h->stats[20] = (double)selected;
     h->ran = true;
     return 0;
 }

@@ -12,17 +12,19 @@
  *   void bounds();                            // bracket [lo0,hi0] per pencil
  *   void round(int r, int max_rounds);        // one bracketing round + its bookkeeping
  *   void prepare();                           // hand brackets to the refinement
- *   void factor(int iter, int optional);      // F pass (optional: skipped once everything converged)
- *   void back(int corr_now, int corr_next, int optional);
+ *   void factor(int iter, int optional);      // F pass (optional: compacted to the eigenpairs the last check listed,
+ *                                             //         skipped once everything converged)
+ *   void back(int iter, int corr_now, int corr_next, int optional);
  *   void resid();                             // residual of the current vectors against their own Rayleigh quotient
- *   void check(int iter);                     // convergence marks + bookkeeping
+ *   void check(int iter, int select);         // convergence marks, compaction list of what is left, bookkeeping
  */
 #ifndef BSP_DRIVER_H
 #define BSP_DRIVER_H
 
 struct BspSchedule {
     int rounds;     /* bracketing rounds enqueued (the flag makes surplus ones free)       */
-    int min_iters;  /* refinement iterations always done (>= 2: the two plain solves; default 3) */
+    int min_iters;  /* solves every eigenpair gets (2: default, a third only where the residual / gap test asks
+                       for it; 3: the round-1 schedule, everybody gets the correction pass) */
     int max_iters;  /* iterations enqueued; those beyond min_iters only touch stragglers   */
 };
 
@@ -40,18 +42,21 @@ inline void bsp_enqueue_chunk(Exec &ex, const BspSchedule &sch)
     ex.bounds();
     for (int r = 0; r < sch.rounds; ++r) ex.round(r, sch.rounds);
     ex.prepare();
-    /* iteration t: plain for t < 2, residual-correction form afterwards.  The default schedule always does
-     * the first correction step (min_iters = 3): it is what brings the S-orthogonality of neighbouring
-     * vectors from ~1e-8 to ~1e-12.  With min_iters = 2 ("fast" setting) the check may retire eigenpairs
-     * after the second plain solve; a plain pass only knows its residual against the PREVIOUS Rayleigh
-     * quotient, so one cheap residual pass (no factor traffic) evaluates (H - rho S) x with the current one
-     * first, and the correction iterations then only touch what is left. */
+    /* iteration t: plain for t < 2 (inverse iteration at the bracket midpoint, then at the Rayleigh quotient),
+     * residual-correction form afterwards.  Default (min_iters = 2): after the second solve one cheap residual pass
+     * (no factor traffic) evaluates r = (H - rho S) x with the CURRENT Rayleigh quotient -- a solving pass only knows
+     * its residual against the previous one -- and the check keeps in the iteration what misses conv_tol or has
+     * ||r||_2 / gap > vec_tol (bsp_check_converged): 10-17 % of the eigenpairs of the N = 1000 pencils.  The passes
+     * from there on are COMPACTED to that list (bsp_listed_index), so the correction pass that brings the
+     * S-orthogonality of neighbouring vectors from ~1e-8 to ~1e-12 costs what its eigenpairs cost. */
+    const bool select = sch.min_iters <= 2;
     for (int t = 0; t < sch.max_iters; ++t) {
         const int optional = (t >= sch.min_iters);
+        const bool resid_follows = (t == 1 && select);
         ex.factor(t, optional);
-        ex.back(t >= 2, t + 1 >= 2, optional);
-        if (t == 1 && sch.min_iters <= 2) ex.resid();
-        if (t + 1 >= sch.min_iters) ex.check(t);
+        ex.back(t, t >= 2, resid_follows ? -1 : (t + 1 >= 2), optional);
+        if (resid_follows) ex.resid();
+        if (t + 1 >= sch.min_iters) ex.check(t, resid_follows ? 1 : 0);
     }
 }
 

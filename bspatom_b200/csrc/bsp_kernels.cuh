@@ -337,6 +337,24 @@ __global__ void bsp_prepare_kernel(BspEigChunk g)
 #endif
 /* wide bands: fewer groups, so that tiles + ring stay within the 48 KB of static shared memory */
 __host__ __device__ constexpr int bsp_rhs_ring(int B) { return B <= 6 ? BSP_RHS_RING : (B == 7 ? (BSP_RHS_RING < 2 ? BSP_RHS_RING : 2) : 1); }
+/* thread -> (eigen index, factor column): identity at full width; in an optional (compacted) pass the slot-th
+ * entry of the list the previous convergence check wrote.  Returns false for the whole block when it has nothing
+ * to do (block-uniform). */
+__device__ __forceinline__ bool bsp_refine_map(const BspEigChunk &g, int p, int iter, int listed, int &e, bool &active)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (listed) {
+        const int cnt = g.rcount[((iter - 1) & 1) * g.npencil + p];
+        if ((int)(blockIdx.x * blockDim.x) >= cnt) return false;
+        active = slot < cnt;
+        e = active ? g.rlist[((size_t)((iter - 1) & 1) * g.npencil + p) * g.ldw + slot] : 0;
+    } else {
+        e = slot;
+        active = bsp_refine_active(g, p, e);
+    }
+    return true;
+}
+
 template <int B>
 __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_kernel(BspEigChunk g, int iter, int optional)
 {
@@ -345,32 +363,36 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B))
     __shared__ __align__(16) double ring[(RING + 1) * (B + 1) * BSP_EIG_THREADS];
     __shared__ __align__(8) uint64_t bars[2];
     if (optional && g.counters[BSP_C_REFINED]) return;
-    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = bsp_refine_active(g, p, e);
+    const int p = blockIdx.y, ls = blockIdx.x * blockDim.x + threadIdx.x;
+    int e;
+    bool active;
+    if (!bsp_refine_map(g, p, iter, optional && g.rlist != nullptr, e, active)) return;
     bsp_stage_bars_init(bars);
     if (!__syncthreads_or(active)) return;
     constexpr int FS = 2 * B + 2;
     BspRowsStaged<B, RING> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
     src.rq = ring + threadIdx.x;
-    bsp_factor_forward_rows<B>(g, p, e, iter, active, src);
+    bsp_factor_forward_rows<B>(g, p, e, ls, iter, active, src);
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_back_kernel(BspEigChunk g, int corr_now, int corr_next, int optional)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_back_kernel(BspEigChunk g, int iter, int corr_now, int corr_next, int optional)
 {
     __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
     __shared__ __align__(8) uint64_t bars[2];
     if (optional && g.counters[BSP_C_REFINED]) return;
-    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = bsp_refine_active(g, p, e);
+    const int p = blockIdx.y, ls = blockIdx.x * blockDim.x + threadIdx.x;
+    int e;
+    bool active;
+    if (!bsp_refine_map(g, p, iter, optional && g.rlist != nullptr, e, active)) return;
     bsp_stage_bars_init(bars);
     if (!__syncthreads_or(active)) return;
     constexpr int FS = 2 * B + 2;
     BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
-    bsp_back_substitute_rows<B>(g, p, e, corr_now, corr_next, active, src);
+    bsp_back_substitute_rows<B>(g, p, e, ls, corr_now, corr_next, active, src);
 }
 
-/* residual of the vectors in X against their own Rayleigh quotient (min_iters = 2 schedule) */
+/* residual of the vectors in X against their own Rayleigh quotient (after the second solve) */
 template <int B>
 __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_resid_kernel(BspEigChunk g)
 {
@@ -382,27 +404,13 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) b
     if (!__syncthreads_or(active)) return;
     constexpr int FS = 2 * B + 2;
     BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
-    bsp_back_substitute_rows<B, true>(g, p, e, 0, 1, active, src);
+    bsp_back_substitute_rows<B, true>(g, p, e, e, 0, 1, active, src);
 }
 
-template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_ckpt_kernel(BspEigChunk g, int iter, int optional)
-{
-    if (optional && g.counters[BSP_C_REFINED]) return;
-    bsp_factor_checkpoint<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter);
-}
-
-template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_back_rc_kernel(BspEigChunk g, int corr_now, int corr_next, int iter, int optional)
-{
-    if (optional && g.counters[BSP_C_REFINED]) return;
-    bsp_back_recompute<B>(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, corr_now, corr_next, iter);
-}
-
-__global__ void bsp_check_kernel(BspEigChunk g, int iter)
+__global__ void bsp_check_kernel(BspEigChunk g, int iter, int select)
 {
     if (g.counters[BSP_C_REFINED]) return;
-    bsp_check_converged(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, 1);
+    bsp_check_converged(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter, select);
     if (bsp_last_block(g.counters + BSP_C_ARRIVE)) bsp_check_ctl(g, iter);
 }
 

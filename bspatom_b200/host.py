@@ -263,7 +263,7 @@ class BspAtom(BspInputs):
         keys = ["launches", "rounds", "iters", "ms_assembly", "ms_eigenvalues", "ms_eigenvectors", "ms_finalize",
                 "ms_total", "ms_k_round", "ms_k_factor", "ms_k_back", "ms_k_assembly",
                 "n_k_round", "n_k_factor", "n_k_back", "n_k_assembly", "wall_ms_upload", "wall_ms_run",
-                "wall_ms_download", "ms_gap_before_chunk", "ms_gap_after_last_chunk", "wall_ms_copy_tail"]
+                "wall_ms_download", "chunks_redone", "selected_third_solve", "wall_ms_copy_tail"]
         return dict(zip(keys, list(out)))
 
     # ---- MATRIX_SVT (matrices.f90:1-200) ------------------------------------------------
@@ -355,6 +355,14 @@ class BspAtom(BspInputs):
                                              Cbuf.ctypes.data_as(C.c_void_p) if Cbuf is not None else None,
                                              info.ctypes.data_as(C.c_void_p))
         _lib.check(self.lib, self._h, rc, "bspatom_batch_download")
+
+    def batch_verify(self) -> dict:
+        """Device-side check of the resident batch: max scaled residual over every eigenpair, max |C^T S C - I|
+        over every pencil, ascending spectra (bspatom_batch_verify)."""
+        out = (C.c_double * 4)()
+        _lib.check(self.lib, self._h, self.lib.bspatom_batch_verify(self._h, out), "bspatom_batch_verify")
+        return {"max_scaled_residual": out[0], "max_orthonormality_defect": out[1], "not_ascending": out[2],
+                "eigenpairs_checked": int(out[3])}
 
     # ---- WRITE_WF (Bsp_Atom.f90:101-152) ------------------------------------------------
     def WRITE_WF(self, ci: np.ndarray, npts: int = 10000):

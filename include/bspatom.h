@@ -85,10 +85,11 @@ void *bspatom_alloc_host(size_t bytes);
 void bspatom_free_host(void *p);
 
 /* tunables: "tau", "delta_rel", "conv_tol", "res_tol", "rounds_enqueued", "max_rounds", "min_iters"
- * (3; 2 = fast schedule: eigenpairs may retire after the second solve, S-orthogonality of neighbouring
- * vectors ~1e-8 instead of ~1e-12), "max_iters", "chunk", "workers" (chunk streams of a resident batch,
- * 1..8), "stream_chunks" / "stream_workers" (chunks and chunk streams when results go to pinned host
- * buffers), "recompute", "trace" (1: chunk / copy timeline on stderr) */
+ * (2: every eigenpair gets two solves and a residual check, a third -- correction -- solve only where
+ * ||r||_2 / gap > "vec_tol" (1e-12); 3: everybody gets the third solve; vec_tol = 1e300 is the fast
+ * schedule: S-orthogonality of neighbouring vectors ~1e-8 instead of ~1e-11), "max_iters", "chunk",
+ * "workers" (chunk streams of a resident batch, 1..8), "stream_chunks" / "stream_workers" (chunks and
+ * chunk streams when results go to pinned host buffers), "trace" (1: chunk / copy timeline on stderr) */
 int bspatom_set_option(bspatom_handle h, const char *name, double value);
 
 /* ---- assembly: replaces MATRIX_SVT (matrices.f90:1-200) ------------------ *
@@ -118,6 +119,12 @@ int bspatom_solve_batch(bspatom_handle h, int nprob, const bsp_problem *probs, d
 int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs);
 int bspatom_batch_run(bspatom_handle h);
 int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info);
+
+/* device-side check of the resident batch (after bspatom_batch_run): out[0] = max scaled residual
+ * |H_l c - E S c|_inf / max(1,|E|) over EVERY eigenpair, out[1] = max |C^T S C - I| over every pencil,
+ * out[2] = 0 when every spectrum is strictly ascending, out[3] = eigenpairs checked.  What the host would
+ * otherwise verify after gathering Hij (matrices.f90:248) -- without moving the eigenvectors.           */
+int bspatom_batch_verify(bspatom_handle h, double *out4);
 
 /* ---- LAPACK-compatible entry: one-token rename at matrices.f90:248 --------- *
  * DSYGV semantics for itype=1, jobz='V'|'N', uplo='U'|'L'.  The pencil must be

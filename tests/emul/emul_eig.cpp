@@ -15,7 +15,7 @@ struct EmulExec {
     BspEigChunk g;
     std::vector<double> cand_s;
     std::vector<int> cand_c;
-    int recompute = 0, cur_iter = 0, open_ok = 0;
+    int cur_iter = 0, open_ok = 0;
     void bounds() {
         cand_s.assign(g.npencil * BSP_NCAND, 0.0);
         cand_c.assign(g.npencil * BSP_NCAND, 0);
@@ -39,31 +39,44 @@ struct EmulExec {
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_refine_prepare(g, p, e);
     }
+    /* optional passes run on the compaction list of the previous check, like the kernels: thread `slot` works on
+     * eigen index rlist[slot] and keeps its factor in column `slot` of L */
+    template <class F> void for_each_active(int it, int optional, F f) {
+        for (int p = 0; p < g.npencil; ++p) {
+            if (optional) {
+                for (int slot = 0; slot < g.n; ++slot) {
+                    const int e = bsp_listed_index(g, p, slot, it);
+                    if (e < 0) break;
+                    f(p, e, slot);
+                }
+            } else {
+                for (int e = 0; e < g.n; ++e) if (bsp_refine_active(g, p, e)) f(p, e, e);
+            }
+        }
+    }
     void factor(int it, int optional) {
         cur_iter = it;
         if (optional && g.counters[BSP_C_REFINED]) return;
-        for (int p = 0; p < g.npencil; ++p)
-            for (int e = 0; e < g.n; ++e) {
-                if (recompute) bsp_factor_checkpoint<B>(g, p, e, it);
-                else bsp_factor_forward<B>(g, p, e, it);
-            }
+        for_each_active(it, optional, [&](int p, int e, int ls) {
+            BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
+            bsp_factor_forward_rows<B>(g, p, e, ls, it, true, src);
+        });
     }
-    void back(int cn, int cx, int optional) {
+    void back(int it, int cn, int cx, int optional) {
         if (optional && g.counters[BSP_C_REFINED]) return;
-        for (int p = 0; p < g.npencil; ++p)
-            for (int e = 0; e < g.n; ++e) {
-                if (recompute) bsp_back_recompute<B>(g, p, e, cn, cx, cur_iter);
-                else bsp_back_substitute<B>(g, p, e, cn, cx);
-            }
+        for_each_active(it, optional, [&](int p, int e, int ls) {
+            BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
+            bsp_back_substitute_rows<B>(g, p, e, ls, cn, cx, true, src);
+        });
     }
     void resid() {
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_residual_pass<B>(g, p, e);
     }
-    void check(int it) {
+    void check(int it, int select) {
         if (g.counters[BSP_C_REFINED]) return;
         for (int p = 0; p < g.npencil; ++p)
-            for (int e = 0; e < g.n; ++e) bsp_check_converged(g, p, e, 1);
+            for (int e = 0; e < g.n; ++e) bsp_check_converged(g, p, e, it, select);
         if (getenv("BSP_EMUL_TRACE")) fprintf(stderr, "iteration %d unconverged %d\n", it, g.counters[BSP_C_UNCONV]);
         bsp_check_ctl(g, it);
     }
@@ -71,7 +84,7 @@ struct EmulExec {
 
 template <int B>
 static int run(int n, int npencil, const double *hb, const double *sb, const int *nvec_in, double tau,
-               double delta_rel, double conv_tol, int max_rounds, int min_iters, int max_iters,
+               double delta_rel, double conv_tol, double vec_tol, int max_rounds, int min_iters, int max_iters,
                double *E, double *C, double *stats)
 {
     constexpr int K1 = B + 1, FS = 2 * B + 2;
@@ -98,7 +111,8 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     std::vector<int> inst(npencil), nvec(npencil);
     for (int p = 0; p < npencil; ++p) { inst[p] = p; nvec[p] = nvec_in[p]; }
     std::vector<double> pbound(npencil * 4), lo(2 * per), hi(2 * per), samp_s(2 * per), gap(per), sigma(per),
-        rho(per), rho_prev(per), scale(per), res(per), xmax(per);
+        rho(per), rho_prev(per), scale(per), res(per), res2(per), xmax(per);
+    std::vector<int> rlist(2 * per), rcount(2 * npencil, 0);
     std::vector<int> clo(2 * per), chi(2 * per), samp_c(2 * per), done(per), status(per), counters(BSP_C_WORDS, 0);
     std::vector<double> samp_fm(2 * per), flm(per), fhm(per), beta(per);
     std::vector<int> samp_fe(2 * per), fle(per), fhe(per), side(per);
@@ -110,9 +124,9 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     g.samp_fm = samp_fm.data(); g.samp_fe = samp_fe.data(); g.flm = flm.data(); g.fhm = fhm.data();
     g.fle = fle.data(); g.fhe = fhe.data(); g.side = side.data(); g.beta = beta.data();
     g.sigma = sigma.data(); g.rho = rho.data(); g.rho_prev = rho_prev.data(); g.scale = scale.data();
-    g.res = res.data(); g.xmax = xmax.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
+    g.res = res.data(); g.res2 = res2.data(); g.rlist = rlist.data(); g.rcount = rcount.data(); g.vec_tol = vec_tol; g.xmax = xmax.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
     g.counters = counters.data(); g.tau = tau; g.delta_rel = delta_rel; g.conv_tol = conv_tol;
-    EmulExec<B> ex; ex.g = g; ex.recompute = getenv("BSP_EMUL_RECOMPUTE") ? atoi(getenv("BSP_EMUL_RECOMPUTE")) : 0;
+    EmulExec<B> ex; ex.g = g;
     BspSchedule sch = {max_rounds, min_iters, max_iters};
     bsp_enqueue_chunk(ex, sch);
     BspRunStats st = {counters[BSP_C_ROUNDS], counters[BSP_C_ITERS], counters[BSP_C_OPEN_END], counters[BSP_C_CROWDED_END],
@@ -131,14 +145,15 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     stats[4] = rmax;
     int nb = 0; for (int p = 0; p < npencil; ++p) nb += bad[p];
     stats[5] = nb;
+    stats[6] = counters[BSP_C_SELECTED];   /* eigenpairs that went through a third solve */
     return 0;
 }
 
 extern "C" int emul_solve(int n, int B, int npencil, const double *hb, const double *sb, const int *nvec,
-                          double tau, double delta_rel, double conv_tol, int max_rounds, int min_iters,
+                          double tau, double delta_rel, double conv_tol, double vec_tol, int max_rounds, int min_iters,
                           int max_iters, double *E, double *C, double *stats)
 {
-#define CASE(b) case b: return run<b>(n, npencil, hb, sb, nvec, tau, delta_rel, conv_tol, max_rounds, min_iters, max_iters, E, C, stats);
+#define CASE(b) case b: return run<b>(n, npencil, hb, sb, nvec, tau, delta_rel, conv_tol, vec_tol, max_rounds, min_iters, max_iters, E, C, stats);
     switch (B) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) default: return -2; }
 }
 

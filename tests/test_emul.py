@@ -24,7 +24,7 @@ def emul():
     if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-o", SO, SRC])
     lib = C.CDLL(SO)
-    lib.emul_solve.argtypes = [C.c_int] * 3 + [dp, dp, ip] + [C.c_double] * 3 + [C.c_int] * 3 + [dp] * 3
+    lib.emul_solve.argtypes = [C.c_int] * 3 + [dp, dp, ip] + [C.c_double] * 4 + [C.c_int] * 3 + [dp] * 3
     lib.emul_count.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double]
     return lib
 
@@ -37,7 +37,7 @@ def lower_band(A, b):
     return np.ascontiguousarray(ab)
 
 
-def solve(emul, H, S, b, nvec=None, tau=1e-4, min_iters=3):
+def solve(emul, H, S, b, nvec=None, tau=1e-4, min_iters=2, vec_tol=1e-12):
     n = H.shape[0]
     hb, sb = lower_band(H, b), lower_band(S, b)
     nv = np.array([n if nvec is None else nvec], dtype=np.int32)
@@ -45,7 +45,7 @@ def solve(emul, H, S, b, nvec=None, tau=1e-4, min_iters=3):
     Cm = np.zeros((n, n))
     st = np.zeros(8)
     rc = emul.emul_solve(n, b, 1, hb.ctypes.data_as(dp), sb.ctypes.data_as(dp), nv.ctypes.data_as(ip), tau, 1e-4,
-                         1e-11, 90, min_iters, 12, E.ctypes.data_as(dp), Cm.ctypes.data_as(dp), st.ctypes.data_as(dp))
+                         1e-11, vec_tol, 90, min_iters, 12, E.ctypes.data_as(dp), Cm.ctypes.data_as(dp), st.ctypes.data_as(dp))
     assert rc == 0
     return E, Cm.T[:, :nv[0]].copy(), st
 
@@ -112,22 +112,17 @@ def test_partial_vectors_still_give_all_eigenvalues(emul, oracle):
     assert Cm.shape[1] == 5 and np.abs(np.abs(np.sum(Cm * (m["S"] @ v[:, :5]), 0)) - 1).max() < 1e-9
 
 
-def test_checkpointed_refinement_equals_stored_factor(oracle):
-    """the check-pointed sweeps (re-elimination in the back sweep) do the same arithmetic as the
-    stored-factor sweeps: bit-identical eigenpairs."""
-    import importlib
-
-    b = oracle.make_basis(kind_grid=0, k=7, nfun=150, rb=80.0)
+def test_values_only_eigenvalues_close_their_brackets(emul, oracle):
+    """nvec = 0 / nvec < n: eigen indices without a vector are never refined, so the bracketing itself must close
+    their brackets to rounding (they used to come back as the midpoint of a possibly open bracket)."""
+    b = oracle.make_basis(kind_grid=2, k=7, nfun=100, rb=500.0, rmax=60.0)
     m = oracle.matrix_svt(b, lmax=1)
     H = oracle.hamiltonian(m["T"], m["U"][:, :, 1], m["V"])
-    out = []
-    for mode in ("0", "1"):
-        os.environ["BSP_EMUL_RECOMPUTE"] = mode
-        lib = C.CDLL(SO)
-        lib.emul_solve.argtypes = [C.c_int] * 3 + [dp, dp, ip] + [C.c_double] * 3 + [C.c_int] * 3 + [dp] * 3
-        out.append(solve(lib, H, m["S"], 6))
-    os.environ.pop("BSP_EMUL_RECOMPUTE")
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    truth = oracle.band_bisect_truth(H, m["S"], 6)
+    for nv in (0, 7):
+        E, Cm, st = solve(emul, H, m["S"], 6, nvec=nv)
+        assert st[5] == 0
+        assert np.max(np.abs(E - truth) / np.maximum(np.abs(truth), 1e-2)) < 1e-13
 
 
 def test_tiny_bases(emul, oracle):
@@ -141,21 +136,29 @@ def test_tiny_bases(emul, oracle):
         assert st[3] == 0 and st[5] == 0
 
 
-def test_fast_schedule_two_solves_plus_residual_pass(emul, oracle):
-    """min_iters = 2: eigenpairs may retire after the second plain solve, judged by the residual pass against
-    their own Rayleigh quotient.  Eigenvalues and residuals keep their tolerances; the S-orthogonality of
-    neighbouring vectors is what the skipped correction step would have bought (~1e-8 instead of ~1e-12)."""
-    b = oracle.shipped_basis()
-    m = oracle.matrix_svt(b, lmax=1)
-    H = oracle.hamiltonian(m["T"], m["U"][:, :, 1], m["V"])
-    E3, C3, st3 = solve(emul, H, m["S"], b.k - 1)
-    E2, C2, st2 = solve(emul, H, m["S"], b.k - 1, min_iters=2)
-    assert st2[2] == 0 and st2[3] == 0 and st2[5] == 0
-    assert st2[1] <= st3[1]
-    assert np.max(np.abs(E2 - E3) / np.maximum(np.abs(E3), 1e-2)) < 1e-12
-    R = H @ C2 - (m["S"] @ C2) * E2
-    assert (np.abs(R).max(0) / np.maximum(1, np.abs(E2))).max() < 1e-10
-    assert np.abs(C2.T @ m["S"] @ C2 - np.eye(b.nfun)).max() < 1e-6
+def test_third_solve_only_where_the_gap_test_asks_for_it(emul, oracle):
+    """Default schedule: two solves, a residual pass, then the correction pass only for the eigenpairs with
+    ||r||_2 / gap > vec_tol (compacted list).  Against the round-1 schedule (min_iters = 3: everybody gets the
+    third solve): same eigenvalues, same residual bar, S-orthonormality still at the 1e-11 level, and only a
+    fraction of the eigenpairs selected.  vec_tol = inf is the "fast" schedule (nobody selected for orthogonality):
+    the looser ~1e-8 orthogonality is what the selected correction passes buy."""
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=400, rb=200.0)
+    m = oracle.matrix_svt(b, lmax=3)
+    H = oracle.hamiltonian(m["T"], m["U"][:, :, 3], m["V"])
+    S = m["S"]
+    n = b.nfun
+    E3, C3, st3 = solve(emul, H, S, 6, min_iters=3)
+    E2, C2, st2 = solve(emul, H, S, 6)
+    Ef, Cf, stf = solve(emul, H, S, 6, vec_tol=1e300)
+    for st in (st2, st3, stf):
+        assert st[2] == 0 and st[3] == 0 and st[5] == 0
+    assert 0 < st2[6] < 0.4 * n, st2[6]                     # a minority goes through the third solve
+    assert np.max(np.abs(E2 - E3) / np.maximum(np.abs(E3), 1e-2)) < 1e-13
+    for Cm, E, orth_tol in ((C3, E3, 2e-11), (C2, E2, 2e-11), (Cf, Ef, 1e-6)):
+        R = H @ Cm - (S @ Cm) * E
+        assert (np.abs(R).max(0) / np.maximum(1, np.abs(E))).max() < 1e-11
+        assert np.abs(Cm.T @ S @ Cm - np.eye(n)).max() < orth_tol
+    assert np.abs(Cf.T @ S @ Cf - np.eye(n)).max() > np.abs(C2.T @ S @ C2 - np.eye(n)).max()
 
 
 @pytest.mark.parametrize("kw,lmax,max_rounds", [
@@ -173,4 +176,4 @@ def test_schedule_budget(emul, oracle, kw, lmax, max_rounds):
         H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
         E, Cm, st = solve(emul, H, m["S"], b.k - 1)
         assert st[0] <= max_rounds, (l, st[0])
-        assert st[1] == 3 and st[2] == 0 and st[3] == 0 and st[5] == 0, (l, list(st))
+        assert st[1] <= 3 and st[2] == 0 and st[3] == 0 and st[5] == 0, (l, list(st))

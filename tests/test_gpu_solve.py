@@ -246,41 +246,35 @@ def test_other_orders_solve(atom, oracle, k, nfun, grid):
     check_eigenpairs(Es[0], Cs[0], H, S, res_tol=1e-11, orth_tol=1e-9)
 
 
-def test_check_pointed_refinement_option_is_bit_identical(atom):
-    """option `recompute` (check-pointed sweeps, off by default) must reproduce the stored-factor results."""
-    a = host_basis(kind_grid=0, k=7, nfun=260, rb=130.0)
-    items = [(a.problem(), l) for l in range(3)]
-    E0, C0, _ = atom.solve_batch(items)
-    atom.set_option("recompute", 1)
-    try:
-        E1, C1, _ = atom.solve_batch(items)
-    finally:
-        atom.set_option("recompute", 0)
-    for x, y in zip(E0 + C0, E1 + C1):
-        assert np.array_equal(x, y)
-
-
-def test_fast_schedule_min_iters_2(atom, oracle):
-    """option min_iters = 2: eigenpairs retire after the second solve when the residual pass says so.
-    Eigenvalues and residuals keep the north-star tolerances; only the S-orthogonality of neighbouring
-    vectors is looser than with the default schedule (no correction step)."""
+def test_third_solve_selection_against_the_full_schedule(atom, oracle):
+    """Default schedule (two solves + residual pass, correction pass compacted to the eigenpairs with
+    ||r||_2 / gap > vec_tol) against min_iters = 3 (everybody gets the correction pass, the round-1 schedule) and
+    against vec_tol = inf (nobody selected for orthogonality: the fast schedule).  Eigenvalues agree to rounding,
+    residuals keep the bar everywhere; S-orthonormality stays at the 1e-11 level with a minority selected."""
     a = host_basis(kind_grid=0, k=7, nfun=400, rb=200.0)
     items = [(a.problem(), l) for l in (0, 3)]
-    E3, C3, info3 = atom.solve_batch(items)
-    atom.set_option("min_iters", 2)
+    E2, C2, info2 = atom.solve_batch(items)
+    st2 = atom.stats()
+    atom.set_option("min_iters", 3)
     try:
-        E2, C2, info2 = atom.solve_batch(items)
-        iters2 = atom.stats()["iters"]
+        E3, C3, info3 = atom.solve_batch(items)
     finally:
-        atom.set_option("min_iters", 3)
-    assert not info2.any() and not info3.any()
-    assert iters2 <= 3
-    for (p, l), e2, e3, c2 in zip(items, E2, E3, C2):
-        assert np.max(np.abs(e2 - e3) / np.maximum(np.abs(e3), 1e-2)) < 1e-12
+        atom.set_option("min_iters", 2)
+    atom.set_option("vec_tol", 1e300)
+    try:
+        Ef, Cf, infof = atom.solve_batch(items)
+    finally:
+        atom.set_option("vec_tol", 1e-12)
+    assert not info2.any() and not info3.any() and not infof.any()
+    assert 0 < st2["selected_third_solve"] < 0.4 * 2 * a.nfun, st2["selected_third_solve"]
+    for (p, l), e2, e3, ef, c2, c3, cf in zip(items, E2, E3, Ef, C2, C3, Cf):
+        assert np.max(np.abs(e2 - e3) / np.maximum(np.abs(e3), 1e-2)) < 1e-13
+        assert np.max(np.abs(ef - e3) / np.maximum(np.abs(e3), 1e-2)) < 1e-12
         b, H, S = oracle_pencil(oracle, a, 400, l)
-        R = H @ c2 - (S @ c2) * e2
-        assert (np.abs(R).max(0) / np.maximum(1, np.abs(e2))).max() < 1e-9
-        assert np.abs(c2.T @ S @ c2 - np.eye(a.nfun)).max() < 1e-6
+        for Cm, E, orth_tol in ((c2, e2, 3e-11), (c3, e3, 3e-11), (cf, ef, 1e-6)):
+            R = H @ Cm - (S @ Cm) * E
+            assert (np.abs(R).max(0) / np.maximum(1, np.abs(E))).max() < 1e-11
+            assert np.abs(Cm.T @ S @ Cm - np.eye(a.nfun)).max() < orth_tol
 
 
 # ------------------------------------------------------------------------------------------
