@@ -40,6 +40,7 @@ struct Options {
     double res_tol = 1e-9;
     int max_rounds = 90;      /* cap used when a chunk has to be redone */
     int rounds_enqueued = 26; /* bracketing rounds enqueued up front (surplus ones return at once) */
+    int ckpt = 0;             /* check-pointed full-width solves: 0 never (default: measured break-even), 1 always, -1 for half bandwidth <= 6 */
     double vec_tol = 1e-12;   /* ||r||_2 / gap above which an eigenpair gets the correction pass after its second solve */
     int min_iters = 2;        /* solves every eigenpair gets (3 = round-1 schedule: everybody gets the correction pass) */
     int trace = 0;        /* diagnostics: print the chunk / copy timeline of every run to stderr */
@@ -366,9 +367,14 @@ struct GpuExec {
     int *cand_c;
     int open_ok = 0;
     int cur_iter = 0;
+    bool ckpt = false;   /* iterations 0 and 1 run check-pointed (no stored factor) */
     cudaEvent_t ev_refine = nullptr; /* recorded between the bracketing and the refinement */
     cudaError_t first_err = cudaSuccess;
     dim3 grid() const { return dim3((g.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS, g.npencil); }
+    /* compacted passes: a pencil lists 10-17 % of its eigenpairs (64-thread blocks were measured: factor +0.25 ms,
+     * no gain overall) */
+    static constexpr int LISTED_THREADS = 128;
+    dim3 grid_listed() const { return dim3((g.n + LISTED_THREADS - 1) / LISTED_THREADS, g.npencil); }
     void note() {
         h->launches++;
         cudaError_t e = cudaGetLastError();
@@ -390,19 +396,30 @@ struct GpuExec {
     void factor(int it, int optional) {
         cur_iter = it;
         const int s = timed_begin(h, 1);
-        bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional);
+        if (ckpt && it < 2 && !optional) bsp_factor_ckpt_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it);
+        else if (optional) bsp_factor_kernel<B><<<grid_listed(), LISTED_THREADS, 0, h->st>>>(g, it, optional);
+        else bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional);
         note();
         timed_end(h, s);
     }
     void back(int it, int cn, int cx, int optional) {
         const int s = timed_begin(h, 2);
-        bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, cn, cx, optional);
+        if (ckpt && it < 2 && !optional) {
+            const size_t smem = bsp_back_ckpt_smem<B>(BSP_CKB_THREADS);
+            cudaFuncSetAttribute(bsp_back_ckpt_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            dim3 gr((g.n + BSP_CKB_THREADS - 1) / BSP_CKB_THREADS, g.npencil);
+            bsp_back_ckpt_kernel<B><<<gr, BSP_CKB_THREADS, smem, h->st>>>(g, it, cx);
+        } else if (optional) {
+            bsp_back_kernel<B><<<grid_listed(), LISTED_THREADS, 0, h->st>>>(g, it, cn, cx, optional);
+        } else {
+            bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, cn, cx, optional);
+        }
         note();
         timed_end(h, s);
     }
-    void resid() {
+    void resid(int optional) {
         const int s = timed_begin(h, 2);
-        bsp_resid_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g); note();
+        bsp_resid_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, optional); note();
         timed_end(h, s);
     }
     void check(int it, int select) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, select); note(); }
@@ -426,11 +443,11 @@ struct Carver {
 
 struct ChunkPtrs {
     double *fbH, *pbound, *lo, *hi, *samp_s, *gap, *sigma, *rho, *rho_prev, *scale, *res, *L, *X, *R, *cand_s, *fac;
-    double *samp_fm, *flm, *fhm, *beta, *xmax, *res2;
+    double *samp_fm, *flm, *fhm, *beta, *xmax, *res2, *CK;
     int *clo, *chi, *samp_c, *done, *status, *counters, *cand_c, *samp_fe, *fle, *fhe, *side, *olist, *ocount, *rlist, *rcount;
 };
 
-size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
+size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c, bool ckpt)
 {
     Carver cv{base};
     const size_t per = (size_t)np * G.ldw;
@@ -452,10 +469,13 @@ size_t carve_chunk(const Group &G, int np, char *base, ChunkPtrs &c)
     c.rlist = cv.take<int>(2 * per); c.rcount = cv.take<int>(2 * (size_t)np);
     c.cand_s = cv.take<double>((size_t)np * BSP_NCAND); c.cand_c = cv.take<int>((size_t)np * BSP_NCAND);
     c.L = cv.take<double>((size_t)np * G.npad * (G.B + 1) * G.ldw);
+    c.CK = ckpt ? cv.take<double>((size_t)np * (G.npad / BSP_CK_STEPS(G.B)) * BSP_CK_DOUBLES(G.B) * G.ldw) : nullptr;
     c.X = cv.take<double>((size_t)np * G.xrows * G.ldw);
     c.R = cv.take<double>((size_t)np * G.xrows * G.ldw);
     return cv.used;
 }
+
+bool use_ckpt(bspatom_handle h, const Group &G) { return h->opt.ckpt > 0 || (h->opt.ckpt < 0 && G.B <= 6); }
 
 /* Enqueue the whole stage schedule of pencils [p0, p0+np) of G on h's stream: no host read-back.
  * report: BSP_C_WORDS ints on the device that receive the chunk's control block at the end. */
@@ -479,12 +499,13 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     g.samp_s = c.samp_s; g.samp_c = c.samp_c; g.gap = c.gap; g.done = c.done;
     g.samp_fm = c.samp_fm; g.samp_fe = c.samp_fe; g.flm = c.flm; g.fhm = c.fhm; g.fle = c.fle; g.fhe = c.fhe; g.side = c.side; g.beta = c.beta;
     g.sigma = c.sigma; g.rho = c.rho; g.rho_prev = c.rho_prev; g.scale = c.scale; g.res = c.res; g.xmax = c.xmax;
-    g.status = c.status; g.L = c.L; g.X = c.X; g.R = c.R; g.counters = c.counters;
+    g.status = c.status; g.L = c.L; g.CK = c.CK; g.X = c.X; g.R = c.R; g.counters = c.counters;
     g.olist = c.olist; g.ocount = c.ocount; g.res2 = c.res2; g.rlist = c.rlist; g.rcount = c.rcount;
     g.tau = h->opt.tau; g.delta_rel = h->opt.delta_rel; g.conv_tol = h->opt.conv_tol; g.vec_tol = h->opt.vec_tol;
 
     GpuExec<B> ex;
     ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.ev_refine = tm.ev[1];
+    ex.ckpt = (c.CK != nullptr);
     /* a few stragglers per hundred thousand eigenpairs are cheaper to finish inside the refinement */
     ex.open_ok = (int)((long long)np * G.n / 20000);
     bsp_zero_words_kernel<<<1, 32, 0, h->st>>>(c.counters, BSP_C_WORDS);
@@ -687,6 +708,7 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "first_check_round" || s == "check_every") { /* accepted and ignored: the schedule is static */ }
     else if (s == "chunk") h->opt.chunk = (int)v;
     else if (s == "vec_tol") h->opt.vec_tol = v;
+    else if (s == "ckpt") { h->opt.ckpt = (int)v; h->budget_bytes = 0; }
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
     else if (s == "stream_workers") h->opt.stream_workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
     else if (s == "workers") h->opt.workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
@@ -992,7 +1014,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         CU(cudaEventRecord(pd_done, h->st_copy));
         /* ---- chunking ---- */
         ChunkPtrs c;
-        const size_t per_pencil = carve_chunk(G, 1, nullptr, c);
+        const size_t per_pencil = carve_chunk(G, 1, nullptr, c, use_ckpt(h, G));
         const int blocks_per_pencil = (G.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS;
         const int fill_pencils = std::max(1, (148 * 4 + blocks_per_pencil - 1) / blocks_per_pencil); /* one full wave */
         const bool streaming = (E_out || C_out);
@@ -1050,7 +1072,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             for (int i = 0; i < nchunks; ++i) chunk = std::max(chunk, bounds[i + 1] - bounds[i]);
         }
         workers = std::min(workers, nchunks);
-        const size_t need = carve_chunk(G, chunk, nullptr, c);
+        const size_t need = carve_chunk(G, chunk, nullptr, c, use_ckpt(h, G));
         if ((rc = ensure_workspace(h, need))) return rc;
         while ((int)h->aux.size() < workers - 1) {
             bspatom_handle x = new_context(h->dev);
@@ -1085,7 +1107,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             load[wsel] += bounds[ci + 1] - bounds[ci];
             bspatom_handle x = ctx[wsel];
             ChunkPtrs cc;
-            carve_chunk(G, chunk, x->ws.base, cc);
+            carve_chunk(G, chunk, x->ws.base, cc, use_ckpt(h, G));
             const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
             if ((rc = enqueue_chunk(x, G, p0, np, cc, sch, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) {
                 if (x != h) h->err = x->err;
@@ -1142,7 +1164,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             if (again) {
                 ++redone;
                 ChunkPtrs cc;
-                carve_chunk(G, chunk, h->ws.base, cc);
+                carve_chunk(G, chunk, h->ws.base, cc, use_ckpt(h, G));
                 const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
                 CU(cudaMemsetAsync(G.d_bad + p0, 0, sizeof(int) * np, h->st));
                 if ((rc = enqueue_chunk(h, G, p0, np, cc, sch_redo, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) return rc;

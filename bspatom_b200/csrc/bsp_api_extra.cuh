@@ -497,7 +497,7 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
     h->groups.push_back(G);
     Group &GG = h->groups.back();
     ChunkPtrs c;
-    const size_t need = carve_chunk(GG, 1, nullptr, c);
+    const size_t need = carve_chunk(GG, 1, nullptr, c, use_ckpt(h, GG));
     ChunkTimes tm;
     bool ev_ok = true;
     for (int i = 0; i < 4; ++i) ev_ok = ev_ok && (cudaEventCreate(&tm.ev[i]) == cudaSuccess);
@@ -505,7 +505,7 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
     int *d_report = nullptr;
     if (!rc) rc = dev_alloc(h, &d_report, (size_t)BSP_C_WORDS);
     if (!rc) {
-        carve_chunk(GG, 1, h->ws.base, c);
+        carve_chunk(GG, 1, h->ws.base, c, use_ckpt(h, GG));
         h->ev_used = 0;
         const BspSchedule sch = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters};   /* one pencil: full limits at once */
         rc = enqueue_chunk(h, GG, 0, 1, c, sch, tm, d_report);

@@ -65,18 +65,26 @@ __device__ __forceinline__ double bsp_drcp(double x)
  * decoupled: diag(H) = 1, rest 0) */
 #define BSP_NROWS(npad, B) ((npad) + (B) + 2)
 
-/* Check-pointed refinement: the forward sweep keeps only the elimination state (pivot window + rhs
- * window, BSP_CK_DOUBLES(B) doubles) at the start of every segment of BSP_SEG_BLOCKS*(B+1) rows
- * instead of the whole factor; the back sweep re-eliminates one segment at a time into a
- * thread-private scratch (L1/L2 resident) and consumes it at once.  Factor traffic to HBM drops from
- * (B+1) doubles per row to BSP_CK_DOUBLES/(BSP_SEG_BLOCKS*(B+1)), at the price of eliminating twice. */
+/* rows are padded to a whole number of BSP_SEG_BLOCKS groups of B+1 steps (a whole number of tiles) */
 #ifndef BSP_SEG_BLOCKS
 #define BSP_SEG_BLOCKS 4
 #endif
 #define BSP_SEG_STEPS(B) (BSP_SEG_BLOCKS * ((B) + 1))
-#define BSP_CK_DOUBLES(B) ((((B) + 1) * ((B) + 2)) / 2 + (B) + 1)
-/* rows are padded to a whole number of segments */
 #define BSP_NPAD(n, B) ((((n) + BSP_SEG_STEPS(B) - 1) / BSP_SEG_STEPS(B)) * BSP_SEG_STEPS(B))
+
+/* Check-pointed solves (the two full-width solves of every eigenpair): the forward sweep does not store the
+ * factor (B+1 doubles per row and eigenpair: 57 MB per pencil at N = 1000, written once and read once) but, at
+ * the start of every segment of BSP_CK_GROUPS(B) groups of B+1 rows, the part of the elimination state that
+ * cannot be re-read from the band: rows 0..B-1 of the pivot window (lower triangle), the right-hand-side window
+ * y[0..B] and the B+1 raw right-hand-side values already in flight -- BSP_CK_DOUBLES(B) doubles.  The back sweep
+ * takes the segments last to first: it re-eliminates a segment from its check-point into a scratch of
+ * BSP_CK_STEPS(B) x (B+1) doubles (shared memory in the kernel: the thread-private local-memory scratch of round 1
+ * thrashed L1) and back-substitutes it at once.  HBM traffic of the pair of sweeps at
+ * B = 6: 2 x 56 -> 2 x 20 bytes per row and eigenpair, at the price of eliminating twice (the FP64 pipe idles at
+ * 17-26 % in the stored-factor sweeps). */
+#define BSP_CK_GROUPS(B) ((B) <= 6 ? 2 : 1)
+#define BSP_CK_STEPS(B) (BSP_CK_GROUPS(B) * ((B) + 1))
+#define BSP_CK_DOUBLES(B) ((((B)) * ((B) + 1)) / 2 + 2 * ((B) + 1))
 
 /* The sweeps walk the band rows of a pencil in tiles of BSP_TILE_STEPS(B) steps (whole unrolled groups of
  * B+1 steps; npad is a whole number of tiles).  A row source hands out one tile at a time: on the host (and
@@ -140,8 +148,9 @@ struct BspEigChunk {
     double *xmax;   /* max |x_j| of the vector in X (tracked by the back sweep; the sign convention needs it) */
     int *status;
     /* workspaces */
-    double *L; /* [npencil][npad][B+1][ldw]  (zd, l_1..l_B), or, check-pointed:
-                  [npencil][npad/SEG][BSP_CK_DOUBLES][ldw]        */
+    double *L; /* [npencil][npad][B+1][ldw]  (zd, l_1..l_B): stored factor (compacted correction passes) */
+    double *CK; /* [npencil][npad / BSP_CK_STEPS][BSP_CK_DOUBLES][ldw]: check-points of the full-width solves,
+                   or null: every solve stores its factor */
     double *X; /* [npencil][xrows][ldw]                           */
     double *R; /* [npencil][xrows][ldw]                           */
     int *counters; /* control block, BSP_C_* */
@@ -277,21 +286,26 @@ struct BspFalse { static constexpr bool value = false; };
 
 /* row source reading global memory.  Forward tiles: pointer to band row t*TR, rows t*TR .. (t+1)*TR+B are
  * read.  Backward tiles (taken in descending t): same pointer, rows t*TR .. (t+1)*TR-1 are read. */
-template <int B>
+template <int B, int G = BSP_TILE_GROUPS(B)>
 struct BspRowsGlobal {
     static constexpr bool GL = true;
     static constexpr int RHS_RING = 0;   /* no shared-memory ring for the right-hand side */
+    static constexpr int TR = G * (B + 1);   /* steps per tile */
     const double *H, *S;
     BSP_HD void begin_forward(int) {}
     BSP_HD void acquire_forward(int t, const double *&tH, const double *&tS)
     {
-        tH = H + (size_t)t * BSP_TILE_STEPS(B) * (2 * B + 2);
-        tS = S + (size_t)t * BSP_TILE_STEPS(B) * (2 * B + 2);
+        tH = H + (size_t)t * TR * (2 * B + 2);
+        tS = S + (size_t)t * TR * (2 * B + 2);
     }
     BSP_HD void release_forward(int, int) {}
     BSP_HD void begin_backward(int) {}
     BSP_HD void acquire_backward(int t, int, const double *&tH, const double *&tS) { acquire_forward(t, tH, tS); }
     BSP_HD void release_backward(int, int) {}
+    /* backward order, forward-sized tiles (rows t*TR .. (t+1)*TR + B): the check-pointed back sweep */
+    BSP_HD void begin_backward_wide(int) {}
+    BSP_HD void acquire_backward_wide(int t, int, const double *&tH, const double *&tS) { acquire_forward(t, tH, tS); }
+    BSP_HD void release_backward_wide(int, int) {}
 };
 
 /* called by every thread that shares `src` (the staged source synchronises the block);
@@ -302,7 +316,7 @@ BSP_HD int bsp_sturm_sweep(Src &src, int npad, bool active, double sigma, double
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
-    constexpr int TR = BSP_TILE_STEPS(B);
+    constexpr int TR = Src::TR;
     const int ntiles = npad / TR;
     double w[K1][K1];
     int cnt = 0, first = -1;
@@ -697,13 +711,17 @@ BSP_HD void bsp_refine_prepare(const BspEigChunk &g, int p, int e)
  *   iter == 0 : rhs = hashed uniform(-1,1)      (plain inverse iteration)
  *   iter  > 0 : rhs = scale * R  (R written by the previous B pass)
  * ------------------------------------------------------------------------- */
-/* ls: column of the factor workspace L this thread uses (= e at full width, = its slot in a compacted pass) */
-template <int B, class Src>
+/* ls: column of the factor workspace L this thread uses (= e at full width, = its slot in a compacted pass).
+ * CKPT: check-pointed form -- nothing is stored per row; at every segment start the state of the elimination
+ * goes to CK[p][segment][0..BSP_CK_DOUBLES)[ls] (see BSP_CK_GROUPS). */
+template <int B, bool CKPT = false, class Src>
 BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, int iter, bool active, Src &src)
 {
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
-    constexpr int TR = BSP_TILE_STEPS(B);
+    constexpr int TR = Src::TR;
+    constexpr int CKD = BSP_CK_DOUBLES(B);
+    static_assert(!CKPT || TR % BSP_CK_STEPS(B) == 0, "tiles hold whole check-point segments");
     const int n = g.n, npad = g.npad, ldw = g.ldw;
     const int ntiles = npad / TR;
     const size_t id = (size_t)p * g.ldw + (active ? e : 0);
@@ -711,7 +729,8 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
     const double sc = active ? g.scale[id] : 1.0;
     const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(sigma) * g.pbound[p * 4 + 3]);
     const double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
-    double *__restrict__ Lp = g.L + (size_t)p * npad * K1 * ldw + ls;
+    double *__restrict__ Lp = CKPT ? g.CK + (size_t)p * (npad / BSP_CK_STEPS(B)) * CKD * ldw + ls
+                                   : g.L + (size_t)p * npad * K1 * ldw + ls;
 
     double w[K1][K1], y[K1];
     int cnt = 0;
@@ -770,6 +789,10 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
             for (int gq = 0; gq < TR; gq += K1) {
                 const int j0 = tl * TR + gq;
                 const double *hnext = tH + (size_t)(gq + K1) * FS, *snext = tS + (size_t)(gq + K1) * FS;
+                if constexpr (CKPT) {
+                    /* with the shared-memory ring the values of the next group are fetched below, before they are
+                     * needed by the steps: the check-point takes them from the ring as well */
+                }
                 if constexpr (Src::RHS_RING > 0) {
                     if (ring) {
                         /* this group consumes the rows of group gi+1; group gi+1+RHS_RING takes the slot that
@@ -779,6 +802,23 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
                         src.template rhs_wait<Src::RHS_RING>();
 #pragma unroll
                         for (int t = 0; t < K1; ++t) rq[t] = src.rhs_read(((gi + 1) % (Src::RHS_RING + 1)) * K1 + t);
+                    }
+                }
+                if constexpr (CKPT) {
+                    if ((j0 / K1) % BSP_CK_GROUPS(B) == 0) {
+                        /* at a group start the window slots are in identity position; row B of the window is
+                         * still the plain band row (it entered with the last step) and is not stored */
+                        double *ck = Lp + (size_t)(j0 / BSP_CK_STEPS(B)) * CKD * ldw;
+                        int q = 0;
+#pragma unroll
+                        for (int r = 0; r < B; ++r) {
+#pragma unroll
+                            for (int c = 0; c <= r; ++c) { ck[(size_t)q * ldw] = w[r][c]; ++q; }
+                        }
+#pragma unroll
+                        for (int r = 0; r < K1; ++r) { ck[(size_t)q * ldw] = y[r]; ++q; }
+#pragma unroll
+                        for (int r = 0; r < K1; ++r) { ck[(size_t)q * ldw] = rq[r]; ++q; }   /* raw rhs of rows j0+K1 .. j0+2K1-1 */
                     }
                 }
 #pragma unroll
@@ -799,12 +839,12 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
                     double col[K1], l[K1];
                     const double y0 = y[t];
                     double *Lrow = Lp + (size_t)j * K1 * ldw;
-                    Lrow[0] = y0 * rinv;
+                    if (!CKPT) Lrow[0] = y0 * rinv;
 #pragma unroll
                     for (int i = 1; i <= B; ++i) {
                         col[i] = w[(t + i) % K1][t];
                         l[i] = col[i] * rinv;
-                        Lrow[(size_t)i * ldw] = l[i];
+                        if (!CKPT) Lrow[(size_t)i * ldw] = l[i];
                         y[(t + i) % K1] = fma(-l[i], y0, y[(t + i) % K1]);
                     }
 #pragma unroll
@@ -851,6 +891,35 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
  *               1 -> h - rho' s  (rho' = Rayleigh quotient known at pass start)
  *               0 -> s
  * ------------------------------------------------------------------------- */
+/* end of a solving back sweep: Rayleigh quotient, normalisation, residual norms, next shift */
+BSP_HD void bsp_back_finish(const BspEigChunk &g, size_t id, int corr_next, double sc, double rho_p, double xSx, double xHx,
+                            double resmax, double rr2, double xabs)
+{
+    double lo = g.lo[id], hi = g.hi[id];
+    const double good = (xSx > 0.0 && xSx < INFINITY) ? 1.0 : 0.0;
+    double rho_new = rho_p, scn = sc, res = INFINITY, res2 = INFINITY;
+    if (good != 0.0) {
+        rho_new = xHx / xSx;
+        scn = 1.0 / sqrt(xSx);
+        res = resmax * scn;
+        res2 = sqrt(rr2) * scn;
+    }
+    g.xmax[id] = xabs;
+    g.rho_prev[id] = rho_p;
+    g.rho[id] = rho_new;
+    g.scale[id] = scn;
+    g.res[id] = res;
+    g.res2[id] = res2;
+    double sig = (rho_new > lo && rho_new < hi) ? rho_new : 0.5 * (lo + hi);
+    if (corr_next > 0) {
+        double gp = g.gap[id];
+        if (!(gp > 0.0) || !(gp < INFINITY)) gp = fmax(hi - lo, fabs(rho_new) * 1e-6 + 1e-12);
+        const double delta = g.delta_rel * gp;
+        if (fabs(sig - rho_p) < delta) sig = (rho_p + delta < hi) ? rho_p + delta : rho_p - delta;
+    }
+    g.sigma[id] = sig;
+}
+
 #ifndef BSP_BACK_PF
 #define BSP_BACK_PF 2 /* factor rows in flight per thread in the back sweep */
 #endif
@@ -865,7 +934,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
     constexpr int K1 = B + 1;
     constexpr int FS = 2 * B + 2;
     constexpr int PF = RESID ? 2 * K1 : BSP_BACK_PF; /* rows in flight per thread */
-    constexpr int TR = BSP_TILE_STEPS(B);
+    constexpr int TR = Src::TR;
     static_assert(TR % PF == 0, "tiles hold whole groups of PF steps");
     const size_t id = (size_t)p * g.ldw + (active ? e : 0);
     const int n = g.n, npad = g.npad, ldw = g.ldw;
@@ -1014,30 +1083,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
         g.sigma[id] = sig;
         return;
     }
-    /* bookkeeping + next shift */
-    double lo = g.lo[id], hi = g.hi[id];
-    const double good = (xSx > 0.0 && xSx < INFINITY) ? 1.0 : 0.0;
-    double rho_new = rho_p, scn = sc, res = INFINITY, res2 = INFINITY;
-    if (good != 0.0) {
-        rho_new = xHx / xSx;
-        scn = 1.0 / sqrt(xSx);
-        res = resmax * scn;
-        res2 = sqrt(rr2) * scn;
-    }
-    g.xmax[id] = xabs;
-    g.rho_prev[id] = rho_p;
-    g.rho[id] = rho_new;
-    g.scale[id] = scn;
-    g.res[id] = res;
-    g.res2[id] = res2;
-    double sig = (rho_new > lo && rho_new < hi) ? rho_new : 0.5 * (lo + hi);
-    if (corr_next > 0) {
-        double gp = g.gap[id];
-        if (!(gp > 0.0) || !(gp < INFINITY)) gp = fmax(hi - lo, fabs(rho_new) * 1e-6 + 1e-12);
-        const double delta = g.delta_rel * gp;
-        if (fabs(sig - rho_p) < delta) sig = (rho_p + delta < hi) ? rho_p + delta : rho_p - delta;
-    }
-    g.sigma[id] = sig;
+    bsp_back_finish(g, id, corr_next, sc, rho_p, xSx, xHx, resmax, rr2, xabs);
 }
 
 template <int B>
@@ -1054,6 +1100,208 @@ BSP_HD void bsp_residual_pass(const BspEigChunk &g, int p, int e)
     if (!bsp_refine_active(g, p, e)) return;
     BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
     bsp_back_substitute_rows<B, true>(g, p, e, e, 0, 1, true, src);
+}
+
+/* ------------------------------------------------------------------------- *
+ * Check-pointed B pass (plain solves only: corr_now = 0).  Segments of BSP_CK_STEPS(B) rows, last to first:
+ *   phase A  restore the elimination state from the check-point the forward sweep left (rows 0..B-1 of the pivot
+ *            window, y[0..B], the raw rhs of the following group; row B of the window is re-read from the band) and
+ *            re-eliminate the segment: (zd, l_1..l_B) of its rows go to the scratch;
+ *   phase B  back substitution + column-sweep band matvecs over the segment, exactly the steps of
+ *            bsp_back_substitute_rows with the factor rows taken from the scratch.
+ * Same arithmetic in the same order as the stored-factor pair of sweeps: bit-identical results.
+ * Scratch: `Scr` hands out slot(i), i < BSP_CK_STEPS*(B+1) -- a thread-private array on the host replay, a column of
+ * shared memory in the kernel, where the check-point of the NEXT segment is also prefetched (cp.async) into the
+ * slots phase B has already consumed.
+ * ------------------------------------------------------------------------- */
+template <int B>
+struct BspScratchLocal {
+    static constexpr int SLOTS = BSP_CK_STEPS(B) * (B + 1);
+    double s[SLOTS];
+    BSP_HD double &slot(int i) { return s[i]; }
+    /* check-point values are read straight from global memory: no prefetch on the host */
+    BSP_HD void prefetch(int, const double *) {}
+    BSP_HD void prefetch_commit() {}
+    BSP_HD void prefetch_wait() {}
+    BSP_HD double fetched(int, const double *gp) { return *gp; }
+};
+
+template <int B, class Src, class Scr>
+BSP_HD void bsp_back_ckpt_rows(const BspEigChunk &g, int p, int e, int ls, int iter, int corr_next, bool active, Src &src, Scr &scr)
+{
+    constexpr int K1 = B + 1;
+    constexpr int FS = 2 * B + 2;
+    constexpr int SG = BSP_CK_GROUPS(B);
+    constexpr int ST = BSP_CK_STEPS(B);
+    constexpr int CKD = BSP_CK_DOUBLES(B);
+    constexpr int TR = Src::TR;
+    static_assert(TR == ST, "the check-pointed back sweep takes one segment per tile");
+    constexpr int PRE_ROWS = (CKD + K1 - 1) / K1;   /* scratch rows (from the top) that receive the next check-point */
+    static_assert(PRE_ROWS < ST, "segment too short to prefetch a check-point into its own scratch");
+    const size_t id = (size_t)p * g.ldw + (active ? e : 0);
+    const int n = g.n, npad = g.npad, ldw = g.ldw;
+    const int nseg = npad / ST;
+    const double *__restrict__ Cp = g.CK + (size_t)p * nseg * CKD * ldw + ls;
+    double *__restrict__ Xp = g.X + (size_t)p * g.xrows * ldw + e;
+    double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
+    const double sc = active ? g.scale[id] : 1.0;
+    const double rho_p = active ? g.rho[id] : 0.0;
+    const double sigma = active ? g.sigma[id] : 0.0;
+    const double pivmin = 1e-30 * (g.pbound[p * 4 + 2] + fabs(sigma) * g.pbound[p * 4 + 3]);
+    /* the forward sweep scaled the raw right-hand side when it consumed it: iteration 0 (hashed start vector) by 1,
+     * later ones by the normalisation of the previous vector.  rho' and scale are untouched between the two sweeps. */
+    const double scr_f = (iter == 0) ? 1.0 : sc;
+
+    double yw[K1], xv[K1], hs[K1], ss[K1];
+#pragma unroll
+    for (int i = 0; i < K1; ++i) { yw[i] = 0.0; xv[i] = 0.0; hs[i] = 0.0; ss[i] = 0.0; }
+    double xSx = 0.0, xHx = 0.0, resmax = 0.0, xabs = 0.0, rr2 = 0.0;
+
+    auto back_step = [&](auto tail_c, int j, const double *rowH, const double *rowS, int srow) {
+        constexpr bool TAIL = decltype(tail_c)::value;
+        double ah[K1], as[K1];
+        if (!TAIL) {
+#pragma unroll
+            for (int d = 0; d <= B; ++d) {
+                ah[d] = bsp_ld<Src::GL>(rowH + B + d);
+                as[d] = bsp_ld<Src::GL>(rowS + B + d);
+            }
+        }
+#pragma unroll
+        for (int i = B; i >= 1; --i) { yw[i] = yw[i - 1]; xv[i] = xv[i - 1]; hs[i] = hs[i - 1]; ss[i] = ss[i - 1]; }
+        double xn = 0.0;
+        if (!TAIL) {
+            double yj = scr.slot(srow * K1);
+#pragma unroll
+            for (int i = B; i >= 1; --i) yj = fma(-scr.slot(srow * K1 + i), yw[i], yj);
+            yw[0] = yj;
+            if (j < n) {
+                xn = 0.0 - yj;   /* = fma(0, x_old, -y) of the stored-factor sweep, bit for bit */
+                Xp[(size_t)j * ldw] = xn;
+                xabs = fmax(xabs, fabs(xn));
+            }
+        } else {
+            yw[0] = 0.0;
+        }
+        xv[0] = xn;
+        double h0 = 0.0, s0 = 0.0;
+        if (!TAIL) {
+#pragma unroll
+            for (int d = 1; d <= B; ++d) {
+                hs[d] = fma(ah[d], xn, hs[d]);
+                ss[d] = fma(as[d], xn, ss[d]);
+            }
+#pragma unroll
+            for (int d = 0; d <= B; ++d) {
+                h0 = fma(ah[d], xv[d], h0);
+                s0 = fma(as[d], xv[d], s0);
+            }
+        }
+        hs[0] = h0;
+        ss[0] = s0;
+        const int i = j + B;
+        if (i < n) {
+            const double h = hs[B], sv = ss[B], xi = xv[B];
+            xSx = fma(xi, sv, xSx);
+            xHx = fma(xi, h, xHx);
+            const double r = fma(-rho_p, sv, h);
+            resmax = fmax(resmax, fabs(r));
+            rr2 = fma(r, r, rr2);
+            if (corr_next >= 0) Rp[(size_t)i * ldw] = corr_next ? r : sv;
+        }
+    };
+
+    src.begin_backward_wide(nseg);
+    /* check-point of the last segment: nothing to hide its latency behind */
+    if (active) {
+        const double *ck = Cp + (size_t)(nseg - 1) * CKD * ldw;
+        for (int q = 0; q < CKD; ++q) scr.prefetch((ST - PRE_ROWS) * K1 + q, ck + (size_t)q * ldw);
+        scr.prefetch_commit();
+    }
+    for (int seg = nseg - 1; seg >= 0; --seg) {
+        const double *tH, *tS;   /* band rows seg*ST .. seg*ST + ST + B */
+        src.acquire_backward_wide(seg, nseg, tH, tS);
+        if (active) {
+            const int js = seg * ST;
+            /* ---- phase A: re-eliminate rows js .. js+ST-1 ---- */
+            double w[K1][K1], y[K1], rq[K1];
+            {
+                const double *ck = Cp + (size_t)seg * CKD * ldw;
+                scr.prefetch_wait();
+                int q = 0;
+#pragma unroll
+                for (int r = 0; r < B; ++r) {
+#pragma unroll
+                    for (int c = 0; c < K1; ++c) {
+                        if (c <= r) { w[r][c] = scr.fetched((ST - PRE_ROWS) * K1 + q, ck + (size_t)q * ldw); ++q; } else w[r][c] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < K1; ++r) { y[r] = scr.fetched((ST - PRE_ROWS) * K1 + q, ck + (size_t)q * ldw); ++q; }
+#pragma unroll
+                for (int r = 0; r < K1; ++r) { rq[r] = scr.fetched((ST - PRE_ROWS) * K1 + q, ck + (size_t)q * ldw); ++q; }
+                /* row B of the window: the plain band row js + B */
+#pragma unroll
+                for (int m = 0; m <= B; ++m)
+                    w[B][m] = fma(-sigma, bsp_ld<Src::GL>(tS + (size_t)B * FS + m), bsp_ld<Src::GL>(tH + (size_t)B * FS + m));
+            }
+#pragma unroll
+            for (int gq = 0; gq < SG; ++gq) {
+#pragma unroll
+                for (int t = 0; t < K1; ++t) {
+                    const int jj = gq * K1 + t;
+                    double nh[K1], ns[K1];
+#pragma unroll
+                    for (int m = 0; m <= B; ++m) {
+                        nh[m] = bsp_ld<Src::GL>(tH + (size_t)(jj + K1) * FS + m);
+                        ns[m] = bsp_ld<Src::GL>(tS + (size_t)(jj + K1) * FS + m);
+                    }
+                    /* the right-hand side of row js+jj+K1 matters only while that row belongs to this segment */
+                    const double rnew = (gq + 1 < SG) ? scr_f * rq[t] : 0.0;
+                    double d = w[t][t];
+                    if (fabs(d) < pivmin) d = -pivmin;
+                    const double rinv = BSP_RCP(d);
+                    double col[K1], l[K1];
+                    const double y0 = y[t];
+                    scr.slot(jj * K1) = y0 * rinv;
+#pragma unroll
+                    for (int i = 1; i <= B; ++i) {
+                        col[i] = w[(t + i) % K1][t];
+                        l[i] = col[i] * rinv;
+                        scr.slot(jj * K1 + i) = l[i];
+                        y[(t + i) % K1] = fma(-l[i], y0, y[(t + i) % K1]);
+                    }
+#pragma unroll
+                    for (int m = 1; m <= B; ++m) {
+#pragma unroll
+                        for (int i = m; i <= B; ++i) {
+                            w[(t + i) % K1][(t + m) % K1] = fma(-l[i], col[m], w[(t + i) % K1][(t + m) % K1]);
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m <= B; ++m) w[t][(t + 1 + m) % K1] = fma(-sigma, ns[m], nh[m]);
+                    y[t] = rnew;
+                }
+            }
+            /* ---- phase B: back substitution + matvecs, last row of the segment first ---- */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int jj = ST - 1; jj >= 0; --jj) {
+                back_step(BspFalse(), js + jj, tH + (size_t)jj * FS, tS + (size_t)jj * FS, jj);
+                if (jj == ST - PRE_ROWS && seg > 0) {
+                    /* the top PRE_ROWS scratch rows are consumed: the next check-point goes in flight into them */
+                    const double *ck = Cp + (size_t)(seg - 1) * CKD * ldw;
+                    for (int q = 0; q < CKD; ++q) scr.prefetch((ST - PRE_ROWS) * K1 + q, ck + (size_t)q * ldw);
+                    scr.prefetch_commit();
+                }
+            }
+        }
+        src.release_backward_wide(seg, nseg);
+    }
+    if (!active) return;
+    for (int j = -1; j >= -B; --j) back_step(BspTrue(), j, nullptr, nullptr, 0);
+    bsp_back_finish(g, id, corr_next, sc, rho_p, xSx, xHx, resmax, rr2, xabs);
 }
 
 /* convergence bookkeeping after a B / residual pass (separate tiny kernel): marks eigenpairs whose scaled residual

@@ -15,7 +15,7 @@
  *   void factor(int iter, int optional);      // F pass (optional: compacted to the eigenpairs the last check listed,
  *                                             //         skipped once everything converged)
  *   void back(int iter, int corr_now, int corr_next, int optional);
- *   void resid();                             // residual of the current vectors against their own Rayleigh quotient
+ *   void resid(int optional);                 // residual of the current vectors against their own Rayleigh quotient
  *   void check(int iter, int select);         // convergence marks, compaction list of what is left, bookkeeping
  */
 #ifndef BSP_DRIVER_H
@@ -53,9 +53,14 @@ inline void bsp_enqueue_chunk(Exec &ex, const BspSchedule &sch)
     for (int t = 0; t < sch.max_iters; ++t) {
         const int optional = (t >= sch.min_iters);
         const bool resid_follows = (t == 1 && select);
+        /* compacted passes do not write the next right-hand side (scattered 8-byte stores, and the pass after the
+         * first correction is almost never needed): when one more is needed, a residual pass over what is left
+         * rebuilds it first */
+        const bool lean = select && optional;
+        if (lean && t > sch.min_iters) ex.resid(1);
         ex.factor(t, optional);
-        ex.back(t, t >= 2, resid_follows ? -1 : (t + 1 >= 2), optional);
-        if (resid_follows) ex.resid();
+        ex.back(t, t >= 2, (resid_follows || lean) ? -1 : (t + 1 >= 2), optional);
+        if (resid_follows) ex.resid(0);
         if (t + 1 >= sch.min_iters) ex.check(t, resid_follows ? 1 : 0);
     }
 }

@@ -69,11 +69,11 @@ __device__ __forceinline__ bool bsp_last_block(int *arrive)
  * reads of the steps of tile t stay inside tile t.  Without the staging the leading warp of an SM pays the
  * L2 latency on every new row and the other warps queue up behind it.
  * ------------------------------------------------------------------------- */
-template <int B>
+template <int B, int G = BSP_TILE_GROUPS(B)>
 struct BspTile {
     static constexpr int K1 = B + 1;
     static constexpr int FS = 2 * B + 2;
-    static constexpr int TR = BSP_TILE_STEPS(B);  /* steps per tile                         */
+    static constexpr int TR = G * (B + 1);        /* steps per tile                         */
     static constexpr int ROWS = TR + K1;          /* band rows staged per (forward) tile    */
     static constexpr int DOUBLES = ROWS * FS;     /* per matrix                             */
     static constexpr unsigned ROW_BYTES = FS * 8u; /* 16(B+1): bulk copies stay 16-byte aligned */
@@ -115,10 +115,11 @@ __device__ __forceinline__ void bsp_mbar_expect(uint64_t *bar, unsigned bytes)
 
 /* row source of the sweeps (see BspRowsGlobal): tiles staged in shared memory.  One object per sweep; every
  * thread of the block calls the same sequence (the release is a block barrier), thread 0 drives the copies. */
-template <int B, int RING = 0>
+template <int B, int RING = 0, int G = BSP_TILE_GROUPS(B)>
 struct BspRowsStaged {
-    using T = BspTile<B>;
+    using T = BspTile<B, G>;
     static constexpr bool GL = false;
+    static constexpr int TR = T::TR;
     static constexpr int RHS_RING = RING;   /* groups of the right-hand side in flight (factor kernel) */
     double *sm;
     uint64_t *bars;   /* two mbarriers, count 1, not used by an earlier sweep of this launch */
@@ -196,6 +197,29 @@ struct BspRowsStaged {
     {
         __syncthreads();
         if (threadIdx.x == 0 && t - 2 >= 0) issue_backward(t - 2, ntiles);
+    }
+    /* backward order with forward-sized tiles (rows t*TR .. t*TR + ROWS - 1): the check-pointed back sweep
+     * re-eliminates a tile (needs the B+1 rows beyond it) before it back-substitutes it */
+    __device__ __forceinline__ void issue_backward_wide(int t, int ntiles)
+    {
+        issue(ntiles - 1 - t, gH + (size_t)t * T::TR * T::FS, gS + (size_t)t * T::TR * T::FS, T::ROWS, 0);
+    }
+    __device__ __forceinline__ void begin_backward_wide(int ntiles)
+    {
+        if (threadIdx.x == 0) {
+            fence_before_first_copy();
+            issue_backward_wide(ntiles - 1, ntiles);
+            if (ntiles > 1) issue_backward_wide(ntiles - 2, ntiles);
+        }
+    }
+    __device__ __forceinline__ void acquire_backward_wide(int t, int ntiles, const double *&tH, const double *&tS)
+    {
+        acquire(ntiles - 1 - t, tH, tS);
+    }
+    __device__ __forceinline__ void release_backward_wide(int t, int ntiles)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0 && t - 2 >= 0) issue_backward_wide(t - 2, ntiles);
     }
 };
 
@@ -392,12 +416,73 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) b
     bsp_back_substitute_rows<B>(g, p, e, ls, corr_now, corr_next, active, src);
 }
 
+/* ---- check-pointed solves (full-width iterations 0 and 1) ---------------------------------------------------- */
+template <int B>
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_ckpt_kernel(BspEigChunk g, int iter)
+{
+    __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
+    constexpr int RING = bsp_rhs_ring(B);
+    __shared__ __align__(16) double ring[(RING + 1) * (B + 1) * BSP_EIG_THREADS];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = bsp_refine_active(g, p, e);
+    bsp_stage_bars_init(bars);
+    if (!__syncthreads_or(active)) return;
+    constexpr int FS = 2 * B + 2;
+    BspRowsStaged<B, RING> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    src.rq = ring + threadIdx.x;
+    bsp_factor_forward_rows<B, true>(g, p, e, e, iter, active, src);
+}
+
+/* scratch of the check-pointed back sweep: one column of shared memory per thread (slot i at base[i * blockDim.x]:
+ * conflict-free), also the landing zone of the asynchronous copy of the next check-point */
+struct BspScratchShared {
+    double *base;
+    int nt;
+    __device__ __forceinline__ double &slot(int i) { return base[(size_t)i * nt]; }
+    __device__ __forceinline__ void prefetch(int i, const double *gp)
+    {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(bsp_smem_u32(base + (size_t)i * nt)), "l"(gp) : "memory");
+    }
+    __device__ __forceinline__ void prefetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ void prefetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    __device__ __forceinline__ double fetched(int i, const double *) { return base[(size_t)i * nt]; }
+};
+
+#ifndef BSP_CKB_THREADS
+#define BSP_CKB_THREADS 128
+#endif
+#ifndef BSP_CKB_MINB
+#define BSP_CKB_MINB 2
+#endif
+template <int B>
+constexpr size_t bsp_back_ckpt_smem(int threads)
+{
+    return (size_t)(BspTile<B, BSP_CK_GROUPS(B)>::SMEM_DOUBLES + BSP_CK_STEPS(B) * (B + 1) * threads) * sizeof(double);
+}
+template <int B>
+__global__ void __launch_bounds__(BSP_CKB_THREADS, BSP_CKB_MINB) bsp_back_ckpt_kernel(BspEigChunk g, int iter, int corr_next)
+{
+    extern __shared__ __align__(128) double dsm[];
+    __shared__ __align__(8) uint64_t bars[2];
+    using T = BspTile<B, BSP_CK_GROUPS(B)>;
+    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = bsp_refine_active(g, p, e);
+    bsp_stage_bars_init(bars);
+    if (!__syncthreads_or(active)) return;
+    constexpr int FS = 2 * B + 2;
+    BspRowsStaged<B, 0, BSP_CK_GROUPS(B)> src{dsm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    BspScratchShared scr{dsm + T::SMEM_DOUBLES + threadIdx.x, (int)blockDim.x};
+    bsp_back_ckpt_rows<B>(g, p, e, e, iter, corr_next, active, src, scr);
+}
+
 /* residual of the vectors in X against their own Rayleigh quotient (after the second solve) */
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_resid_kernel(BspEigChunk g)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_resid_kernel(BspEigChunk g, int optional)
 {
     __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
     __shared__ __align__(8) uint64_t bars[2];
+    if (optional && g.counters[BSP_C_REFINED]) return;
     const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = bsp_refine_active(g, p, e);
     bsp_stage_bars_init(bars);

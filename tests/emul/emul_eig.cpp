@@ -16,6 +16,7 @@ struct EmulExec {
     std::vector<double> cand_s;
     std::vector<int> cand_c;
     int cur_iter = 0, open_ok = 0;
+    int ckpt = 0;   /* 1: the full-width solves (iterations 0, 1) run check-pointed, like the kernels for B <= 6 */
     void bounds() {
         cand_s.assign(g.npencil * BSP_NCAND, 0.0);
         cand_c.assign(g.npencil * BSP_NCAND, 0);
@@ -59,17 +60,25 @@ struct EmulExec {
         if (optional && g.counters[BSP_C_REFINED]) return;
         for_each_active(it, optional, [&](int p, int e, int ls) {
             BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
-            bsp_factor_forward_rows<B>(g, p, e, ls, it, true, src);
+            if (ckpt && it < 2) bsp_factor_forward_rows<B, true>(g, p, e, ls, it, true, src);
+            else bsp_factor_forward_rows<B>(g, p, e, ls, it, true, src);
         });
     }
     void back(int it, int cn, int cx, int optional) {
         if (optional && g.counters[BSP_C_REFINED]) return;
         for_each_active(it, optional, [&](int p, int e, int ls) {
-            BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
-            bsp_back_substitute_rows<B>(g, p, e, ls, cn, cx, true, src);
+            if (ckpt && it < 2) {
+                BspRowsGlobal<B, BSP_CK_GROUPS(B)> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
+                BspScratchLocal<B> scr;
+                bsp_back_ckpt_rows<B>(g, p, e, ls, it, cx, true, src, scr);
+            } else {
+                BspRowsGlobal<B> src{g.fbH + (size_t)p * g.nrows * (2 * B + 2), g.fbS + (size_t)g.inst[p] * g.nrows * (2 * B + 2)};
+                bsp_back_substitute_rows<B>(g, p, e, ls, cn, cx, true, src);
+            }
         });
     }
-    void resid() {
+    void resid(int optional) {
+        if (optional && g.counters[BSP_C_REFINED]) return;
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_residual_pass<B>(g, p, e);
     }
@@ -118,6 +127,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     std::vector<int> samp_fe(2 * per), fle(per), fhe(per), side(per);
     std::vector<double> L((size_t)npencil * g.npad * K1 * g.ldw), X((size_t)npencil * g.xrows * g.ldw, 0.0),
         R((size_t)npencil * g.xrows * g.ldw, 0.0);
+    std::vector<double> CK((size_t)npencil * (g.npad / BSP_CK_STEPS(B)) * BSP_CK_DOUBLES(B) * g.ldw);
     g.fbH = fbH.data(); g.fbS = fbS.data(); g.inst = inst.data(); g.nvec = nvec.data();
     g.pbound = pbound.data(); g.lo = lo.data(); g.hi = hi.data(); g.clo = clo.data(); g.chi = chi.data();
     g.samp_s = samp_s.data(); g.samp_c = samp_c.data(); g.gap = gap.data(); g.done = done.data();
@@ -126,7 +136,8 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     g.sigma = sigma.data(); g.rho = rho.data(); g.rho_prev = rho_prev.data(); g.scale = scale.data();
     g.res = res.data(); g.res2 = res2.data(); g.rlist = rlist.data(); g.rcount = rcount.data(); g.vec_tol = vec_tol; g.xmax = xmax.data(); g.status = status.data(); g.L = L.data(); g.X = X.data(); g.R = R.data();
     g.counters = counters.data(); g.tau = tau; g.delta_rel = delta_rel; g.conv_tol = conv_tol;
-    EmulExec<B> ex; ex.g = g;
+    g.CK = CK.data();
+    EmulExec<B> ex; ex.g = g; ex.ckpt = getenv("BSP_EMUL_CKPT") ? atoi(getenv("BSP_EMUL_CKPT")) : 0;
     BspSchedule sch = {max_rounds, min_iters, max_iters};
     bsp_enqueue_chunk(ex, sch);
     BspRunStats st = {counters[BSP_C_ROUNDS], counters[BSP_C_ITERS], counters[BSP_C_OPEN_END], counters[BSP_C_CROWDED_END],

@@ -246,6 +246,25 @@ def test_other_orders_solve(atom, oracle, k, nfun, grid):
     check_eigenpairs(Es[0], Cs[0], H, S, res_tol=1e-11, orth_tol=1e-9)
 
 
+@pytest.mark.parametrize("k,nfun", [(7, 260), (5, 131), (3, 64), (8, 150), (10, 97)])
+def test_check_pointed_solves_are_bit_identical_to_stored_factor(atom, k, nfun):
+    """option `ckpt`: the two full-width solves run check-pointed (elimination state every 1-2 groups of k rows
+    instead of the factor, re-elimination into shared memory in the back sweep; default for k <= 7) -- same
+    arithmetic in the same order as the stored-factor sweeps, so the results must agree bit for bit."""
+    a = host_basis(kind_grid=0, k=k, nfun=nfun, rb=130.0)
+    items = [(a.problem(), l) for l in range(3)]
+    out = {}
+    try:
+        for mode in (0, 1):
+            atom.set_option("ckpt", mode)
+            out[mode] = atom.solve_batch(items)
+    finally:
+        atom.set_option("ckpt", -1)
+    assert not out[0][2].any() and not out[1][2].any()
+    for x, y in zip(out[0][0] + out[0][1], out[1][0] + out[1][1]):
+        assert np.array_equal(x, y)
+
+
 def test_third_solve_selection_against_the_full_schedule(atom, oracle):
     """Default schedule (two solves + residual pass, correction pass compacted to the eigenpairs with
     ||r||_2 / gap > vec_tol) against min_iters = 3 (everybody gets the correction pass, the round-1 schedule) and
