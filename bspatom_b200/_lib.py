@@ -19,8 +19,8 @@ EXPORTS = [
     "bspatom_create", "bspatom_destroy", "bspatom_last_error", "bspatom_version", "bspatom_set_option",
     "bspatom_alloc_host", "bspatom_free_host",
     "bspatom_assemble_band", "bspatom_solve_batch", "bspatom_batch_upload", "bspatom_batch_run",
-    "bspatom_batch_download", "bspatom_batch_verify", "bspatom_dsygv_", "bspatom_dipole", "bspatom_dipole_chain", "bspatom_trans_amp_hermitian",
-    "bspatom_wavefunction", "bspatom_get_stats",
+    "bspatom_batch_download", "bspatom_get_selection", "bspatom_batch_verify", "bspatom_dsygv_", "bspatom_dipole", "bspatom_dipole_chain", "bspatom_dipole_chain_resident",
+    "bspatom_trans_amp_hermitian", "bspatom_wavefunction", "bspatom_wavefunction_resident", "bspatom_get_stats",
 ]
 
 
@@ -33,6 +33,8 @@ class BspProblem(C.Structure):
         ("pot_kind", C.c_int), ("pot_par", C.c_double * 8),
         ("v_tab", _dp),
         ("l", C.c_int), ("ul_extra", C.c_double), ("nvec", C.c_int),
+        ("sel_mode", C.c_int), ("sel_extra", C.c_int), ("sel_group", C.c_int),
+        ("sel_ecut_a", C.c_double), ("sel_ecut_b", C.c_double),
     ]
 
 
@@ -69,6 +71,7 @@ def load():
     L.bspatom_batch_run.argtypes = [H]
     L.bspatom_batch_download.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bspatom_batch_verify.argtypes = [H, _dp]
+    L.bspatom_get_selection.argtypes = [H, C.c_void_p]
     L.bspatom_dsygv_.argtypes = [_ip, C.c_char_p, C.c_char_p, _ip, C.c_void_p, _ip, C.c_void_p, _ip,
                                  C.c_void_p, C.c_void_p, _ip, _ip]
     L.bspatom_dsygv_.restype = None
@@ -79,6 +82,9 @@ def load():
                                               C.c_void_p]
     L.bspatom_wavefunction.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bspatom_dipole_chain_resident.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.bspatom_wavefunction_resident.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                                C.c_void_p, C.c_void_p]
     L.bspatom_get_stats.argtypes = [H, _dp, C.c_int]
     _lib = L
     return L

@@ -69,6 +69,14 @@ struct Group {
     BspInstParams *d_par = nullptr;
     double *d_fbS = nullptr, *d_fbH0 = nullptr, *d_fbQ = nullptr;
     int *d_inst = nullptr, *d_nvec = nullptr, *d_pdinfo = nullptr, *d_bad = nullptr;
+    /* device-side state selection (bsp_problem.sel_mode): per pencil rule, the nvec the bracketing sees (0 where
+     * the selection needs every eigenvalue to rounding first) and the nvec the refinement sees (written by the
+     * selection kernel); sel_off = offset of this group's counts in the handle's mapped selection mailbox */
+    bool any_sel = false;
+    std::vector<BspSelect> sel;
+    BspSelect *d_sel = nullptr;
+    int *d_nvec_br = nullptr, *d_nvec_eff = nullptr;
+    size_t sel_off = 0;
     double *d_cl = nullptr, *d_E = nullptr, *d_C = nullptr;
     long long *d_coff = nullptr;
     std::vector<int> pdinfo, bad;
@@ -103,6 +111,9 @@ struct bspatom_handle_s {
      * D2H transfer -- which would queue behind the bulk eigenvector copies of this or another handle. */
     int *h_counter = nullptr;     /* pinned + mapped, BSP_MAIL_INTS ints */
     int *h_counter_dev = nullptr; /* device view of h_counter */
+    int *h_sel = nullptr, *h_sel_dev = nullptr;   /* pinned + mapped: eigenvectors selected per pencil (device-written) */
+    size_t h_sel_cap = 0;
+    long long c_bytes_copied = 0; /* eigenvector bytes the last run sent to the host */
     size_t budget_bytes = 0;      /* workspace budget of this handle (decided on the first run) */
     bool mail_info = false;       /* the mailbox holds pdinfo / bad of the last run (see run_internal) */
     double stats[24] = {0};
@@ -186,6 +197,9 @@ void free_group(bspatom_handle h, Group &g)
     dev_free(h, g.d_fbQ, per_mat * g.ninst);
     dev_free(h, g.d_inst, (size_t)g.npencil);
     dev_free(h, g.d_nvec, (size_t)g.npencil);
+    dev_free(h, g.d_sel, (size_t)g.npencil);
+    dev_free(h, g.d_nvec_br, (size_t)g.npencil);
+    dev_free(h, g.d_nvec_eff, (size_t)g.npencil);
     dev_free(h, g.d_pdinfo, (size_t)g.ninst);
     dev_free(h, g.d_bad, (size_t)g.npencil);
     dev_free(h, g.d_cl, (size_t)g.npencil);
@@ -247,6 +261,8 @@ int validate_problem(const bsp_problem &p)
     if (p.pot_kind == BSPATOM_POT_TABLE && !p.v_tab) return -3;
     if (p.nvec < 0 || p.nvec > p.nfun) return -3;
     if (p.l < 0) return -3;
+    if (p.sel_mode != 0 && p.sel_mode != 1) return -3;
+    if (p.sel_mode == 1 && (p.sel_extra < 0 || !(p.sel_ecut_a == p.sel_ecut_a) || !(p.sel_ecut_b == p.sel_ecut_b))) return -3;
     return 0;
 }
 
@@ -389,6 +405,14 @@ struct GpuExec {
         bsp_round_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, r, max_rounds, open_ok); note();
         timed_end(h, s);
     }
+    const BspSelect *d_sel = nullptr;   /* selection rules of the chunk's pencils, or null */
+    int *d_nvec_eff = nullptr, *sel_report = nullptr;
+    cudaEvent_t ev_selected = nullptr;  /* recorded behind the selection kernel: the host sizes the copies with its counts */
+    void select() {
+        if (!d_sel) return;
+        bsp_select_kernel<<<1, 1, 0, h->st>>>(g, d_sel, d_nvec_eff, sel_report); note();
+        if (ev_selected) cudaEventRecord(ev_selected, h->st);
+    }
     void prepare() {
         if (ev_refine) cudaEventRecord(ev_refine, h->st);
         bsp_prepare_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g); note();
@@ -427,6 +451,8 @@ struct GpuExec {
 
 struct ChunkTimes {
     cudaEvent_t ev[4];
+    cudaEvent_t selected = nullptr;   /* owned by the caller; null when the group has no selection */
+    int *sel_report = nullptr;        /* device view of the selection mailbox slots of this chunk's pencils */
 };
 
 /* carve the chunk workspace out of one allocation */
@@ -494,7 +520,9 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     BspEigChunk g;
     memset(&g, 0, sizeof g);
     g.n = G.n; g.npad = G.npad; g.nrows = G.nrows; g.xrows = G.xrows; g.ldw = G.ldw; g.npencil = np;
-    g.fbH = c.fbH; g.fbS = G.d_fbS; g.inst = G.d_inst + p0; g.nvec = G.d_nvec + p0;
+    g.fbH = c.fbH; g.fbS = G.d_fbS; g.inst = G.d_inst + p0;
+    g.nvec = (G.any_sel ? G.d_nvec_eff : G.d_nvec) + p0;
+    g.nvec_br = (G.any_sel ? G.d_nvec_br : G.d_nvec) + p0;
     g.pbound = c.pbound; g.lo = c.lo; g.hi = c.hi; g.clo = c.clo; g.chi = c.chi;
     g.samp_s = c.samp_s; g.samp_c = c.samp_c; g.gap = c.gap; g.done = c.done;
     g.samp_fm = c.samp_fm; g.samp_fe = c.samp_fe; g.flm = c.flm; g.fhm = c.fhm; g.fle = c.fle; g.fhe = c.fhe; g.side = c.side; g.beta = c.beta;
@@ -506,6 +534,11 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     GpuExec<B> ex;
     ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.ev_refine = tm.ev[1];
     ex.ckpt = (c.CK != nullptr);
+    if (G.any_sel) {
+        ex.d_sel = G.d_sel + p0; ex.d_nvec_eff = G.d_nvec_eff + p0;
+        ex.sel_report = tm.sel_report;
+        ex.ev_selected = tm.selected;
+    }
     /* a few stragglers per hundred thousand eigenpairs are cheaper to finish inside the refinement */
     ex.open_ok = (int)((long long)np * G.n / 20000);
     bsp_zero_words_kernel<<<1, 32, 0, h->st>>>(c.counters, BSP_C_WORDS);
@@ -635,6 +668,7 @@ void free_context(bspatom_handle h)
     if (h->ws.base) cudaFree(h->ws.base);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_counter) cudaFreeHost(h->h_counter);
+    if (h->h_sel) cudaFreeHost(h->h_sel);
     for (auto e : h->chunk_done) cudaEventDestroy(e);
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->st) cudaStreamDestroy(h->st);
@@ -804,6 +838,13 @@ int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs)
         G.prob_index.push_back(i);
         G.inst.push_back(inst);
         G.nvec.push_back(p.nvec);
+        {
+            BspSelect sl;
+            sl.mode = p.sel_mode; sl.extra = p.sel_extra; sl.group = p.sel_mode ? p.sel_group : -1; sl.cap = p.nvec;
+            sl.ecut_a = p.sel_ecut_a; sl.ecut_b = p.sel_ecut_b;
+            G.sel.push_back(sl);
+            if (p.sel_mode) G.any_sel = true;
+        }
         G.cl.push_back((double)p.l * (double)(p.l + 1) + 2.0 * p.ul_extra);
         G.coff.push_back(G.c_elems);
         G.c_elems += (long long)p.nfun * p.nvec;
@@ -827,9 +868,30 @@ int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs)
         if ((rc = dev_alloc(h, &G.d_C, (size_t)G.c_elems))) return rc;
         CU(cudaMemcpyAsync(G.d_inst, G.inst.data(), sizeof(int) * G.npencil, cudaMemcpyHostToDevice, h->st));
         CU(cudaMemcpyAsync(G.d_nvec, G.nvec.data(), sizeof(int) * G.npencil, cudaMemcpyHostToDevice, h->st));
+        std::vector<int> nvec_br(G.nvec);
+        if (G.any_sel) {
+            for (int p = 0; p < G.npencil; ++p) if (G.sel[p].mode) nvec_br[p] = 0;
+            if ((rc = dev_alloc(h, &G.d_sel, G.npencil))) return rc;
+            if ((rc = dev_alloc(h, &G.d_nvec_br, G.npencil))) return rc;
+            if ((rc = dev_alloc(h, &G.d_nvec_eff, G.npencil))) return rc;
+            CU(cudaMemcpyAsync(G.d_sel, G.sel.data(), sizeof(BspSelect) * G.npencil, cudaMemcpyHostToDevice, h->st));
+            CU(cudaMemcpyAsync(G.d_nvec_br, nvec_br.data(), sizeof(int) * G.npencil, cudaMemcpyHostToDevice, h->st));
+            CU(cudaMemcpyAsync(G.d_nvec_eff, G.nvec.data(), sizeof(int) * G.npencil, cudaMemcpyHostToDevice, h->st));
+        }
         CU(cudaMemcpyAsync(G.d_cl, G.cl.data(), sizeof(double) * G.npencil, cudaMemcpyHostToDevice, h->st));
         CU(cudaMemcpyAsync(G.d_coff, G.coff.data(), sizeof(long long) * G.npencil, cudaMemcpyHostToDevice, h->st));
         CU(cudaStreamSynchronize(h->st));
+    }
+    {
+        size_t need = 0;
+        for (auto &G : h->groups) { G.sel_off = need; if (G.any_sel) need += (size_t)G.npencil; }
+        if (need > h->h_sel_cap) {
+            if (h->h_sel) cudaFreeHost(h->h_sel);
+            h->h_sel = nullptr; h->h_sel_cap = 0;
+            CU(cudaHostAlloc((void **)&h->h_sel, sizeof(int) * need, cudaHostAllocMapped));
+            CU(cudaHostGetDevicePointer((void **)&h->h_sel_dev, h->h_sel, 0));
+            h->h_sel_cap = need;
+        }
     }
     h->uploaded = true;
     return 0;
@@ -877,8 +939,23 @@ CopyQueue *copy_queue(int dev)
 }
 
 /* enqueue on `cs` the D2H of pencils [p0, p0+np) of group G into the caller's E / C */
-int copy_chunk_out(bspatom_handle h, Group &G, int p0, int np, double *E, double *C, cudaStream_t cs)
+int copy_chunk_out(bspatom_handle h, Group &G, int p0, int np, double *E, double *C, cudaStream_t cs, const int *nsel = nullptr)
 {
+    if (nsel) {
+        /* device-side selection: E in merged runs, C problem by problem, the selected columns only (a prefix of the
+         * problem's column-major block) */
+        int rc = copy_chunk_out(h, G, p0, np, E, nullptr, cs, nullptr);
+        if (rc) return rc;
+        if (C)
+            for (int p = p0; p < p0 + np; ++p) {
+                const long long nel = (long long)G.n * std::min(nsel[p - p0], G.nvec[p]);
+                if (nel > 0) {
+                    CU(cudaMemcpyAsync(C + h->c_off[G.prob_index[p]], G.d_C + G.coff[p], sizeof(double) * (size_t)nel, cudaMemcpyDeviceToHost, cs));
+                    h->c_bytes_copied += 8 * nel;
+                }
+            }
+        return 0;
+    }
     int p = p0;
     while (p < p0 + np) {
         int q = p;
@@ -891,6 +968,7 @@ int copy_chunk_out(bspatom_handle h, Group &G, int p0, int np, double *E, double
             const long long nel = (q + 1 < G.npencil ? G.coff[q + 1] : G.c_elems) - G.coff[p];
             if (nel > 0) CU(cudaMemcpyAsync(C + h->c_off[i0], G.d_C + G.coff[p], sizeof(double) * (size_t)nel,
                                             cudaMemcpyDeviceToHost, cs));
+            h->c_bytes_copied += 8 * nel;
         }
         p = q + 1;
     }
@@ -976,6 +1054,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     double t_asm = 0, t_val = 0, t_vec = 0, t_fin = 0;
     int rounds = 0, iters = 0, redone = 0;
     long long selected = 0;
+    h->c_bytes_copied = 0;
     cudaEvent_t e0, e1, e2, copies_done;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
     CU(cudaEventCreateWithFlags(&copies_done, cudaEventDisableTiming));
@@ -988,10 +1067,16 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     if (cq) turn = std::unique_lock<std::mutex>(cq->turn);
     if (cq) CU(cudaEventRecord(copies_done, cq->st));
     CU(cudaEventRecord(e0, h->st));
-    const BspSchedule sch = {std::min(h->opt.rounds_enqueued, h->opt.max_rounds), h->opt.min_iters,
-                             std::min(h->opt.max_iters, h->opt.min_iters + 3)};
+    const BspSchedule sch_vec = {std::min(h->opt.rounds_enqueued, h->opt.max_rounds), h->opt.min_iters,
+                                 std::min(h->opt.max_iters, h->opt.min_iters + 3)};
+    /* eigen indices without a vector (nvec < nfun, device-side selection) close their brackets to rounding inside the
+     * bracketing: a tail of ~25 cheap (compacted) rounds beyond the 13 of the hand-over; surplus launches are no-ops */
+    const BspSchedule sch_val = {std::min(std::max(h->opt.rounds_enqueued, 64), h->opt.max_rounds), sch_vec.min_iters, sch_vec.max_iters};
     const BspSchedule sch_redo = {h->opt.max_rounds, h->opt.min_iters, h->opt.max_iters};
     for (auto &G : h->groups) {
+        bool values_only = G.any_sel;
+        for (int p = 0; p < G.npencil && !values_only; ++p) values_only = G.nvec[p] < G.n;
+        const BspSchedule sch = values_only ? sch_val : sch_vec;
         /* ---- assembly, once per instance ---- */
         CU(cudaEventRecord(e1, h->st));
         BspAsmArgs a;
@@ -1071,6 +1156,25 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             chunk = 0;
             for (int i = 0; i < nchunks; ++i) chunk = std::max(chunk, bounds[i + 1] - bounds[i]);
         }
+        if (G.any_sel) {
+            /* the running maximum of a selection group is sequential over its pencils: a group stays in one chunk */
+            for (size_t b = 1; b + 1 < bounds.size(); ++b) {
+                int x = std::max(bounds[b], bounds[b - 1]);
+                while (x < G.npencil && x > 0 && G.sel[x].mode && G.sel[x].group >= 0 && G.sel[x - 1].mode &&
+                       G.sel[x - 1].group == G.sel[x].group) ++x;
+                bounds[b] = x;
+            }
+            std::vector<int> nb(1, 0);
+            for (size_t b = 1; b < bounds.size(); ++b) if (bounds[b] > nb.back()) nb.push_back(bounds[b]);
+            bounds = nb;
+            nchunks = (int)bounds.size() - 1;
+            chunk = 0;
+            for (int i = 0; i < nchunks; ++i) chunk = std::max(chunk, bounds[i + 1] - bounds[i]);
+            if (chunk > std::max(cap, 1) && h->opt.chunk <= 0) {
+                h->err = "a selection group (sel_group) has more pencils than fit one chunk of the workspace";
+                return BSPATOM_ENOMEM;
+            }
+        }
         workers = std::min(workers, nchunks);
         const size_t need = carve_chunk(G, chunk, nullptr, c, use_ckpt(h, G));
         if ((rc = ensure_workspace(h, need))) return rc;
@@ -1092,8 +1196,15 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         if (report_mail) d_report = h->h_counter_dev;
         else if ((rc = dev_alloc(h, &d_report, (size_t)nchunks * BSP_C_WORDS))) return rc;
         std::vector<ChunkTimes> tms(nchunks);
-        for (int ci = 0; ci < nchunks; ++ci)
+        for (int ci = 0; ci < nchunks; ++ci) {
             for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tms[ci].ev[i]));
+            if (G.any_sel) {
+                CU(cudaEventCreateWithFlags(&tms[ci].selected, cudaEventDisableTiming));
+                tms[ci].sel_report = h->h_sel_dev + G.sel_off + bounds[ci];
+            }
+        }
+        std::vector<cudaEvent_t> final_ev(nchunks, nullptr);   /* selection mode: chunk final, copies not yet enqueued */
+        std::vector<bspatom_handle> chunk_ctx(nchunks, nullptr);
         struct TraceRec { int ci, w, np; cudaEvent_t done, c0, c1; };
         std::vector<TraceRec> trace;
         std::vector<long long> load(workers, 0);      /* pencils assigned to each stream so far */
@@ -1113,7 +1224,12 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
                 if (x != h) h->err = x->err;
                 return rc;
             }
-            if (E_out || C_out) {
+            chunk_ctx[ci] = x;
+            if ((E_out || C_out) && G.any_sel) {
+                /* the copies are sized by the selection: enqueued below, once the chunk's counts are in the mailbox */
+                CU(cudaEventCreateWithFlags(&final_ev[ci], cudaEventDisableTiming));
+                CU(cudaEventRecord(final_ev[ci], x->st));
+            } else if (E_out || C_out) {
                 if (h->opt.trace) {     /* diagnostics: when was the chunk final, when did its copy run */
                     TraceRec tr = {ci, wsel, np, nullptr, nullptr, nullptr};
                     CU(cudaEventCreate(&tr.done)); CU(cudaEventCreate(&tr.c0)); CU(cudaEventCreate(&tr.c1));
@@ -1124,6 +1240,17 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
                     CU(cudaEventRecord(tr.c1, cq->st));
                     trace.push_back(tr);
                 } else if ((rc = stream_chunk_out(h, x, G, p0, np, E_out, C_out, cq->st))) return rc;
+            }
+        }
+        if (streaming && G.any_sel) {
+            for (int ci = 0; ci < nchunks; ++ci) {
+                /* the selection kernel of the chunk ran right after its bracketing: its counts are in the mapped
+                 * mailbox long before the vectors are final */
+                CU(cudaEventSynchronize(tms[ci].selected));
+                CU(cudaStreamWaitEvent(cq->st, final_ev[ci], 0));
+                h->chunk_done.push_back(final_ev[ci]);
+                if ((rc = copy_chunk_out(h, G, bounds[ci], bounds[ci + 1] - bounds[ci], E_out, C_out, cq->st,
+                                         h->h_sel + G.sel_off + bounds[ci]))) return rc;
             }
         }
         if (streaming) {
@@ -1168,12 +1295,17 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
                 const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
                 CU(cudaMemsetAsync(G.d_bad + p0, 0, sizeof(int) * np, h->st));
                 if ((rc = enqueue_chunk(h, G, p0, np, cc, sch_redo, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) return rc;
-                if (streaming) {
+                if (streaming && !G.any_sel) {
                     std::lock_guard<std::mutex> lk(cq->mu);
                     if ((rc = stream_chunk_out(h, h, G, p0, np, E_out, C_out, cq->st))) return rc;
                     CU(cudaEventRecord(copies_done, cq->st));
                 }
                 CU(cudaStreamSynchronize(h->st));
+                if (streaming && G.any_sel) {      /* the redone chunk's counts are in the mailbox now */
+                    std::lock_guard<std::mutex> lk(cq->mu);
+                    if ((rc = copy_chunk_out(h, G, p0, np, E_out, C_out, cq->st, h->h_sel + G.sel_off + p0))) return rc;
+                    CU(cudaEventRecord(copies_done, cq->st));
+                }
                 if (report_mail) memcpy(&report[(size_t)ci * BSP_C_WORDS], h->h_counter + (size_t)ci * BSP_C_WORDS, BSP_C_WORDS * sizeof(int));
                 else CU(cudaMemcpy(&report[(size_t)ci * BSP_C_WORDS], d_report + (size_t)ci * BSP_C_WORDS, BSP_C_WORDS * sizeof(int),
                                    cudaMemcpyDeviceToHost));
@@ -1188,8 +1320,10 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             CU(cudaEventElapsedTime(&ms, tms[ci].ev[2], tms[ci].ev[3])); t_fin += ms;
         }
         for (auto x : ctx) timed_collect(x);
-        for (int ci = 0; ci < nchunks; ++ci)
+        for (int ci = 0; ci < nchunks; ++ci) {
             for (int i = 0; i < 4; ++i) cudaEventDestroy(tms[ci].ev[i]);
+            if (tms[ci].selected) cudaEventDestroy(tms[ci].selected);
+        }
         if (!report_mail) dev_free(h, d_report, (size_t)nchunks * BSP_C_WORDS);
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, e1, e2)); t_asm += ms;
@@ -1231,7 +1365,7 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         h->stats[12 + i] = (double)h->k_cnt[i];
         for (auto x : h->aux) { h->stats[8 + i] += x->k_ms[i]; h->stats[12 + i] += (double)x->k_cnt[i]; }
     }
-    h->stats[19] = redone; h->stats[20] = (double)selected;
+    h->stats[19] = redone; h->stats[20] = (double)selected; h->stats[22] = (double)h->c_bytes_copied;
     h->ran = true;
     return 0;
 }
@@ -1258,6 +1392,10 @@ int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info)
             CU(cudaMemcpyAsync(G.pdinfo.data(), G.d_pdinfo, sizeof(int) * G.ninst, cudaMemcpyDeviceToHost, h->st));
             CU(cudaMemcpyAsync(G.bad.data(), G.d_bad, sizeof(int) * G.npencil, cudaMemcpyDeviceToHost, h->st));
         }
+        if (G.any_sel) {   /* selected columns only */
+            if ((rc = copy_chunk_out(h, G, 0, G.npencil, E, C, h->st, h->h_sel + G.sel_off))) return rc;
+            continue;
+        }
         /* pencils of a group are usually contiguous in the caller's order: merge runs */
         int p = 0;
         while (p < G.npencil) {
@@ -1283,6 +1421,18 @@ int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info)
                 info[G.prob_index[p]] = pd ? G.n + pd : G.bad[p];
             }
     }
+    return 0;
+}
+
+int bspatom_get_selection(bspatom_handle h, int *nsel)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!nsel) return -2;
+    if (!h->ran) { h->err = "get_selection before a run"; return BSPATOM_ESTATE; }
+    for (auto &G : h->groups)
+        for (int p = 0; p < G.npencil; ++p)
+            nsel[G.prob_index[p]] = G.any_sel ? std::min(h->h_sel[G.sel_off + p], G.nvec[p]) : G.nvec[p];
     return 0;
 }
 

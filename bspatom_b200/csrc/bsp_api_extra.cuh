@@ -261,6 +261,120 @@ int bspatom_dipole_chain(bspatom_handle h, int n, int kd, const double *A_band, 
     return 0;
 }
 
+/* locate caller problem i of the resident batch: group, pencil */
+static bool find_resident(bspatom_handle h, int i, Group *&Gout, int &pout)
+{
+    for (auto &G : h->groups)
+        for (int p = 0; p < G.npencil; ++p)
+            if (G.prob_index[p] == i) { Gout = &G; pout = p; return true; }
+    return false;
+}
+
+/* eigenvectors computed for pencil p by the last run */
+static int resident_nvec(bspatom_handle h, const Group &G, int p)
+{
+    return G.any_sel ? std::min(h->h_sel[G.sel_off + p], G.nvec[p]) : G.nvec[p];
+}
+
+/* cfg5 on the eigenvectors the last run LEFT IN HBM (no host round trip of the 8 MB blocks: the reference's TRANS_AMP
+ * reads Hij / cinl in place, PhotoIon.f90:90-105): D_l = C_{i0+l+1}(:, 1:nvec)^T A C_{i0+l}(:, 1:nvec), l = 0..nl-2,
+ * over the nl consecutive problems i0 .. i0+nl-1 of the resident batch. */
+int bspatom_dipole_chain_resident(bspatom_handle h, int i0, int nl, int nvec, int kd, const double *A_band, double *D_all)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!h->ran) { h->err = "dipole_chain_resident before a run"; return BSPATOM_ESTATE; }
+    if (i0 < 0 || i0 + nl > h->nprob) return -2;
+    if (nl < 2) return -3;
+    if (nvec < 1) return -4;
+    if (!A_band) return -6;
+    if (!D_all) return -7;
+    Group *G = nullptr;
+    int p0 = 0;
+    if (!find_resident(h, i0, G, p0)) return -2;
+    const int n = G->n;
+    if (kd < 0 || kd >= n) return -5;
+    std::vector<const double *> blocks(nl);
+    bool uniform = true;
+    for (int l = 0; l < nl; ++l) {
+        Group *Gl = nullptr;
+        int pl = 0;
+        if (!find_resident(h, i0 + l, Gl, pl) || Gl != G) { h->err = "dipole_chain_resident: problems of different shapes"; return -2; }
+        if (resident_nvec(h, *G, pl) < nvec) { h->err = "dipole_chain_resident: fewer eigenvectors resident than asked for"; return -4; }
+        blocks[l] = G->d_C + G->coff[pl];
+        if (l > 0 && blocks[l] - blocks[l - 1] != blocks[1] - blocks[0]) uniform = false;
+    }
+    const int ld = 2 * kd + 1;
+    const size_t yblk = (size_t)n * nvec, dblk = (size_t)nvec * nvec;
+    double *d_A = nullptr, *d_Y = nullptr, *d_D = nullptr;
+    if ((rc = dev_alloc(h, &d_A, (size_t)ld * n))) return rc;
+    if ((rc = dev_alloc(h, &d_Y, yblk * (nl - 1)))) return rc;
+    if ((rc = dev_alloc(h, &d_D, dblk * (nl - 1)))) return rc;
+    CU(cudaMemcpyAsync(d_A, A_band, sizeof(double) * (size_t)ld * n, cudaMemcpyHostToDevice, h->st));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, h->st));
+    if (uniform) {
+        const long long cs = (long long)(blocks[1] - blocks[0]);
+        bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, nvec, nl - 1), 128, 0, h->st>>>(n, kd, d_A, nvec, blocks[0], d_Y, cs, (long long)yblk);
+        CU(cudaGetLastError());
+        CU(bsp_launch_dgemm_tn(h->st, nvec, nvec, n, blocks[1], n, d_Y, n, d_D, nvec, nl - 1, cs, (long long)yblk, (long long)dblk));
+        h->launches += 2;
+    } else {
+        for (int l = 0; l + 1 < nl; ++l) {
+            bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, nvec, 1), 128, 0, h->st>>>(n, kd, d_A, nvec, blocks[l], d_Y + yblk * l);
+            CU(cudaGetLastError());
+            CU(bsp_launch_dgemm_tn(h->st, nvec, nvec, n, blocks[l + 1], n, d_Y + yblk * l, n, d_D + dblk * l, nvec, 1, 0, 0, 0));
+            h->launches += 2;
+        }
+    }
+    CU(cudaEventRecord(e1, h->st));
+    CU(cudaMemcpyAsync(D_all, d_D, sizeof(double) * dblk * (nl - 1), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    h->stats[23] = ms;    /* device time of the contraction alone (the solver's own stats stay in place) */
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dev_free(h, d_A, (size_t)ld * n); dev_free(h, d_Y, yblk * (nl - 1)); dev_free(h, d_D, dblk * (nl - 1));
+    return 0;
+}
+
+/* WRITE_WF on eigenvectors still resident: psi(ip, iv) for the vectors ivec0 .. ivec0+nvec-1 of problem iprob of
+ * the last batch, on the problem's own knots (Bsp_Atom.f90:101-152 reads Hij(:, n0_ini) in place). */
+int bspatom_wavefunction_resident(bspatom_handle h, int iprob, int ivec0, int nvec, double ra, double rb, int npts,
+                                  double *r_out, double *psi_out)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!h->ran) { h->err = "wavefunction_resident before a run"; return BSPATOM_ESTATE; }
+    Group *G = nullptr;
+    int p = 0;
+    if (iprob < 0 || iprob >= h->nprob || !find_resident(h, iprob, G, p)) return -2;
+    if (ivec0 < 0 || nvec < 1 || ivec0 + nvec > resident_nvec(h, *G, p)) return -3;
+    if (npts < 1 || !r_out || !psi_out) return -6;
+    double *d_r = nullptr, *d_psi = nullptr;
+    if ((rc = dev_alloc(h, &d_r, (size_t)npts + 1))) return rc;
+    if ((rc = dev_alloc(h, &d_psi, (size_t)(npts + 1) * nvec))) return rc;
+    const double *d_rt = G->d_rt + (size_t)G->inst[p] * G->nkp;
+    const double *d_C = G->d_C + G->coff[p] + (size_t)ivec0 * G->n;
+    switch (G->k) {
+    case 3: launch_wavefunction<3>(h, G->n, G->nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 4: launch_wavefunction<4>(h, G->n, G->nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 5: launch_wavefunction<5>(h, G->n, G->nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 6: launch_wavefunction<6>(h, G->n, G->nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 7: launch_wavefunction<7>(h, G->n, G->nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 8: launch_wavefunction<8>(h, G->n, G->nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    case 9: launch_wavefunction<9>(h, G->n, G->nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    default: launch_wavefunction<10>(h, G->n, G->nkp, d_rt, ra, rb, npts, nvec, d_C, d_r, d_psi); break;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(r_out, d_r, sizeof(double) * ((size_t)npts + 1), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(psi_out, d_psi, sizeof(double) * (size_t)(npts + 1) * nvec, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    dev_free(h, d_r, (size_t)npts + 1); dev_free(h, d_psi, (size_t)(npts + 1) * nvec);
+    return 0;
+}
+
 /* General (structured-light) branch of TRANS_AMP, PhotoIon.f90:218-232: for one angular block (il, jl, component)
  * the reference loops over every (bra, ket) pair and calls ZHVMV = ZHEMV('U') + ZDOTU (Modules.f90:398-425) on the
  * N x N complex block zAij(:,:,il,jl,i) with the REAL eigenvectors as zx, zy.  ZHEMV('U') reads the upper triangle

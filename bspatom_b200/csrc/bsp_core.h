@@ -126,7 +126,10 @@ struct BspEigChunk {
     const double *fbH; /* [npencil][nrows][FS]  H_l = H0 + c_l Q  */
     const double *fbS; /* [ninst][nrows][FS]                      */
     const int *inst;   /* [npencil] instance of each pencil       */
-    const int *nvec;   /* [npencil] eigenvectors wanted           */
+    const int *nvec;   /* [npencil] eigenvectors wanted (with device-side selection: written by bsp_select_states
+                          after the bracketing, <= the caller's cap)                                         */
+    const int *nvec_br; /* [npencil] the same as seen by the bracketing: the caller's nvec, or zeros when the
+                          selection needs every eigenvalue to rounding before it can decide */
     double *pbound;    /* [npencil][4]  lo0, hi0, hmax, smax      */
     /* bracket state, double buffered: index (buf*npencil + p)*ldw + e */
     double *lo, *hi;
@@ -482,7 +485,7 @@ BSP_HD void bsp_round_begin(const BspEigChunk &g, int p, int e, int round, BspRo
     int done = was_done;
     if (!done) {
         if (wdt <= 4.0 * BSP_EPS * amax + 1e-300) done = 1;
-        else if (e < g.nvec[p] && gp > 0.0 && wdt <= g.tau * gp) done = 1;
+        else if (e < g.nvec_br[p] && gp > 0.0 && wdt <= g.tau * gp) done = 1;
     }
     st.lo = lo; st.hi = hi; st.flm = flm; st.fhm = fhm; st.beta = beta; st.gp = gp; st.wdt = wdt;
     st.clo = clo; st.chi = chi; st.fle = fle; st.fhe = fhe; st.side = side; st.done = done; st.was_done = was_done;
@@ -619,7 +622,7 @@ BSP_HD void bsp_round_end(const BspEigChunk &g, int p, int e, int round, BspRoun
         /* counters[0]: brackets still open; counters[2]: open AND not yet isolating one eigenvalue.  An eigen
          * index whose vector is not wanted (e >= nvec) is never touched by the refinement: its bracket must
          * close here, so it counts as crowded until it does (no hand-over while any is open). */
-        const int crowded = (st.chi - st.clo != 1 || !(st.gp > 0.0) || e >= g.nvec[p]) ? 1 : 0;
+        const int crowded = (st.chi - st.clo != 1 || !(st.gp > 0.0) || e >= g.nvec_br[p]) ? 1 : 0;
 #if defined(__CUDA_ARCH__)
         atomicAdd(g.counters + BSP_C_OPEN, 1);
         if (crowded) atomicAdd(g.counters + BSP_C_CROWDED, 1);
@@ -681,6 +684,59 @@ BSP_HD void bsp_check_ctl(const BspEigChunk &g, int iter)
     c[BSP_C_UNCONV] = 0;
     /* the list the check of iteration iter + 1 appends to starts empty */
     if (g.rcount) for (int p = 0; p < g.npencil; ++p) g.rcount[((iter + 1) & 1) * g.npencil + p] = 0;
+}
+
+/* ------------------------------------------------------------------------- *
+ * Device-side state selection: which eigenvectors SOLVE_SYSTEM keeps (matrices.f90:296-334, KIND_PI >= 3 branch):
+ *   n1_fin = #{E <= Emax_fin} + 1,  ntemp_raw = #{E <= Elim},  nlim = max over the l done so far of ntemp_raw,
+ *   ntemp  = MIN(MAX(n1_fin + 40, nlim), nfun)        -> ctemp(:, 1:ntemp, l) = Hij(:, 1:ntemp)
+ * With sel.mode = 1 the bracketing closes EVERY bracket to rounding first (nvec_br = 0), so the counts below are
+ * taken on final eigenvalues and equal the reference's; the refinement then only computes columns 1..ntemp.
+ * One thread walks the pencils of the chunk in the caller's order (the running maximum nlim is sequential over
+ * l; pencils of one selection group are kept in one chunk).
+ * ------------------------------------------------------------------------- */
+struct BspSelect {
+    int mode;      /* 0: keep the caller's nvec */
+    int extra;     /* 41 for the reference's "n1_fin + 40" (n1_fin itself is the count + 1) */
+    int group;     /* running-maximum group (>= 0) or -1 */
+    int cap;       /* the caller's nvec: upper limit */
+    double ecut_a; /* Emax_fin */
+    double ecut_b; /* Elim     */
+};
+
+BSP_HD int bsp_count_below(const double *lo, const double *hi, int n, double cut)
+{
+    /* #{e: E_e <= cut}, E_e = bracket midpoint, ascending */
+    int a = -1, b = n;
+    while (b - a > 1) {
+        const int m = (a + b) >> 1;
+        if (0.5 * (lo[m] + hi[m]) <= cut) a = m; else b = m;
+    }
+    return a + 1;
+}
+
+BSP_HD void bsp_select_states(const BspEigChunk &g, const BspSelect *sel, int *nvec_out, int *nsel_report)
+{
+    const int buf = g.counters[BSP_C_BUF];
+    const size_t per = (size_t)g.npencil * g.ldw;
+    int cur_group = -2, runmax = 0;
+    for (int p = 0; p < g.npencil; ++p) {
+        const BspSelect s = sel[p];
+        int nv = s.cap;
+        if (s.mode == 1) {
+            const double *lo = g.lo + (size_t)buf * per + (size_t)p * g.ldw, *hi = g.hi + (size_t)buf * per + (size_t)p * g.ldw;
+            const int ca = bsp_count_below(lo, hi, g.n, s.ecut_a), cb = bsp_count_below(lo, hi, g.n, s.ecut_b);
+            if (s.group != cur_group) { cur_group = s.group; runmax = 0; }
+            if (cb > runmax) runmax = cb;
+            int want = ca + s.extra;
+            if (s.group >= 0 && runmax > want) want = runmax;
+            else if (s.group < 0 && cb > want) want = cb;
+            nv = want < s.cap ? want : s.cap;
+            if (nv < 0) nv = 0;
+        }
+        nvec_out[p] = nv;
+        if (nsel_report) nsel_report[p] = nv;
+    }
 }
 
 /* ------------------------------------------------------------------------- *

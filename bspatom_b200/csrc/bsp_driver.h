@@ -11,6 +11,7 @@
  * Exec must provide:
  *   void bounds();                            // bracket [lo0,hi0] per pencil
  *   void round(int r, int max_rounds);        // one bracketing round + its bookkeeping
+ *   void select();                            // device-side state selection (no-op unless the batch asks for it)
  *   void prepare();                           // hand brackets to the refinement
  *   void factor(int iter, int optional);      // F pass (optional: compacted to the eigenpairs the last check listed,
  *                                             //         skipped once everything converged)
@@ -41,6 +42,7 @@ inline void bsp_enqueue_chunk(Exec &ex, const BspSchedule &sch)
 {
     ex.bounds();
     for (int r = 0; r < sch.rounds; ++r) ex.round(r, sch.rounds);
+    ex.select();
     ex.prepare();
     /* iteration t: plain for t < 2 (inverse iteration at the bracket midpoint, then at the Rayleigh quotient),
      * residual-correction form afterwards.  Default (min_iters = 2): after the second solve one cheap residual pass

@@ -15,14 +15,16 @@
 /* Y(i, v) = sum_j A(i,j) Ci(j, v),  A in LAPACK general band storage
  * AB[(kd + i - j) + j*ld], ld = 2kd+1.  i fastest over threads: coalesced. */
 __global__ void bsp_band_times_dense_kernel(int n, int kd, const double *__restrict__ AB, int nv,
-                                            const double *__restrict__ Ci, double *__restrict__ Y)
+                                            const double *__restrict__ Ci, double *__restrict__ Y,
+                                            long long strideC = -1, long long strideY = -1)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
     if (i >= n || v >= nv) return;
     const int ld = 2 * kd + 1;
-    Ci += (size_t)blockIdx.z * n * nv;     /* batch of vector blocks sharing the operator */
-    Y += (size_t)blockIdx.z * n * nv;
+    /* batch of vector blocks sharing the operator (default: blocks of n x nv back to back) */
+    Ci += (size_t)blockIdx.z * (strideC < 0 ? (long long)n * nv : strideC);
+    Y += (size_t)blockIdx.z * (strideY < 0 ? (long long)n * nv : strideY);
     const double *x = Ci + (size_t)v * n;
     double s = 0.0;
     const int j0 = max(0, i - kd), j1 = min(n - 1, i + kd);

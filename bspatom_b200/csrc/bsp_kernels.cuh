@@ -351,6 +351,14 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) 
     }
 }
 
+/* device-side state selection of the chunk (one thread: the running maximum over l is sequential); the counts also
+ * go to the mapped mailbox, from which the host sizes the result copies while the refinement runs */
+__global__ void bsp_select_kernel(BspEigChunk g, const BspSelect *sel, int *nvec_eff, int *report)
+{
+    bsp_select_states(g, sel, nvec_eff, report);
+    __threadfence_system();
+}
+
 __global__ void bsp_prepare_kernel(BspEigChunk g)
 {
     bsp_refine_prepare(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);

@@ -263,7 +263,8 @@ class BspAtom(BspInputs):
         keys = ["launches", "rounds", "iters", "ms_assembly", "ms_eigenvalues", "ms_eigenvectors", "ms_finalize",
                 "ms_total", "ms_k_round", "ms_k_factor", "ms_k_back", "ms_k_assembly",
                 "n_k_round", "n_k_factor", "n_k_back", "n_k_assembly", "wall_ms_upload", "wall_ms_run",
-                "wall_ms_download", "chunks_redone", "selected_third_solve", "wall_ms_copy_tail"]
+                "wall_ms_download", "chunks_redone", "selected_third_solve", "wall_ms_copy_tail", "c_bytes_copied",
+                "ms_resident_contraction"]
         return dict(zip(keys, list(out)))
 
     # ---- MATRIX_SVT (matrices.f90:1-200) ------------------------------------------------
@@ -317,13 +318,17 @@ class BspAtom(BspInputs):
             postproc.write_eigenvec_all(os.path.join(directory, "Eigenvec_All.dat"), cinl)
 
     def solve_batch(self, items: Iterable, nvec: Optional[int] = None, want_vectors: bool = True,
-                    out_E: Optional[np.ndarray] = None, out_C: Optional[np.ndarray] = None):
-        """items: iterable of (Problem, l).  Returns (list of E arrays, list of C arrays, info)."""
+                    out_E: Optional[np.ndarray] = None, out_C: Optional[np.ndarray] = None,
+                    select: Optional["Selection"] = None):
+        """items: iterable of (Problem, l).  Returns (list of E arrays, list of C arrays, info).
+        select: device-side state selection (Selection): C blocks keep the shape (nfun, nvec) but only the first
+        ``self.selection()[i]`` columns of block i are computed and copied out."""
         items = list(items)
-        arr, keep = build_problem_array(items, nvec)
+        arr, keep = build_problem_array(items, nvec, select)
         nfs, nvs = arr.rec["nfun"].astype(np.int64), arr.rec["nvec"].astype(np.int64)
         n_e = int(nfs.sum())
         n_c = int((nfs * nvs).sum())
+        self._last_items = items
         E = out_E if out_E is not None else pinned_empty(n_e)
         Cbuf = (out_C if out_C is not None else pinned_empty(n_c)) if want_vectors else None
         info = np.zeros(len(items), dtype=np.int32)
@@ -340,9 +345,18 @@ class BspAtom(BspInputs):
         return Es, Cs, info
 
     # staged variant: keeps the batch resident in HBM (bench.py times batch_run alone)
-    def batch_upload(self, items: Iterable, nvec: Optional[int] = None):
+    def selection(self) -> np.ndarray:
+        """eigenvectors computed per problem by the last run (bspatom_get_selection)"""
+        n = len(self._last_items)
+        out = np.zeros(n, dtype=np.int32)
+        _lib.check(self.lib, self._h, self.lib.bspatom_get_selection(self._h, out.ctypes.data_as(C.c_void_p)),
+                   "bspatom_get_selection")
+        return out
+
+    def batch_upload(self, items: Iterable, nvec: Optional[int] = None, select: Optional["Selection"] = None):
         items = list(items)
-        arr, keep = build_problem_array(items, nvec)
+        self._last_items = items
+        arr, keep = build_problem_array(items, nvec, select)
         rc = self.lib.bspatom_batch_upload(self._h, len(items), arr)
         _lib.check(self.lib, self._h, rc, "bspatom_batch_upload")
         self._resident = (items, arr.rec["nvec"].copy())
@@ -436,6 +450,30 @@ def _dipole_chain(self, A_band: np.ndarray, C_blocks) -> np.ndarray:
 
 
 BspAtom.dipole_chain = _dipole_chain
+
+
+def _dipole_chain_resident(self, A_band: np.ndarray, i0: int, nl: int, nvec: int) -> np.ndarray:
+    """cfg5 on the eigenvectors the last batch left in HBM: D[l] = C[i0+l+1]^T A C[i0+l] (first nvec vectors each)."""
+    A_band = np.asfortranarray(A_band, dtype=np.float64)
+    kd = (A_band.shape[0] - 1) // 2
+    D = np.empty((nl - 1, nvec, nvec))
+    rc = self.lib.bspatom_dipole_chain_resident(self._h, int(i0), int(nl), int(nvec), kd,
+                                                A_band.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p))
+    _lib.check(self.lib, self._h, rc, "bspatom_dipole_chain_resident")
+    return np.transpose(D, (0, 2, 1))
+
+
+def _wavefunction_resident(self, iprob: int, ivec0: int, nvec: int, ra: float, rb: float, npts: int = 10000):
+    r = np.empty(npts + 1)
+    psi = np.empty((npts + 1, nvec), order="F")
+    rc = self.lib.bspatom_wavefunction_resident(self._h, int(iprob), int(ivec0), int(nvec), float(ra), float(rb), int(npts),
+                                                r.ctypes.data_as(C.c_void_p), psi.ctypes.data_as(C.c_void_p))
+    _lib.check(self.lib, self._h, rc, "bspatom_wavefunction_resident")
+    return r, psi
+
+
+BspAtom.dipole_chain_resident = _dipole_chain_resident
+BspAtom.wavefunction_resident = _wavefunction_resident
 
 
 class BspAtomPipeline:
@@ -544,22 +582,55 @@ def _to_c_problem(p: Problem, l: int, nvec: int, keep: list) -> BspProblem:
 
 
 _PROBLEM_DTYPE = np.dtype({
-    "names": ["k", "nfun", "nkp", "ka", "rt", "xg", "wg", "pot_kind", "pot_par", "v_tab", "l", "ul_extra", "nvec"],
-    "formats": ["<i4", "<i4", "<i4", "<i4", "<u8", "<u8", "<u8", "<i4", ("<f8", 8), "<u8", "<i4", "<f8", "<i4"],
+    "names": ["k", "nfun", "nkp", "ka", "rt", "xg", "wg", "pot_kind", "pot_par", "v_tab", "l", "ul_extra", "nvec",
+              "sel_mode", "sel_extra", "sel_group", "sel_ecut_a", "sel_ecut_b"],
+    "formats": ["<i4", "<i4", "<i4", "<i4", "<u8", "<u8", "<u8", "<i4", ("<f8", 8), "<u8", "<i4", "<f8", "<i4",
+                "<i4", "<i4", "<i4", "<f8", "<f8"],
     "offsets": [BspProblem.k.offset, BspProblem.nfun.offset, BspProblem.nkp.offset, BspProblem.ka.offset,
                 BspProblem.rt.offset, BspProblem.xg.offset, BspProblem.wg.offset, BspProblem.pot_kind.offset,
                 BspProblem.pot_par.offset, BspProblem.v_tab.offset, BspProblem.l.offset,
-                BspProblem.ul_extra.offset, BspProblem.nvec.offset],
+                BspProblem.ul_extra.offset, BspProblem.nvec.offset, BspProblem.sel_mode.offset,
+                BspProblem.sel_extra.offset, BspProblem.sel_group.offset, BspProblem.sel_ecut_a.offset,
+                BspProblem.sel_ecut_b.offset],
     "itemsize": C.sizeof(BspProblem),
 })
 
 
-def build_problem_array(items: List, nvec: Optional[int]):
+@dataclass
+class Selection:
+    """Device-side state selection of SOLVE_SYSTEM's KIND_PI >= 3 branch (matrices.f90:296-334): keep the
+    eigenvectors 1..ntemp, ntemp = MIN(MAX(n1_fin + 40, nlim), nfun).  Emax_fin / Elim as in the reference
+    (Elim = Emax_fin + 0.25, or Emax_fin for KIND_PI >= 8); one running-maximum group per distinct Problem,
+    its items in the order of the reference's l loop."""
+
+    Emax_fin: float
+    Elim: Optional[float] = None
+    extra: int = 41          # n1_fin + 40 with n1_fin = count + 1
+
+    @classmethod
+    def from_kind_pi(cls, Emax_fin: float, kind_pi: int):
+        return cls(Emax_fin, Emax_fin if kind_pi >= 8 else Emax_fin + 0.25)
+
+
+def build_problem_array(items: List, nvec: Optional[int], select: Optional["Selection"] = None):
     """(Problem, l) list -> contiguous array of struct bsp_problem (numpy structured array with the
     C layout; filled per distinct Problem, not per item: a sweep has few instances and many l)."""
     keep: list = []
     n = len(items)
     rec = np.zeros(n, dtype=_PROBLEM_DTYPE)
+    if select is not None:
+        rec["sel_mode"] = 1
+        rec["sel_extra"] = int(select.extra)
+        rec["sel_ecut_a"] = float(select.Emax_fin)
+        rec["sel_ecut_b"] = float(select.Emax_fin if select.Elim is None else select.Elim)
+        gid, seen, last = np.zeros(n, dtype=np.int32), {}, None
+        for i, (p, _) in enumerate(items):       # contiguous runs of one Problem form a group
+            if last is None or id(p) != last:
+                seen[i] = len(seen)
+                cur = seen[i]
+                last = id(p)
+            gid[i] = cur
+        rec["sel_group"] = gid
     groups: dict = {}
     for i, (p, l) in enumerate(items):
         groups.setdefault(id(p), (p, []))[1].append(i)

@@ -69,7 +69,21 @@ typedef struct bsp_problem {
                             (1-based m = 1..nkp-1) at v_tab[(m-1)*ka + g]        */
     int l;            /* angular momentum: U_l = [l(l+1) + 2 ul_extra] / (2 r^2)  */
     double ul_extra;  /* Bl(l) for KIND_POT=2 (matrices.f90:151), else 0          */
-    int nvec;         /* leading eigenvectors wanted, 0..nfun                     */
+    int nvec;         /* leading eigenvectors wanted, 0..nfun (upper limit when sel_mode = 1) */
+    /* Optional device-side state selection: what SOLVE_SYSTEM keeps of Hij for KIND_PI >= 3
+     * (matrices.f90:296-334): ctemp(:, 1:ntemp, l), ntemp = MIN(MAX(n1_fin + 40, nlim), nfun) with
+     * n1_fin = #{En <= Emax_fin} + 1 and nlim = the largest #{En <= Elim} of the l solved so far.
+     * sel_mode = 1: every eigenvalue is still returned to rounding, but only the eigenvectors
+     *   1 .. MIN(nvec, MAX(#{E <= sel_ecut_a} + sel_extra, running max over the group of #{E <= sel_ecut_b}))
+     * are computed and copied out; problems of one group (same sel_group >= 0, contiguous in the array, in the
+     * order of the reference's l loop) share the running maximum.  The reference's numbers: sel_ecut_a = Emax_fin,
+     * sel_extra = 41, sel_ecut_b = Elim (= Emax_fin + 0.25, or Emax_fin for KIND_PI >= 8).  C keeps its layout
+     * (nfun x nvec per problem); columns beyond the selected count are not written.  sel_mode = 0: off. */
+    int sel_mode;
+    int sel_extra;
+    int sel_group;
+    double sel_ecut_a;
+    double sel_ecut_b;
 } bsp_problem;
 
 /* ---- handle ------------------------------------------------------------- */
@@ -120,6 +134,9 @@ int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs);
 int bspatom_batch_run(bspatom_handle h);
 int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info);
 
+/* eigenvectors computed per problem by the last run (= nvec unless sel_mode = 1): nsel[nprob] */
+int bspatom_get_selection(bspatom_handle h, int *nsel);
+
 /* device-side check of the resident batch (after bspatom_batch_run): out[0] = max scaled residual
  * |H_l c - E S c|_inf / max(1,|E|) over EVERY eigenpair, out[1] = max |C^T S C - I| over every pencil,
  * out[2] = 0 when every spectrum is strictly ascending, out[3] = eigenpairs checked.  What the host would
@@ -148,6 +165,12 @@ int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf
 int bspatom_dipole_chain(bspatom_handle h, int n, int kd, const double *A_band, int nl, int nvec,
                          const double *C_all, double *D_all);
 
+/* the same on the eigenvectors the last run left in HBM (no host round trip of the 8 MB blocks; the reference's
+ * TRANS_AMP reads Hij / cinl in place): problems i0 .. i0+nl-1 of the resident batch (equal nfun, at least nvec
+ * eigenvectors each), D_all as above; out of bspatom_get_stats: out[23] = device ms of the contraction.      */
+int bspatom_dipole_chain_resident(bspatom_handle h, int i0, int nl, int nvec, int kd, const double *A_band,
+                                  double *D_all);
+
 /* ---- general branch of TRANS_AMP (structured light), PhotoIon.f90:218-232 ------ *
  * One angular block zAij(:,:,il,jl,i) against all (bra, ket) pairs at once:
  *   T(nf,ni) = Cf^T * ZHEMV_U(zA) * Ci   (what ZHVMV = ZHEMV('U') + ZDOTU, Modules.f90:398-425, gives pair by pair:
@@ -162,6 +185,11 @@ int bspatom_trans_amp_hermitian(bspatom_handle h, int n, int kd, const double *z
 int bspatom_wavefunction(bspatom_handle h, int k, int nfun, int nkp, const double *rt, double ra,
                          double rb, int npts, int nvec, const double *C, double *r_out,
                          double *psi_out);
+
+/* the same for eigenvectors ivec0 .. ivec0+nvec-1 of problem iprob of the resident batch, on its own knots
+ * (WRITE_WF reads Hij(:, n0_ini) in place, matrices.f90:266)                      */
+int bspatom_wavefunction_resident(bspatom_handle h, int iprob, int ivec0, int nvec, double ra, double rb,
+                                  int npts, double *r_out, double *psi_out);
 
 /* ---- statistics of the last run (for bench.py) ----------------------------- *
  * out[0] kernel launches, out[1] multisection rounds, out[2] refinement

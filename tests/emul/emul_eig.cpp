@@ -36,6 +36,9 @@ struct EmulExec {
         }
         bsp_round_ctl(g, r, max_rounds, open_ok);
     }
+    const BspSelect *sel = nullptr;
+    int *nvec_eff = nullptr;
+    void select() { if (sel) bsp_select_states(g, sel, nvec_eff, nullptr); }
     void prepare() {
         for (int p = 0; p < g.npencil; ++p)
             for (int e = 0; e < g.n; ++e) bsp_refine_prepare(g, p, e);
@@ -128,7 +131,7 @@ static int run(int n, int npencil, const double *hb, const double *sb, const int
     std::vector<double> L((size_t)npencil * g.npad * K1 * g.ldw), X((size_t)npencil * g.xrows * g.ldw, 0.0),
         R((size_t)npencil * g.xrows * g.ldw, 0.0);
     std::vector<double> CK((size_t)npencil * (g.npad / BSP_CK_STEPS(B)) * BSP_CK_DOUBLES(B) * g.ldw);
-    g.fbH = fbH.data(); g.fbS = fbS.data(); g.inst = inst.data(); g.nvec = nvec.data();
+    g.fbH = fbH.data(); g.fbS = fbS.data(); g.inst = inst.data(); g.nvec = nvec.data(); g.nvec_br = nvec.data();
     g.pbound = pbound.data(); g.lo = lo.data(); g.hi = hi.data(); g.clo = clo.data(); g.chi = chi.data();
     g.samp_s = samp_s.data(); g.samp_c = samp_c.data(); g.gap = gap.data(); g.done = done.data();
     g.samp_fm = samp_fm.data(); g.samp_fe = samp_fe.data(); g.flm = flm.data(); g.fhm = fhm.data();

@@ -73,9 +73,22 @@ def test_library_exports_every_header_symbol():
     assert lib.bspatom_version() == 100
 
 
-def test_struct_layout_matches_header():
-    # bsp_problem: 4 int, 3 ptr, int(+pad), 8 double, ptr, int(+pad), double, int(+pad)
-    assert ctypes.sizeof(_lib.BspProblem) == 16 + 24 + 8 + 64 + 8 + 8 + 8 + 8
+def test_struct_layout_matches_header(tmp_path):
+    """the ctypes mirror of struct bsp_problem against the C compiler's view of include/bspatom.h: size and the
+    offset of every field"""
+    import subprocess
+
+    fields = [f for f, _ in _lib.BspProblem._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bspatom.h"\nint main(void){\n'
+                   'printf("%zu\\n", sizeof(bsp_problem));\n' +
+                   "".join('printf("%%zu\\n", offsetof(bsp_problem, %s));\n' % f for f in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(_lib.BspProblem)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(_lib.BspProblem, f).offset == off, f
 
 
 def test_no_cpu_fallback_without_device():
