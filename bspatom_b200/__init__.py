@@ -7,6 +7,6 @@ binding), ``host`` (mirror of the reference driver's interface), ``parallel`` (s
 from ._lib import BspAtomError, LIB_PATH, load  # noqa: F401
 from .host import (BspAtom, BspAtomPipeline, BspInputs, Problem, Selection, dsygv, parse_namelists,  # noqa: F401
                    POT_COULOMB, POT_ROGERS, POT_SIMONS_FUES, POT_TABLE, POT_TIETZ, POT_YUKAWA)
-from .parallel import gather_eigenpairs, shard_items  # noqa: F401
+from .parallel import gather_eigenpairs, gather_eigenpairs_device, shard_items  # noqa: F401
 
 __version__ = "0.1.0"

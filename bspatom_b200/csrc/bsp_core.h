@@ -59,6 +59,7 @@ __device__ __forceinline__ double bsp_drcp(double x)
 #endif
 
 #define BSP_EPS 2.220446049250313e-16
+#define BSP_ABS_CLOSE 2e-14   /* absolute bracket width (Hartree) at which a bracket counts as closed */
 
 /* rows stored per band matrix: the sweeps bring in row j+B+1 at step j and
  * prefetch one row further, so npad + B + 2 rows exist (padding rows are
@@ -484,7 +485,9 @@ BSP_HD void bsp_round_begin(const BspEigChunk &g, int p, int e, int round, BspRo
     const double amax = fmax(fabs(lo), fabs(hi));
     int done = was_done;
     if (!done) {
-        if (wdt <= 4.0 * BSP_EPS * amax + 1e-300) done = 1;
+        /* closed to rounding; near-zero levels to BSP_ABS_CLOSE Hartree (north star: 1e-10 absolute for near-zero levels):
+         * relative to |E| ~ 1e-4 the counts are noise long before 4 eps |E|, and the bracket would creep for 60+ rounds */
+        if (wdt <= fmax(4.0 * BSP_EPS * amax, BSP_ABS_CLOSE)) done = 1;
         else if (e < g.nvec_br[p] && gp > 0.0 && wdt <= g.tau * gp) done = 1;
     }
     st.lo = lo; st.hi = hi; st.flm = flm; st.fhm = fhm; st.beta = beta; st.gp = gp; st.wdt = wdt;
@@ -577,6 +580,14 @@ BSP_HD void bsp_round_pick(BspRoundState &st, double bsum)
         }
     }
     double s = st.lo + st.wdt * frac;
+    if (secant) {
+        /* an estimate that is numerically ON one end (root within an ulp of it: the other end then crept towards it
+         * by bisection, one bit per round, for 20+ rounds) is sampled two ulps inside instead: one count closes
+         * the bracket to rounding */
+        const double tiny = 2.0 * BSP_EPS * fmax(fabs(st.lo), fabs(st.hi));
+        if (s - st.lo < tiny) s = st.lo + tiny;
+        if (st.hi - s < tiny) s = st.hi - tiny;
+    }
     if (!(s > st.lo && s < st.hi)) { s = st.lo + 0.5 * st.wdt; secant = false; }
     st.side = secant ? kind : 0;
     st.beta = st.wdt;
@@ -1425,7 +1436,7 @@ BSP_HD void bsp_finalize_eigen(const BspEigChunk &g, int p, int e, double *E, do
         const double lo = g.lo[id], hi = g.hi[id];
         E[(size_t)p * g.n + e] = 0.5 * (lo + hi);
         fac[id] = 0.0;
-        if (!(hi - lo <= 16.0 * BSP_EPS * fmax(fabs(lo), fabs(hi)) + 1e-300)) {
+        if (!(hi - lo <= fmax(16.0 * BSP_EPS * fmax(fabs(lo), fabs(hi)), 4.0 * BSP_ABS_CLOSE))) {
 #if defined(__CUDA_ARCH__)
             atomicAdd(bad + p, 1);
 #else

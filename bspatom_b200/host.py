@@ -378,6 +378,14 @@ class BspAtom(BspInputs):
         return {"max_scaled_residual": out[0], "max_orthonormality_defect": out[1], "not_ascending": out[2],
                 "eigenpairs_checked": int(out[3])}
 
+    def batch_download_ptrs(self, E_ptr: int, C_ptr: Optional[int], info: Optional[np.ndarray] = None):
+        """bspatom_batch_download with raw (host or DEVICE) destination addresses, e.g. torch CUDA tensors'
+        data_ptr(): the eigenpairs stay on the GPU (send buffers of the NCCL gather)."""
+        rc = self.lib.bspatom_batch_download(self._h, C.c_void_p(E_ptr) if E_ptr else None,
+                                             C.c_void_p(C_ptr) if C_ptr else None,
+                                             info.ctypes.data_as(C.c_void_p) if info is not None else None)
+        _lib.check(self.lib, self._h, rc, "bspatom_batch_download")
+
     # ---- WRITE_WF (Bsp_Atom.f90:101-152) ------------------------------------------------
     def WRITE_WF(self, ci: np.ndarray, npts: int = 10000):
         ci = np.asarray(ci, dtype=np.float64)

@@ -64,6 +64,34 @@ def gather_eigenpairs(E_local: np.ndarray, idx_local: Sequence[int], nitems: int
     return E, Cm
 
 
+def gather_eigenpairs_device(E_dev, C_dev=None, dst: int = 0):
+    """The single collective of the path on DEVICE buffers: every rank contributes E_dev (nloc, nfun) and,
+    optionally, C_dev (nloc, ncols * nfun: the selected eigenvector columns of its pencils, e.g. filled by
+    BspAtom.batch_download_ptrs straight from the solver's resident blocks) -- torch CUDA tensors with the same
+    shape on every rank; rank ``dst`` receives them over NCCL / NVLink (ncclSend/Recv under dist.gather) as
+    (world, nloc, ...) tensors that stay on its GPU for the writers.  Returns (E_all, C_all) on dst, (None, None)
+    elsewhere, plus the bytes this rank put on the wire."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return E_dev.unsqueeze(0), (None if C_dev is None else C_dev.unsqueeze(0)), 0
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sent = 0
+    outs = []
+    for t in (E_dev, C_dev):
+        if t is None:
+            outs.append(None)
+            continue
+        t = t.contiguous()
+        recv = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        dist.gather(t, recv, dst=dst)
+        if rank != dst:
+            sent += t.numel() * t.element_size()
+        outs.append(torch.stack(recv) if rank == dst else None)
+    return outs[0], outs[1], sent
+
+
 def bind_host_memory_to_gpu(pci_bus_id: str) -> dict:
     """One process per GPU: place this process (CPU affinity, as far as the cpuset allows) and its future host
     allocations (memory policy MPOL_PREFERRED) on the NUMA node the GPU hangs off.  The end-to-end path returns

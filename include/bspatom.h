@@ -132,7 +132,9 @@ int bspatom_solve_batch(bspatom_handle h, int nprob, const bsp_problem *probs, d
  * download copies E, C, info D2H.  C may be NULL to skip the eigenvectors.    */
 int bspatom_batch_upload(bspatom_handle h, int nprob, const bsp_problem *probs);
 int bspatom_batch_run(bspatom_handle h);
-int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info);
+int bspatom_batch_download(bspatom_handle h, double *E, double *C, int *info);   /* E, C: host OR device pointers
+                                   (unified addressing: a device destination keeps the eigenpairs on the GPU, e.g. as the
+                                   send buffer of the NCCL gather to the rank that runs the writers) */
 
 /* eigenvectors computed per problem by the last run (= nvec unless sel_mode = 1): nsel[nprob] */
 int bspatom_get_selection(bspatom_handle h, int *nsel);

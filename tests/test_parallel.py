@@ -64,6 +64,50 @@ def test_gather_world2_gloo():
     assert np.array_equal(Cg, np.array([[1000.0 * i + j for j in range(nfun * nvec)] for i in range(nitems)]))
 
 
+def _worker_dev(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from bspatom_b200.parallel import gather_eigenpairs_device
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    E = torch.arange(12, dtype=torch.float64).view(3, 4) + 100 * rank
+    Cc = torch.arange(24, dtype=torch.float64).view(3, 8) + 1000 * rank
+    Eg, Cg, sent = gather_eigenpairs_device(E, Cc, dst=0)
+    if rank == 0:
+        q.put((Eg.numpy(), Cg.numpy()))
+    else:
+        assert Eg is None and Cg is None and sent == 8 * (12 + 24)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tensor_gather_world2_gloo():
+    """gather_eigenpairs_device (the NCCL path of bench.py / tests/gather_worker.py) with CPU tensors over gloo"""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_dev, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    Eg, Cg = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert Eg.shape == (2, 3, 4) and Cg.shape == (2, 3, 8)
+    for r in range(2):
+        assert np.array_equal(Eg[r], np.arange(12.0).reshape(3, 4) + 100 * r)
+        assert np.array_equal(Cg[r], np.arange(24.0).reshape(3, 8) + 1000 * r)
+
+
 def test_gather_single_process():
     E = np.arange(12.0).reshape(3, 4)
     Eg, Cg = gather_eigenpairs(E, [0, 1, 2], 3, 4)
