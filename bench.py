@@ -716,7 +716,7 @@ def bench_cfg5(args, torch, dist, bsp, world, rank, local, barrier, allmax):
                         "note": "e2e = bspatom_dipole_chain with the eigenvector blocks in host memory; resident_call = "
                                 "bspatom_dipole_chain_resident (eigenvectors never leave HBM; only D comes back)"},
                 "gpu_launches": 2 * args.steps,
-                "roofline": {"kernel": "bsp_dgemm_tn128_kernel", "bound": "tensor", "achieved": tf / world, "peak": p_dense, "unit": "TFLOP/s",
+                "roofline": {"kernel": "bsp_dgemm_tn_kernel<128,128,4,2,3>", "bound": "tensor", "achieved": tf / world, "peak": p_dense, "unit": "TFLOP/s",
                              "frac": tf / world / p_dense, "traffic": None,
                              "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool (profiles/fp64_peak.json); cuBLAS on the batched TN "
                                             "shape 50 x 1000^3: %.1f TFLOP/s" % float(peak.get("dgemm_tn_batched_50x1000_tflops", float("nan")))},

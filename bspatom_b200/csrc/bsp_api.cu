@@ -743,6 +743,7 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "first_check_round" || s == "check_every") { /* accepted and ignored: the schedule is static */ }
     else if (s == "chunk") h->opt.chunk = (int)v;
     else if (s == "vec_tol") h->opt.vec_tol = v;
+    else if (s == "gemm_variant") bsp_gemm_force = (int)v;   /* process-wide: A/B runs of the contraction kernel only */
     else if (s == "ckpt") { h->opt.ckpt = (int)v; h->budget_bytes = 0; }
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
     else if (s == "stream_workers") h->opt.stream_workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));

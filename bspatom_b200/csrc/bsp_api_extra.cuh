@@ -199,7 +199,7 @@ int bspatom_dipole(bspatom_handle h, int n, int kd, const double *A_band, int nf
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, h->st));
-    bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, ni), 128, 0, h->st>>>(n, kd, d_A, ni, d_Ci, d_Y);
+    CU(bsp_launch_band_times_dense(h->st, n, kd, d_A, ni, d_Ci, d_Y, 1));
     h->launches++;
     CU(cudaGetLastError());
     CU(bsp_launch_dgemm_tn(h->st, nf, ni, n, d_Cf, n, d_Y, n, d_D, nf, 1, 0, 0, 0));
@@ -243,7 +243,7 @@ int bspatom_dipole_chain(bspatom_handle h, int n, int kd, const double *A_band, 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, h->st));
-    bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, nvec, nl - 1), 128, 0, h->st>>>(n, kd, d_A, nvec, d_C, d_Y);
+    CU(bsp_launch_band_times_dense(h->st, n, kd, d_A, nvec, d_C, d_Y, nl - 1));
     h->launches++;
     CU(cudaGetLastError());
     CU(bsp_launch_dgemm_tn(h->st, nvec, nvec, n, d_C + blk, n, d_Y, n, d_D, nvec, nl - 1, (long long)blk, (long long)blk,
@@ -316,13 +316,13 @@ int bspatom_dipole_chain_resident(bspatom_handle h, int i0, int nl, int nvec, in
     CU(cudaEventRecord(e0, h->st));
     if (uniform) {
         const long long cs = (long long)(blocks[1] - blocks[0]);
-        bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, nvec, nl - 1), 128, 0, h->st>>>(n, kd, d_A, nvec, blocks[0], d_Y, cs, (long long)yblk);
+        CU(bsp_launch_band_times_dense(h->st, n, kd, d_A, nvec, blocks[0], d_Y, nl - 1, cs, (long long)yblk));
         CU(cudaGetLastError());
         CU(bsp_launch_dgemm_tn(h->st, nvec, nvec, n, blocks[1], n, d_Y, n, d_D, nvec, nl - 1, cs, (long long)yblk, (long long)dblk));
         h->launches += 2;
     } else {
         for (int l = 0; l + 1 < nl; ++l) {
-            bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, nvec, 1), 128, 0, h->st>>>(n, kd, d_A, nvec, blocks[l], d_Y + yblk * l);
+            CU(bsp_launch_band_times_dense(h->st, n, kd, d_A, nvec, blocks[l], d_Y + yblk * l, 1));
             CU(cudaGetLastError());
             CU(bsp_launch_dgemm_tn(h->st, nvec, nvec, n, blocks[l + 1], n, d_Y + yblk * l, n, d_D + dblk * l, nvec, 1, 0, 0, 0));
             h->launches += 2;
@@ -425,7 +425,7 @@ int bspatom_trans_amp_hermitian(bspatom_handle h, int n, int kd, const double *z
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, h->st));
     for (int part = 0; part < 2; ++part) {
-        bsp_band_times_dense_kernel<<<dim3((n + 127) / 128, ni), 128, 0, h->st>>>(n, kd, d_A + part * abytes, ni, d_Ci, d_Y + part * yblk);
+        CU(bsp_launch_band_times_dense(h->st, n, kd, d_A + part * abytes, ni, d_Ci, d_Y + part * yblk, 1));
         h->launches++;
     }
     CU(cudaGetLastError());
