@@ -41,6 +41,7 @@ struct Options {
     double res_tol = 1e-9;
     int max_rounds = 90;      /* cap used when a chunk has to be redone */
     int rounds_enqueued = 26; /* bracketing rounds enqueued up front (surplus ones return at once) */
+    int sign_rule = 0;        /* 0: first significant coefficient positive; 1: then the literal CHKPHS of matrices.f90:398-449 */
     int ckpt = 0;             /* check-pointed full-width solves: 0 never (default: measured break-even), 1 always, -1 for half bandwidth <= 6 */
     double vec_tol = 1e-12;   /* ||r||_2 / gap above which an eigenpair gets the correction pass after its second solve */
     int min_iters = 2;        /* solves every eigenpair gets (3 = round-1 schedule: everybody gets the correction pass) */
@@ -559,6 +560,16 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
         CU(cudaGetLastError());
         int maxnv = 0;
         for (int p = 0; p < np; ++p) maxnv = std::max(maxnv, G.nvec[p0 + p]);
+        if (maxnv > 0 && h->opt.sign_rule == 1 && G.d_rt) {
+            switch (G.k) {
+#define BSP_CHK_CASE(K_) case K_: bsp_chkphs_kernel<K_><<<grid, BSP_EIG_THREADS, 0, h->st>>>(g, G.d_rt, G.nkp, c.fac); break;
+                BSP_CHK_CASE(3) BSP_CHK_CASE(4) BSP_CHK_CASE(5) BSP_CHK_CASE(6) BSP_CHK_CASE(7) BSP_CHK_CASE(8) BSP_CHK_CASE(9) BSP_CHK_CASE(10)
+#undef BSP_CHK_CASE
+            default: break;
+            }
+            h->launches++;
+            CU(cudaGetLastError());
+        }
         if (maxnv > 0) {
             dim3 tg((maxnv + 31) / 32, (G.n + 32 * BSP_TR_TILES - 1) / (32 * BSP_TR_TILES), np), tb(32, 8);
             bsp_transpose_kernel<<<tg, tb, 0, h->st>>>(g, c.fac, G.d_C, G.d_coff + p0);
@@ -743,6 +754,7 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "first_check_round" || s == "check_every") { /* accepted and ignored: the schedule is static */ }
     else if (s == "chunk") h->opt.chunk = (int)v;
     else if (s == "vec_tol") h->opt.vec_tol = v;
+    else if (s == "sign_rule") h->opt.sign_rule = (int)v;
     else if (s == "gemm_variant") bsp_gemm_force = (int)v;   /* process-wide: A/B runs of the contraction kernel only */
     else if (s == "ckpt") { h->opt.ckpt = (int)v; h->budget_bytes = 0; }
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
@@ -1057,11 +1069,23 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     int rounds = 0, iters = 0, redone = 0;
     long long selected = 0;
     h->c_bytes_copied = 0;
-    cudaEvent_t e0, e1, e2, copies_done;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
-    CU(cudaEventCreateWithFlags(&copies_done, cudaEventDisableTiming));
-    cudaEvent_t pd_done;
-    CU(cudaEventCreateWithFlags(&pd_done, cudaEventDisableTiming));
+    /* every exit (there are many CU(...) returns below) releases the events of the run */
+    struct EventGuard {
+        std::vector<cudaEvent_t> ev;
+        cudaEvent_t make(unsigned flags, cudaError_t &err) {
+            cudaEvent_t e = nullptr;
+            err = cudaEventCreateWithFlags(&e, flags);
+            if (err == cudaSuccess) ev.push_back(e);
+            return e;
+        }
+        ~EventGuard() { for (auto e : ev) cudaEventDestroy(e); }
+    } events;
+    cudaError_t ev_err = cudaSuccess;
+    cudaEvent_t e0 = events.make(cudaEventDefault, ev_err); CU(ev_err);
+    cudaEvent_t e1 = events.make(cudaEventDefault, ev_err); CU(ev_err);
+    cudaEvent_t e2 = events.make(cudaEventDefault, ev_err); CU(ev_err);
+    cudaEvent_t copies_done = events.make(cudaEventDisableTiming, ev_err); CU(ev_err);
+    cudaEvent_t pd_done = events.make(cudaEventDisableTiming, ev_err); CU(ev_err);
     CU(cudaEventRecord(pd_done, h->st_copy));
     CopyQueue *cq = (E_out || C_out) ? copy_queue(h->dev) : nullptr;
     if ((E_out || C_out) && !cq) { h->err = "cannot create the result-copy stream"; return BSPATOM_ECUDA; }
@@ -1195,13 +1219,20 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         /* ---- enqueue every chunk; no host read-back in here ---- */
         const bool report_mail = (size_t)nchunks * BSP_C_WORDS <= BSP_MAIL_REPORT_INTS;
         int *d_report = nullptr;
+        struct ReportGuard {      /* gives the report buffer back to the handle's pool on every exit */
+            bspatom_handle h; int *p = nullptr; size_t count = 0;
+            ~ReportGuard() { if (p) dev_free(h, p, count); }
+        } report_guard{h};
         if (report_mail) d_report = h->h_counter_dev;
-        else if ((rc = dev_alloc(h, &d_report, (size_t)nchunks * BSP_C_WORDS))) return rc;
+        else {
+            if ((rc = dev_alloc(h, &d_report, (size_t)nchunks * BSP_C_WORDS))) return rc;
+            report_guard.p = d_report; report_guard.count = (size_t)nchunks * BSP_C_WORDS;
+        }
         std::vector<ChunkTimes> tms(nchunks);
         for (int ci = 0; ci < nchunks; ++ci) {
-            for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&tms[ci].ev[i]));
+            for (int i = 0; i < 4; ++i) { tms[ci].ev[i] = events.make(cudaEventDefault, ev_err); CU(ev_err); }
             if (G.any_sel) {
-                CU(cudaEventCreateWithFlags(&tms[ci].selected, cudaEventDisableTiming));
+                tms[ci].selected = events.make(cudaEventDisableTiming, ev_err); CU(ev_err);
                 tms[ci].sel_report = h->h_sel_dev + G.sel_off + bounds[ci];
             }
         }
@@ -1322,11 +1353,6 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             CU(cudaEventElapsedTime(&ms, tms[ci].ev[2], tms[ci].ev[3])); t_fin += ms;
         }
         for (auto x : ctx) timed_collect(x);
-        for (int ci = 0; ci < nchunks; ++ci) {
-            for (int i = 0; i < 4; ++i) cudaEventDestroy(tms[ci].ev[i]);
-            if (tms[ci].selected) cudaEventDestroy(tms[ci].selected);
-        }
-        if (!report_mail) dev_free(h, d_report, (size_t)nchunks * BSP_C_WORDS);
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, e1, e2)); t_asm += ms;
     }
@@ -1357,7 +1383,6 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
     }
     float total = 0;
     CU(cudaEventElapsedTime(&total, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(copies_done); cudaEventDestroy(pd_done);
     h->stats[0] = (double)(h->launches + aux_launches() - launches0);
     h->stats[1] = rounds; h->stats[2] = iters;
     /* stage times are summed over the chunk streams: with several streams they overlap in wall time */

@@ -133,6 +133,7 @@ __global__ void bsp_verify_gram_kernel(int n, const int *__restrict__ nvec, cons
 }
 
 bspatom_handle g_level0 = nullptr;
+std::mutex g_level0_mu;   /* the LAPACK-shaped entry shares one lazily created handle: calls are serialised */
 
 } // namespace
 
@@ -535,6 +536,7 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
     if (!Bmat || ldb < std::max(1, n)) { *info = -8; return; }
     if (!w) { *info = -9; return; }
     if (n == 0) return;
+    std::lock_guard<std::mutex> level0_lock(g_level0_mu);
     if (!g_level0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) { *info = -100 - BSPATOM_ENODEVICE; return; }
@@ -592,19 +594,26 @@ void bspatom_dsygv_(const int *itype, const char *jobz, const char *uplo, const 
         if ((rc = dev_alloc(h, &d_L, (size_t)n * (B + 1)))) break;
     } while (0);
     if (rc) { free_group(h, G); dev_free(h, d_L, (size_t)n * (B + 1)); *info = -100 - rc; return; }
-    cudaMemcpyAsync(G.d_fbS, fbS.data(), per_mat * sizeof(double), cudaMemcpyHostToDevice, h->st);
-    cudaMemcpyAsync(G.d_fbH0, fbH.data(), per_mat * sizeof(double), cudaMemcpyHostToDevice, h->st);
-    cudaMemsetAsync(G.d_fbQ, 0, per_mat * sizeof(double), h->st);
-    cudaMemcpyAsync(G.d_inst, G.inst.data(), sizeof(int), cudaMemcpyHostToDevice, h->st);
-    cudaMemcpyAsync(G.d_nvec, G.nvec.data(), sizeof(int), cudaMemcpyHostToDevice, h->st);
-    cudaMemcpyAsync(G.d_cl, G.cl.data(), sizeof(double), cudaMemcpyHostToDevice, h->st);
-    cudaMemcpyAsync(G.d_coff, G.coff.data(), sizeof(long long), cudaMemcpyHostToDevice, h->st);
-    cudaMemsetAsync(G.d_bad, 0, sizeof(int), h->st);
+    cudaError_t ce = cudaSuccess;      /* first failing copy / launch of the set-up (checked once, below) */
+    auto ck = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; };
+    ck(cudaMemcpyAsync(G.d_fbS, fbS.data(), per_mat * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    ck(cudaMemcpyAsync(G.d_fbH0, fbH.data(), per_mat * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    ck(cudaMemsetAsync(G.d_fbQ, 0, per_mat * sizeof(double), h->st));
+    ck(cudaMemcpyAsync(G.d_inst, G.inst.data(), sizeof(int), cudaMemcpyHostToDevice, h->st));
+    ck(cudaMemcpyAsync(G.d_nvec, G.nvec.data(), sizeof(int), cudaMemcpyHostToDevice, h->st));
+    ck(cudaMemcpyAsync(G.d_cl, G.cl.data(), sizeof(double), cudaMemcpyHostToDevice, h->st));
+    ck(cudaMemcpyAsync(G.d_coff, G.coff.data(), sizeof(long long), cudaMemcpyHostToDevice, h->st));
+    ck(cudaMemsetAsync(G.d_bad, 0, sizeof(int), h->st));
     bsp_pdcheck_kernel<<<1, 32, 0, h->st>>>(G.d_fbS, n, G.nrows, B, 1, G.d_pdinfo, d_L);
+    ck(cudaGetLastError());
     h->launches++;
     int pd = 0;
-    cudaMemcpyAsync(&pd, G.d_pdinfo, sizeof(int), cudaMemcpyDeviceToHost, h->st);
-    if (cudaStreamSynchronize(h->st) != cudaSuccess) { free_group(h, G); dev_free(h, d_L, (size_t)n * (B + 1)); *info = -100 - BSPATOM_ECUDA; return; }
+    ck(cudaMemcpyAsync(&pd, G.d_pdinfo, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    ck(cudaStreamSynchronize(h->st));
+    if (ce != cudaSuccess) {
+        h->err = std::string("bspatom_dsygv_: ") + cudaGetErrorString(ce);
+        free_group(h, G); dev_free(h, d_L, (size_t)n * (B + 1)); *info = -100 - BSPATOM_ECUDA; return;
+    }
     if (pd) { free_group(h, G); dev_free(h, d_L, (size_t)n * (B + 1)); *info = n + pd; return; }
     /* run the eigen stages on this explicit pencil */
     h->groups.clear();

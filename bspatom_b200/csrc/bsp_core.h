@@ -59,6 +59,16 @@ __device__ __forceinline__ double bsp_drcp(double x)
 #endif
 
 #define BSP_EPS 2.220446049250313e-16
+
+/* -DBSP_DEBUG (libbspatom_debug.so, tests/test_gpu_debug.py): bounds checks on every workspace / list index and on the
+ * tile pipeline's bookkeeping as device-side asserts -- compute-sanitizer is closed on this pool, so this build is the
+ * memory-safety check of the kernels.  A failed assert traps: the host sees a CUDA error, never a silent wrong answer. */
+#if defined(BSP_DEBUG)
+#include <assert.h>
+#define BSP_ASSERT(c) assert(c)
+#else
+#define BSP_ASSERT(c) ((void)0)
+#endif
 #define BSP_ABS_CLOSE 2e-14   /* absolute bracket width (Hartree) at which a bracket counts as closed */
 
 /* rows stored per band matrix: the sweeps bring in row j+B+1 at step j and
@@ -798,6 +808,8 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
     const double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
     double *__restrict__ Lp = CKPT ? g.CK + (size_t)p * (npad / BSP_CK_STEPS(B)) * CKD * ldw + ls
                                    : g.L + (size_t)p * npad * K1 * ldw + ls;
+    BSP_ASSERT(p >= 0 && p < g.npencil && ls >= 0 && ls < ldw && (!active || (e >= 0 && e < n)));
+    BSP_ASSERT(npad % TR == 0 && g.xrows >= npad && g.nrows >= npad + B + 1);
 
     double w[K1][K1], y[K1];
     int cnt = 0;
@@ -806,6 +818,7 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
     const double scr = (iter == 0) ? 1.0 : sc;
     auto rhs = [&](int row) -> double {
         if (row >= n) return 0.0;
+        BSP_ASSERT(row >= 0 && row < g.xrows);
         return (iter == 0) ? bsp_hash_uniform(0u, (uint32_t)e, (uint32_t)row) : Rp[(size_t)row * ldw];
     };
     /* software pipeline: right-hand side (HBM) a whole unrolled block (B+1 rows) ahead; the band row that
@@ -876,6 +889,7 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
                         /* at a group start the window slots are in identity position; row B of the window is
                          * still the plain band row (it entered with the last step) and is not stored */
                         double *ck = Lp + (size_t)(j0 / BSP_CK_STEPS(B)) * CKD * ldw;
+                        BSP_ASSERT(g.CK != nullptr && j0 % BSP_CK_STEPS(B) == 0 && j0 / BSP_CK_STEPS(B) < npad / BSP_CK_STEPS(B));
                         int q = 0;
 #pragma unroll
                         for (int r = 0; r < B; ++r) {
@@ -906,6 +920,7 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
                     double col[K1], l[K1];
                     const double y0 = y[t];
                     double *Lrow = Lp + (size_t)j * K1 * ldw;
+                    BSP_ASSERT(j >= 0 && j < npad);
                     if (!CKPT) Lrow[0] = y0 * rinv;
 #pragma unroll
                     for (int i = 1; i <= B; ++i) {
@@ -1009,6 +1024,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
     const double *__restrict__ Lp = g.L + (size_t)p * npad * K1 * ldw + ls;
     double *__restrict__ Xp = g.X + (size_t)p * g.xrows * ldw + e;
     double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
+    BSP_ASSERT(p >= 0 && p < g.npencil && ls >= 0 && ls < ldw && (!active || (e >= 0 && e < n)) && npad % TR == 0);
     const double sc = active ? g.scale[id] : 1.0;
     const double rho_p = active ? g.rho[id] : 0.0; /* rho' */
     const double cx = corr_now ? sc : 0.0;
@@ -1031,6 +1047,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
     auto fetch = [&](int q, int row) {
         /* rows -PF..-1 are asked for by the last steps and never used: row 0 is loaded again instead */
         const int r = row < 0 ? 0 : row;
+        BSP_ASSERT(r < npad);
         if (!RESID) {
             const double *Lrow = Lp + (size_t)r * K1 * ldw;
 #pragma unroll
@@ -1071,6 +1088,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
                 yw[0] = yj;
                 if (j < n) {
                     xn = fma(cx, xq[q], -yj);
+                    BSP_ASSERT(j >= 0 && j < g.xrows);
                     Xp[(size_t)j * ldw] = xn;
                     xabs = fmax(xabs, fabs(xn));
                 }
@@ -1185,7 +1203,7 @@ template <int B>
 struct BspScratchLocal {
     static constexpr int SLOTS = BSP_CK_STEPS(B) * (B + 1);
     double s[SLOTS];
-    BSP_HD double &slot(int i) { return s[i]; }
+    BSP_HD double &slot(int i) { BSP_ASSERT(i >= 0 && i < SLOTS); return s[i]; }
     /* check-point values are read straight from global memory: no prefetch on the host */
     BSP_HD void prefetch(int, const double *) {}
     BSP_HD void prefetch_commit() {}
@@ -1404,7 +1422,11 @@ BSP_HD void bsp_check_converged(const BspEigChunk &g, int p, int e, int iter, in
     } else {
 #if defined(__CUDA_ARCH__)
         atomicAdd(g.counters + BSP_C_UNCONV, 1);
-        if (g.rlist) g.rlist[((size_t)(iter & 1) * g.npencil + p) * g.ldw + atomicAdd(g.rcount + (iter & 1) * g.npencil + p, 1)] = e;
+        if (g.rlist) {
+            const int slot = atomicAdd(g.rcount + (iter & 1) * g.npencil + p, 1);
+            BSP_ASSERT(slot >= 0 && slot < g.n);
+            g.rlist[((size_t)(iter & 1) * g.npencil + p) * g.ldw + slot] = e;
+        }
 #else
         g.counters[BSP_C_UNCONV] += 1;
         if (g.rlist) g.rlist[((size_t)(iter & 1) * g.npencil + p) * g.ldw + g.rcount[(iter & 1) * g.npencil + p]++] = e;
@@ -1418,6 +1440,7 @@ BSP_HD int bsp_listed_index(const BspEigChunk &g, int p, int slot, int iter)
 {
     const int buf = (iter - 1) & 1;
     if (slot >= g.rcount[buf * g.npencil + p]) return -1;
+    BSP_ASSERT(g.rcount[buf * g.npencil + p] <= g.n);
     return g.rlist[((size_t)buf * g.npencil + p) * g.ldw + slot];
 }
 
@@ -1468,7 +1491,12 @@ BSP_HD void bsp_finalize_eigen(const BspEigChunk &g, int p, int e, double *E, do
 #if defined(BSP_TRACE_FIN) && !defined(__CUDA_ARCH__)
     if (outside) printf("outside: e=%d rho=%.17g lo=%.17g hi=%.17g r=%.3e slack=%.3e viol=%.3e\n", e, rho, g.lo[id], g.hi[id], r, slack, fmax(g.lo[id]-rho, rho-g.hi[id]));
 #endif
-    if (unbracketed || outside || !(r <= res_tol * fmax(1.0, fabs(rho)))) {
+    /* every vector comes from its own inverse iteration: nothing re-orthogonalises a numerically degenerate pair
+     * (gap below a few hundred ulps), so such a pair is reported instead of returned as if it were S-orthogonal
+     * (radial Sturm-Liouville spectra are simple; the LAPACK-shaped entry accepts any banded pencil) */
+    bool degenerate = false;
+    if (e + 1 < g.nvec[p] && e + 1 < g.n) degenerate = fabs(g.rho[id + 1] - rho) <= 256.0 * BSP_EPS * fmax(fabs(rho), fabs(g.rho[id + 1]));
+    if (unbracketed || outside || degenerate || !(r <= res_tol * fmax(1.0, fabs(rho)))) {
 #if defined(__CUDA_ARCH__)
         atomicAdd(bad + p, 1);
 #else

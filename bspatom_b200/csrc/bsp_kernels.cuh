@@ -12,6 +12,8 @@
 
 #include <cuda_runtime.h>
 #include "bsp_core.h"
+#include "bsp_assembly.cuh"
+#include <assert.h>
 
 #ifndef BSP_EIG_THREADS
 #define BSP_EIG_THREADS 128
@@ -125,6 +127,9 @@ struct BspRowsStaged {
     uint64_t *bars;   /* two mbarriers, count 1, not used by an earlier sweep of this launch */
     const double *gH, *gS;
     double *rq = nullptr;   /* this thread's column of the right-hand-side ring: rq[slot_row * blockDim.x] */
+#if defined(BSP_DEBUG)
+    int dbg_issued = 0, dbg_acquired = 0;   /* thread 0: tiles issued / acquired so far (each stage: issue -> acquire -> release) */
+#endif
 
     __device__ __forceinline__ void rhs_issue(int slot_row, const double *src)
     {
@@ -141,6 +146,11 @@ struct BspRowsStaged {
         const int stage = seq & 1;
         double *dH = sm + (size_t)stage * 2 * T::DOUBLES + (size_t)dst_row * T::FS, *dS = dH + T::DOUBLES;
         const unsigned bytes = (unsigned)rows * T::ROW_BYTES;
+#if defined(BSP_DEBUG)
+        /* tiles go out in sequence, at most two ahead of the one being consumed, and fit their stage */
+        BSP_ASSERT(seq == dbg_issued && dbg_issued - dbg_acquired <= 2 && (dst_row + rows) * T::FS <= T::DOUBLES && rows > 0);
+        ++dbg_issued;
+#endif
         bsp_mbar_expect(bars + stage, 2u * bytes);
         bsp_bulk_g2s(dH, srcH, bytes, bars + stage);
         bsp_bulk_g2s(dS, srcS, bytes, bars + stage);
@@ -148,6 +158,9 @@ struct BspRowsStaged {
     __device__ __forceinline__ void acquire(int seq, const double *&tH, const double *&tS)
     {
         const int stage = seq & 1;
+#if defined(BSP_DEBUG)
+        if (threadIdx.x == 0) { BSP_ASSERT(seq == dbg_acquired && seq < dbg_issued); ++dbg_acquired; }
+#endif
         bsp_mbar_wait(bars + stage, (unsigned)(seq >> 1) & 1u);
         tH = sm + (size_t)stage * 2 * T::DOUBLES;
         tS = tH + T::DOUBLES;
@@ -317,7 +330,9 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) 
     if ((int)(blockIdx.x * blockDim.x) < cnt) {     /* block-uniform */
         const bool valid = slot < cnt;
         const int *list = g.olist + ((size_t)rdb * g.npencil + p) * g.ldw;
+        BSP_ASSERT(cnt >= 0 && cnt <= g.n && cnt_open >= 0 && cnt_open <= cnt);
         const int e = !valid ? g.n : (!listed ? slot : (slot < cnt_open ? list[slot] : list[g.ldw - 1 - (slot - cnt_open)]));
+        BSP_ASSERT(e >= 0 && e <= g.n);
         bsp_stage_bars_init(bars);
         BspRoundState st;
         st.want_defl = 0; st.want_count = 0; st.done = 1; st.was_done = 1; st.lo = st.hi = 0.0;
@@ -339,8 +354,10 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) 
             bsp_round_end(g, p, e, round, st);
             if (compact && !st.was_done) {
                 int *wl = g.olist + ((size_t)wrb * g.npencil + p) * g.ldw;
-                if (!st.done) wl[atomicAdd(g.ocount + (wrb * g.npencil + p) * 2, 1)] = e;
-                else wl[g.ldw - 1 - atomicAdd(g.ocount + (wrb * g.npencil + p) * 2 + 1, 1)] = e;
+                const int at = !st.done ? atomicAdd(g.ocount + (wrb * g.npencil + p) * 2, 1)
+                                        : g.ldw - 1 - atomicAdd(g.ocount + (wrb * g.npencil + p) * 2 + 1, 1);
+                BSP_ASSERT(at >= 0 && at < g.ldw);
+                wl[at] = e;
             }
         }
     }
@@ -380,6 +397,7 @@ __device__ __forceinline__ bool bsp_refine_map(const BspEigChunk &g, int p, int 
         if ((int)(blockIdx.x * blockDim.x) >= cnt) return false;
         active = slot < cnt;
         e = active ? g.rlist[((size_t)((iter - 1) & 1) * g.npencil + p) * g.ldw + slot] : 0;
+        BSP_ASSERT(cnt <= g.n && e >= 0 && e < g.n);
     } else {
         e = slot;
         active = bsp_refine_active(g, p, e);
@@ -447,7 +465,7 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B))
 struct BspScratchShared {
     double *base;
     int nt;
-    __device__ __forceinline__ double &slot(int i) { return base[(size_t)i * nt]; }
+    __device__ __forceinline__ double &slot(int i) { BSP_ASSERT(i >= 0); return base[(size_t)i * nt]; }
     __device__ __forceinline__ void prefetch(int i, const double *gp)
     {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(bsp_smem_u32(base + (size_t)i * nt)), "l"(gp) : "memory");
@@ -525,6 +543,42 @@ __global__ void bsp_copy_ints_kernel(int *dst, const int *src, int n)
 __global__ void bsp_finalize_kernel(BspEigChunk g, double *E, double *fac, int *bad, double res_tol)
 {
     bsp_finalize_eigen(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, E, fac, bad, res_tol);
+}
+
+/* Literal CHKPHS (matrices.f90:398-449; option "sign_rule" = 1): after the default sign convention, evaluate
+ *   fr(i) = sum_j c(j) bsp(j - (left - nbc1)),  j = left-nbc1+1 .. MIN(left-nbc1+k, nfun),  r = ra + i (0.1 - ra)/3, i = 1..3
+ * with the reference's own index mapping (jfun = j - (left - nbc1): one function higher than WRITE_WF's
+ * j = left - k + jfun when nbc1 = k-1, SURVEY.md 8(f) row f-1 -- reproduced, not fixed) and flip the vector when all
+ * three values are negative.  nbc1 = multiplicity of the first knot (rt(1:nbc1) = ra, grid.f90:16-18). */
+template <int K>
+__global__ void bsp_chkphs_kernel(BspEigChunk g, const double *__restrict__ rt_all, int nkp, double *fac)
+{
+    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nvec[p] || e >= g.n) return;
+    const double *rt = rt_all + (size_t)g.inst[p] * nkp;
+    const size_t id = (size_t)p * g.ldw + e;
+    const double *Xp = g.X + (size_t)p * g.xrows * g.ldw + e;
+    const double ra = rt[0];
+    int nbc1 = 1;
+    while (nbc1 < nkp && rt[nbc1] == ra) ++nbc1;
+    const double dr = (0.1 - ra) / 3.0;
+    int neg = 0;
+    for (int i = 1; i <= 3; ++i) {
+        const double r = ra + (double)i * dr;
+        int left = 1;                                   /* interv: largest left with rt(left) <= r < rt(left+1) */
+        while (left < nkp && rt[left] <= r) ++left;     /* rt[left] is rt(left+1) */
+        if (left >= nkp || !(rt[left] > rt[left - 1])) { left = 1; }
+        double bsp[K], dbsp[K];
+        bsp_deboor<K>(rt, nkp, g.n, left, r, bsp, dbsp);
+        const int jmin = left - nbc1 + 1, jmax = min(jmin + K - 1, g.n);
+        double sumf = 0.0;
+        for (int j = jmin; j <= jmax; ++j) {
+            const int jfun = j - (left - nbc1);
+            if (j >= 1) sumf += fac[id] * Xp[(size_t)(j - 1) * g.ldw] * bsp[jfun - 1];
+        }
+        neg += (sumf < 0.0);
+    }
+    if (neg == 3) fac[id] = -fac[id];
 }
 
 /* C[p] (n x nvec_p, column-major, column e = eigenvector e) = fac[e] * X[p][row][e]

@@ -259,3 +259,32 @@ def cubspl_ref(x0, y0, x1):
             b = (xi - x[klo]) / h
             out.append(a * y[klo] + b * y[khi] + ((a ** 3 - a) * y2[klo] + (b ** 3 - b) * y2[khi]) * (h ** 2) / 6.0)
     return out
+
+
+def chkphs_ref(b, cinl_l):
+    """CHKPHS (matrices.f90:398-449) for the vectors of one l, statement by statement: cinl_l is (nfun, nvec) and is
+    returned with the flipped columns.  Keeps the reference's index mapping jfun = j - (left - nbc1) (one function
+    higher than WRITE_WF's when nbc1 = k - 1).  `b` is an oracle.Basis."""
+    from oracle import oracle as O
+
+    out = np.array(cinl_l, dtype=np.float64, copy=True)
+    nr = 3                                                    # :418
+    r0, r1 = b.ra, 0.1                                        # :419-420
+    dr = (r1 - r0) / float(nr)                                # :421
+    for n in range(out.shape[1]):                             # don0
+        fr = [0.0] * nr
+        for i in range(1, nr + 1):                            # dor0
+            r = r0 + float(i) * dr                            # :430
+            left, mflag = O.interv(b.rt, r)                   # :433
+            bsp = O.bsplvb(b.rt, b.k, r, left)                # :434
+            jmin = left - b.nbc1 + 1                          # :436
+            jmax = min(jmin + b.k - 1, b.nfun)                # :437
+            sumf = 0.0
+            for j in range(jmin, jmax + 1):                   # doj
+                jfun = j - (left - b.nbc1)                    # :441
+                if j >= 1:
+                    sumf = sumf + out[j - 1, n] * bsp[jfun - 1]
+            fr[i - 1] = sumf
+        if fr[0] < 0.0 and fr[1] < 0.0 and fr[2] < 0.0:       # :447
+            out[:, n] = -out[:, n]
+    return out

@@ -173,3 +173,27 @@ def test_cfg5_full_size_n1000_against_oracle_loop(atom, oracle, l0):
     assert worst < 1e-12, worst
     if l0 == 0:   # <2p|r|1s> of hydrogen = 128 sqrt(6) / 243 (basis-limited at h = 0.5)
         assert abs(abs(D[0, 0]) - 128 * np.sqrt(6) / 243) < 1e-5
+
+
+def test_literal_chkphs_option(atom, oracle):
+    """option sign_rule = 1: the default convention followed by the literal CHKPHS (matrices.f90:398-449, with its own
+    index mapping) -- equal to the statement-by-statement restatement applied to the default-convention vectors, and a
+    fixed point of CHKPHS."""
+    from oracle import postproc_oracle as po
+
+    a = host_basis(kind_grid=2, k=7, nfun=100, rb=500.0, rmax=60.0)
+    b = oracle.shipped_basis()
+    items = [(a.problem(), l) for l in range(3)]
+    E0, C0, _ = atom.solve_batch(items, nvec=40)
+    atom.set_option("sign_rule", 1)
+    try:
+        E1, C1, _ = atom.solve_batch(items, nvec=40)
+    finally:
+        atom.set_option("sign_rule", 0)
+    flips = 0
+    for l in range(3):
+        want = po.chkphs_ref(b, np.asarray(C0[l]))
+        assert np.array_equal(np.asarray(C1[l]), want)
+        assert np.array_equal(po.chkphs_ref(b, want), want)
+        flips += int(np.sum(np.any(want != np.asarray(C0[l]), axis=0)))
+    print("CHKPHS flipped %d of 120 default-convention vectors" % flips)
