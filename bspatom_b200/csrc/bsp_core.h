@@ -808,7 +808,7 @@ BSP_HD void bsp_factor_forward_rows(const BspEigChunk &g, int p, int e, int ls, 
     const double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
     double *__restrict__ Lp = CKPT ? g.CK + (size_t)p * (npad / BSP_CK_STEPS(B)) * CKD * ldw + ls
                                    : g.L + (size_t)p * npad * K1 * ldw + ls;
-    BSP_ASSERT(p >= 0 && p < g.npencil && ls >= 0 && ls < ldw && (!active || (e >= 0 && e < n)));
+    BSP_ASSERT(p >= 0 && p < g.npencil && (!active || (ls >= 0 && ls < ldw && e >= 0 && e < n)));   /* idle threads touch nothing */
     BSP_ASSERT(npad % TR == 0 && g.xrows >= npad && g.nrows >= npad + B + 1);
 
     double w[K1][K1], y[K1];
@@ -1024,7 +1024,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
     const double *__restrict__ Lp = g.L + (size_t)p * npad * K1 * ldw + ls;
     double *__restrict__ Xp = g.X + (size_t)p * g.xrows * ldw + e;
     double *__restrict__ Rp = g.R + (size_t)p * g.xrows * ldw + e;
-    BSP_ASSERT(p >= 0 && p < g.npencil && ls >= 0 && ls < ldw && (!active || (e >= 0 && e < n)) && npad % TR == 0);
+    BSP_ASSERT(p >= 0 && p < g.npencil && (!active || (ls >= 0 && ls < ldw && e >= 0 && e < n)) && npad % TR == 0);
     const double sc = active ? g.scale[id] : 1.0;
     const double rho_p = active ? g.rho[id] : 0.0; /* rho' */
     const double cx = corr_now ? sc : 0.0;
