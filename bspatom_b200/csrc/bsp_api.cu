@@ -541,8 +541,11 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
         ex.sel_report = tm.sel_report;
         ex.ev_selected = tm.selected;
     }
-    /* a few stragglers per hundred thousand eigenpairs are cheaper to finish inside the refinement */
-    ex.open_ok = (int)((long long)np * G.n / 20000);
+    /* every bracket is closed to tau x gap before the hand-over.  Round 1 handed a few stragglers per hundred thousand
+     * eigenpairs over open (cheaper by two or three compacted rounds, ~0.3 ms): their first solve then starts from the
+     * midpoint of a wide bracket, they pass conv_tol one iteration late with |C^T S C - I| up to 7e-7 (found by
+     * bspatom_batch_verify on cfg3), and -- the count being per chunk -- results depended on how a batch was chunked. */
+    ex.open_ok = 0;
     bsp_zero_words_kernel<<<1, 32, 0, h->st>>>(c.counters, BSP_C_WORDS);
     h->launches++;
     CU(cudaMemsetAsync(c.ocount, 0, sizeof(int) * 4 * (size_t)np, h->st));
