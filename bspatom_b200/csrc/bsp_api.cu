@@ -1162,7 +1162,9 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             for (int i = 1; i <= nchunks; ++i) bounds.push_back(std::min(i * chunk, G.npencil));
         } else {
             int want = workers;
-            if (streaming) want = std::max(want, std::min(h->opt.stream_chunks, std::max(1, (2 * G.npencil) / fill_pencils)));
+            /* with a device-side selection the copies are small and every chunk carries the latency-bound tail of the
+             * rounds that close the values-only brackets: no extra chunks for streaming */
+            if (streaming && !G.any_sel) want = std::max(want, std::min(h->opt.stream_chunks, std::max(1, (2 * G.npencil) / fill_pencils)));
             nchunks = std::max(want, (G.npencil + cap - 1) / cap);
             nchunks = std::min(nchunks, G.npencil);
             const bool shrink = streaming && nchunks >= 4 && (long long)cap * (nchunks + 5) >= 2LL * G.npencil;

@@ -506,8 +506,10 @@ class BspAtomPipeline:
         for a in self.atoms:
             a.close()
 
-    def solve_batches(self, batches, outs_E, outs_C, nvec=None):
+    def solve_batches(self, batches, outs_E, outs_C, nvec=None, select=None, on_done=None):
         """batches[i]: list of (Problem, l); outs_E[i], outs_C[i]: pinned float64 buffers for batch i.
+        select: device-side state selection applied to every batch; on_done(i, atom): called in the worker thread
+        right after batch i returned (e.g. to read atom.selection() / atom.stats() of that batch).
         Returns the list of info arrays."""
         import threading
         import time
@@ -526,7 +528,10 @@ class BspAtomPipeline:
                     time.sleep(w * stagger)
                 for i in range(w, len(batches), depth):
                     t0 = time.perf_counter()
-                    _, _, infos[i] = self.atoms[w].solve_batch(batches[i], nvec=nvec, out_E=outs_E[i], out_C=outs_C[i])
+                    _, _, infos[i] = self.atoms[w].solve_batch(batches[i], nvec=nvec, out_E=outs_E[i], out_C=outs_C[i],
+                                                               select=select)
+                    if on_done is not None:
+                        on_done(i, self.atoms[w])
                     t1 = time.perf_counter()
                     took.append(1e3 * (t1 - t0))
                     timeline.append((i, w, 1e3 * (t0 - t_origin), 1e3 * (t1 - t_origin)))
