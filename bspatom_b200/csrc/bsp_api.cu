@@ -51,11 +51,6 @@ struct Options {
     int workers = 2; /* concurrent chunk streams (1..4) */
     int stream_chunks = 6; /* chunks per group when results stream to the host */
     int stream_workers = 2; /* chunk streams when results stream to the host */
-    /* block slots per SM a full-width bracketing round / factor sweep / back sweep may occupy (0 = no cap: one block per
-     * work item); with a cap the kernels of two chunk streams share every SM instead of taking turns (bsp_kernels.cuh) */
-    int cap_round = 0, cap_factor = 0, cap_back = 0;
-    int carveout = 0;       /* > 0: preferred shared-memory carve-out (percent) of the three sweep kernels, so that they can share an SM */
-    int stagger = 0;        /* the first chunk of chunk stream w > 0 starts when stream w-1 hands its first chunk over to the refinement */
 #define BSP_MAX_STREAMS 8
 #define BSP_MAIL_INTS (1 << 18)
 #define BSP_MAIL_REPORT_INTS (1 << 14)
@@ -98,7 +93,6 @@ struct Workspace {
 
 struct bspatom_handle_s {
     int dev = 0;
-    int nsm = 148;                  /* multiprocessors of the device (grid of the capped work-item launches) */
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr; /* D2H of finished chunks overlaps the next chunk's kernels */
     std::vector<cudaEvent_t> chunk_done;
@@ -395,15 +389,10 @@ struct GpuExec {
     cudaEvent_t ev_refine = nullptr; /* recorded between the bracketing and the refinement */
     cudaError_t first_err = cudaSuccess;
     dim3 grid() const { return dim3((g.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS, g.npencil); }
-    /* work-item launches: nbx slices per pencil, one block per item or `cap` block slots per SM (bsp_kernels.cuh) */
-    int nbx() const { return (g.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS; }
-    int cap_round = 0, cap_factor = 0, cap_back = 0, nsm = 148;
-    dim3 items(int cap) const {
-        const long long n = (long long)nbx() * g.npencil;
-        return dim3((unsigned)(cap > 0 ? std::min<long long>(n, (long long)cap * nsm) : n));
-    }
-    /* compacted passes: a pencil lists 10-17 % of its eigenpairs; they use the same 128-thread blocks (64-thread blocks
-     * were measured: factor +0.25 ms, no gain overall) */
+    /* compacted passes: a pencil lists 10-17 % of its eigenpairs (64-thread blocks were measured: factor +0.25 ms,
+     * no gain overall) */
+    static constexpr int LISTED_THREADS = 128;
+    dim3 grid_listed() const { return dim3((g.n + LISTED_THREADS - 1) / LISTED_THREADS, g.npencil); }
     void note() {
         h->launches++;
         cudaError_t e = cudaGetLastError();
@@ -415,7 +404,7 @@ struct GpuExec {
     }
     void round(int r, int max_rounds) {
         const int s = timed_begin(h, 0);
-        bsp_round_kernel<B><<<items(cap_round), BSP_EIG_THREADS, 0, h->st>>>(g, r, max_rounds, open_ok, nbx()); note();
+        bsp_round_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, r, max_rounds, open_ok); note();
         timed_end(h, s);
     }
     const BspSelect *d_sel = nullptr;   /* selection rules of the chunk's pencils, or null */
@@ -434,7 +423,8 @@ struct GpuExec {
         cur_iter = it;
         const int s = timed_begin(h, 1);
         if (ckpt && it < 2 && !optional) bsp_factor_ckpt_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it);
-        else bsp_factor_kernel<B><<<items(cap_factor), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional, nbx());
+        else if (optional) bsp_factor_kernel<B><<<grid_listed(), LISTED_THREADS, 0, h->st>>>(g, it, optional);
+        else bsp_factor_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, optional);
         note();
         timed_end(h, s);
     }
@@ -445,15 +435,18 @@ struct GpuExec {
             cudaFuncSetAttribute(bsp_back_ckpt_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             dim3 gr((g.n + BSP_CKB_THREADS - 1) / BSP_CKB_THREADS, g.npencil);
             bsp_back_ckpt_kernel<B><<<gr, BSP_CKB_THREADS, smem, h->st>>>(g, it, cx);
+        } else if (optional) {
+            bsp_back_kernel<B><<<grid_listed(), LISTED_THREADS, 0, h->st>>>(g, it, cn, cx, optional);
         } else {
-            bsp_back_kernel<B><<<items(cap_back), BSP_EIG_THREADS, 0, h->st>>>(g, it, cn, cx, optional, nbx());
+            bsp_back_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, cn, cx, optional);
         }
         note();
         timed_end(h, s);
     }
     void resid(int optional) {
         const int s = timed_begin(h, 2);
-        bsp_resid_kernel<B><<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, optional); note();
+        /* runs in front of the factor pass of iteration cur_iter + 1 and follows the same list */
+        bsp_resid_kernel<B><<<grid_listed(), LISTED_THREADS, 0, h->st>>>(g, cur_iter + 1, optional); note();
         timed_end(h, s);
     }
     void check(int it, int select) { bsp_check_kernel<<<grid(), BSP_EIG_THREADS, 0, h->st>>>(g, it, select); note(); }
@@ -544,12 +537,6 @@ int enqueue_chunk_b(bspatom_handle h, Group &G, int p0, int np, const ChunkPtrs 
     GpuExec<B> ex;
     ex.h = h; ex.g = g; ex.cand_s = c.cand_s; ex.cand_c = c.cand_c; ex.ev_refine = tm.ev[1];
     ex.ckpt = (c.CK != nullptr);
-    if (h->opt.carveout > 0) {
-        cudaFuncSetAttribute(bsp_round_kernel<B>, cudaFuncAttributePreferredSharedMemoryCarveout, h->opt.carveout);
-        cudaFuncSetAttribute(bsp_factor_kernel<B>, cudaFuncAttributePreferredSharedMemoryCarveout, h->opt.carveout);
-        cudaFuncSetAttribute(bsp_back_kernel<B>, cudaFuncAttributePreferredSharedMemoryCarveout, h->opt.carveout);
-    }
-    ex.cap_round = h->opt.cap_round; ex.cap_factor = h->opt.cap_factor; ex.cap_back = h->opt.cap_back; ex.nsm = h->nsm;
     if (G.any_sel) {
         ex.d_sel = G.d_sel + p0; ex.d_nvec_eff = G.d_nvec_eff + p0;
         ex.sel_report = tm.sel_report;
@@ -685,8 +672,6 @@ bspatom_handle new_context(int device_id)
         delete h;
         return nullptr;
     }
-    int nsm = 0;
-    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device_id) == cudaSuccess && nsm > 0) h->nsm = nsm;
     return h;
 }
 
@@ -779,11 +764,6 @@ int bspatom_set_option(bspatom_handle h, const char *name, double v)
     else if (s == "stream_chunks") h->opt.stream_chunks = std::max(1, (int)v);
     else if (s == "stream_workers") h->opt.stream_workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
     else if (s == "workers") h->opt.workers = std::min(BSP_MAX_STREAMS, std::max(1, (int)v));
-    else if (s == "cap_round") h->opt.cap_round = std::max(0, (int)v);
-    else if (s == "cap_factor") h->opt.cap_factor = std::max(0, (int)v);
-    else if (s == "cap_back") h->opt.cap_back = std::max(0, (int)v);
-    else if (s == "stagger") h->opt.stagger = (int)v;
-    else if (s == "carveout") h->opt.carveout = std::min(100, std::max(0, (int)v));
     else return -2;
     return 0;
 }
@@ -1267,7 +1247,6 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
         struct TraceRec { int ci, w, np; cudaEvent_t done, c0, c1; };
         std::vector<TraceRec> trace;
         std::vector<long long> load(workers, 0);      /* pencils assigned to each stream so far */
-        std::vector<int> first_chunk(workers, -1);
         std::unique_lock<std::mutex> copy_lock;
         const double t_lock0 = host_ms();
         if (streaming) copy_lock = std::unique_lock<std::mutex>(cq->mu);
@@ -1280,9 +1259,6 @@ int run_internal(bspatom_handle h, double *E_out, double *C_out)
             ChunkPtrs cc;
             carve_chunk(G, chunk, x->ws.base, cc, use_ckpt(h, G));
             const int p0 = bounds[ci], np = bounds[ci + 1] - p0;
-            if (h->opt.stagger && wsel > 0 && first_chunk[wsel] < 0 && first_chunk[wsel - 1] >= 0)
-                CU(cudaStreamWaitEvent(x->st, tms[first_chunk[wsel - 1]].ev[1], 0));   /* ev[1]: hand-over to the refinement */
-            if (first_chunk[wsel] < 0) first_chunk[wsel] = ci;
             if ((rc = enqueue_chunk(x, G, p0, np, cc, sch, tms[ci], d_report + (size_t)ci * BSP_C_WORDS))) {
                 if (x != h) h->err = x->err;
                 return rc;

@@ -974,8 +974,14 @@ BSP_HD void bsp_factor_forward(const BspEigChunk &g, int p, int e, int iter)
  *               0 -> s
  * ------------------------------------------------------------------------- */
 /* end of a solving back sweep: Rayleigh quotient, normalisation, residual norms, next shift */
+/* corr_next < 0 (the check follows at once): the sweep only knows r = (H - rho' S) x against the PREVIOUS quotient rho';
+ * the residual against the new one is r - (rho - rho') S x, whose 2-norm follows from the three sums the sweep carried,
+ *   ||r_new||^2 = rr2 - 2 (rho - rho') rs + (rho - rho')^2 s2,    rs = sum r_i (Sx)_i,  s2 = sum (Sx)_i^2,
+ * so the convergence / selection test needs no residual pass over all eigenpairs (round 2 until this change: a
+ * latency-bound pass of 3 ms per 408 pencils).  The rounding of the three sums is added, so the figure is an upper bound:
+ * a pair near the threshold is selected for the correction pass rather than missed; res (max norm) <= res2. */
 BSP_HD void bsp_back_finish(const BspEigChunk &g, size_t id, int corr_next, double sc, double rho_p, double xSx, double xHx,
-                            double resmax, double rr2, double xabs)
+                            double resmax, double rr2, double xabs, double rs, double s2)
 {
     double lo = g.lo[id], hi = g.hi[id];
     const double good = (xSx > 0.0 && xSx < INFINITY) ? 1.0 : 0.0;
@@ -985,6 +991,13 @@ BSP_HD void bsp_back_finish(const BspEigChunk &g, size_t id, int corr_next, doub
         scn = 1.0 / sqrt(xSx);
         res = resmax * scn;
         res2 = sqrt(rr2) * scn;
+        if (corr_next < 0) {
+            const double dr = rho_new - rho_p;
+            const double t1 = 2.0 * dr * rs, t2 = dr * dr * s2;
+            const double q = fmax(rr2 - t1 + t2, 0.0) + 8.0 * BSP_EPS * (rr2 + fabs(t1) + t2);
+            res2 = sqrt(q) * scn;
+            res = res2;
+        }
     }
     g.xmax[id] = xabs;
     g.rho_prev[id] = rho_p;
@@ -1039,7 +1052,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
     double yw[K1], xv[K1], hs[K1], ss[K1];
 #pragma unroll
     for (int i = 0; i < K1; ++i) { yw[i] = 0.0; xv[i] = 0.0; hs[i] = 0.0; ss[i] = 0.0; }
-    double xSx = 0.0, xHx = 0.0, resmax = 0.0, xabs = 0.0, rr2 = 0.0;
+    double xSx = 0.0, xHx = 0.0, resmax = 0.0, xabs = 0.0, rr2 = 0.0, rs = 0.0, s2 = 0.0;
 
     /* ring of PF factor rows (+ x_old) in flight: row j is consumed PF steps after its loads were
      * issued, which is what hides the HBM latency of this purely streaming sweep */
@@ -1123,6 +1136,8 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
             const double r = fma(-rho_p, sv, h);
             resmax = fmax(resmax, fabs(r));
             rr2 = fma(r, r, rr2);
+            rs = fma(r, sv, rs);
+            s2 = fma(sv, sv, s2);
             /* corr_next < 0: a residual pass follows and writes R itself */
             if (RESID || corr_next >= 0) Rp[(size_t)i * ldw] = (RESID || corr_next) ? r : sv;
         }
@@ -1168,7 +1183,7 @@ BSP_HD void bsp_back_substitute_rows(const BspEigChunk &g, int p, int e, int ls,
         g.sigma[id] = sig;
         return;
     }
-    bsp_back_finish(g, id, corr_next, sc, rho_p, xSx, xHx, resmax, rr2, xabs);
+    bsp_back_finish(g, id, corr_next, sc, rho_p, xSx, xHx, resmax, rr2, xabs, rs, s2);
 }
 
 template <int B>
@@ -1240,7 +1255,7 @@ BSP_HD void bsp_back_ckpt_rows(const BspEigChunk &g, int p, int e, int ls, int i
     double yw[K1], xv[K1], hs[K1], ss[K1];
 #pragma unroll
     for (int i = 0; i < K1; ++i) { yw[i] = 0.0; xv[i] = 0.0; hs[i] = 0.0; ss[i] = 0.0; }
-    double xSx = 0.0, xHx = 0.0, resmax = 0.0, xabs = 0.0, rr2 = 0.0;
+    double xSx = 0.0, xHx = 0.0, resmax = 0.0, xabs = 0.0, rr2 = 0.0, rs = 0.0, s2 = 0.0;
 
     auto back_step = [&](auto tail_c, int j, const double *rowH, const double *rowS, int srow) {
         constexpr bool TAIL = decltype(tail_c)::value;
@@ -1292,6 +1307,8 @@ BSP_HD void bsp_back_ckpt_rows(const BspEigChunk &g, int p, int e, int ls, int i
             const double r = fma(-rho_p, sv, h);
             resmax = fmax(resmax, fabs(r));
             rr2 = fma(r, r, rr2);
+            rs = fma(r, sv, rs);
+            s2 = fma(sv, sv, s2);
             if (corr_next >= 0) Rp[(size_t)i * ldw] = corr_next ? r : sv;
         }
     };
@@ -1386,7 +1403,7 @@ BSP_HD void bsp_back_ckpt_rows(const BspEigChunk &g, int p, int e, int ls, int i
     }
     if (!active) return;
     for (int j = -1; j >= -B; --j) back_step(BspTrue(), j, nullptr, nullptr, 0);
-    bsp_back_finish(g, id, corr_next, sc, rho_p, xSx, xHx, resmax, rr2, xabs);
+    bsp_back_finish(g, id, corr_next, sc, rho_p, xSx, xHx, resmax, rr2, xabs, rs, s2);
 }
 
 /* convergence bookkeeping after a B / residual pass (separate tiny kernel): marks eigenpairs whose scaled residual

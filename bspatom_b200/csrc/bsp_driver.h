@@ -16,7 +16,7 @@
  *   void factor(int iter, int optional);      // F pass (optional: compacted to the eigenpairs the last check listed,
  *                                             //         skipped once everything converged)
  *   void back(int iter, int corr_now, int corr_next, int optional);
- *   void resid(int optional);                 // residual of the current vectors against their own Rayleigh quotient
+ *   void resid(int optional);                 // residual of the listed vectors against their own Rayleigh quotient
  *   void check(int iter, int select);         // convergence marks, compaction list of what is left, bookkeeping
  */
 #ifndef BSP_DRIVER_H
@@ -45,25 +45,23 @@ inline void bsp_enqueue_chunk(Exec &ex, const BspSchedule &sch)
     ex.select();
     ex.prepare();
     /* iteration t: plain for t < 2 (inverse iteration at the bracket midpoint, then at the Rayleigh quotient),
-     * residual-correction form afterwards.  Default (min_iters = 2): after the second solve one cheap residual pass
-     * (no factor traffic) evaluates r = (H - rho S) x with the CURRENT Rayleigh quotient -- a solving pass only knows
-     * its residual against the previous one -- and the check keeps in the iteration what misses conv_tol or has
-     * ||r||_2 / gap > vec_tol (bsp_check_converged): 10-17 % of the eigenpairs of the N = 1000 pencils.  The passes
-     * from there on are COMPACTED to that list (bsp_listed_index), so the correction pass that brings the
-     * S-orthogonality of neighbouring vectors from ~1e-8 to ~1e-12 costs what its eigenpairs cost. */
+     * residual-correction form afterwards.  Default (min_iters = 2): the back sweep of the second solve carries the
+     * sums from which the residual norm against its NEW Rayleigh quotient follows (bsp_back_finish), and the check
+     * keeps in the iteration what misses conv_tol or has ||r||_2 / gap > vec_tol (bsp_check_converged): 10-17 % of
+     * the eigenpairs of the N = 1000 pencils.  The passes from there on are COMPACTED to that list
+     * (bsp_listed_index), so the correction pass that brings the S-orthogonality of neighbouring vectors from ~1e-8
+     * to ~1e-12 costs what its eigenpairs cost.  Compacted passes do not write the next right-hand side (scattered
+     * 8-byte stores): a residual pass over the list (band matvec only, no factor traffic) rebuilds
+     * r = (H - rho S) x with the current quotient in front of every correction. */
     const bool select = sch.min_iters <= 2;
     for (int t = 0; t < sch.max_iters; ++t) {
         const int optional = (t >= sch.min_iters);
-        const bool resid_follows = (t == 1 && select);
-        /* compacted passes do not write the next right-hand side (scattered 8-byte stores, and the pass after the
-         * first correction is almost never needed): when one more is needed, a residual pass over what is left
-         * rebuilds it first */
+        const bool check_follows = (t + 1 == sch.min_iters && select);
         const bool lean = select && optional;
-        if (lean && t > sch.min_iters) ex.resid(1);
+        if (lean) ex.resid(1);
         ex.factor(t, optional);
-        ex.back(t, t >= 2, (resid_follows || lean) ? -1 : (t + 1 >= 2), optional);
-        if (resid_follows) ex.resid(0);
-        if (t + 1 >= sch.min_iters) ex.check(t, resid_follows ? 1 : 0);
+        ex.back(t, t >= 2, (check_follows || lean) ? -1 : (t + 1 >= 2), optional);
+        if (t + 1 >= sch.min_iters) ex.check(t, check_follows ? 1 : 0);
     }
 }
 

@@ -245,30 +245,6 @@ __device__ __forceinline__ void bsp_stage_bars_init(uint64_t *bars)
     }
 }
 
-/* Work-item loops (round / factor / back kernels): a block walks items item = blockIdx.x, blockIdx.x + gridDim.x, ...
- * of (pencil, slice of 128 eigen indices), slices of one pencil adjacent.  With gridDim.x = number of items every
- * block has one item (the classic launch); with gridDim.x = cap x number of SMs the kernel occupies `cap` block slots
- * per SM for its whole duration and leaves the rest of the SM to a kernel of another chunk stream: an FP64-bound
- * bracketing round and an HBM-bound sweep then run side by side on every SM instead of one after the other.
- * The staging barriers are re-created per item (every tile issued in an item is consumed in it). */
-__device__ __forceinline__ void bsp_stage_bars_begin(uint64_t *bars, bool &fresh)
-{
-    if (!fresh) {
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();   /* every thread is through with the previous item's tiles and barriers */
-    }
-    if (threadIdx.x == 0) {
-        if (!fresh) {
-            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bsp_smem_u32(bars)) : "memory");
-            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bsp_smem_u32(bars + 1)) : "memory");
-        }
-        bsp_mbar_init(bars, 1);
-        bsp_mbar_init(bars + 1, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    fresh = false;
-}
-
 /* spectrum bounds: the BSP_NCAND shifts of the ladder, one thread each, band rows staged like in the sweeps */
 template <int B>
 __global__ void __launch_bounds__(BSP_NCAND) bsp_bounds_kernel(BspEigChunk g, double *cand_s, int *cand_c)
@@ -336,32 +312,28 @@ __device__ __forceinline__ double bsp_deflation_sum_block(const BspEigChunk &g, 
  * once, and the cost of the late rounds follows the number of open brackets instead of n.  The order of the list
  * (atomic appends) varies from run to run; the result of an eigen index does not depend on its slot. */
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) bsp_round_kernel(BspEigChunk g, int round, int max_rounds, int open_ok, int nbx)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_ROUND, B)) bsp_round_kernel(BspEigChunk g, int round, int max_rounds, int open_ok)
 {
     using T = BspTile<B>;
     constexpr int SMD = T::SMEM_DOUBLES > BSP_DEFL_TILE ? T::SMEM_DOUBLES : BSP_DEFL_TILE;
     __shared__ __align__(128) double sm[SMD];
     __shared__ __align__(8) uint64_t bars[2];
     if (g.counters[BSP_C_BRACKETED]) return;       /* written by the previous kernel: grid-uniform */
+    const int p = blockIdx.y, slot = blockIdx.x * blockDim.x + threadIdx.x;
     const bool compact = g.olist != nullptr;
     const int rdb = round & 1, wrb = (round + 1) & 1;
     /* two lists per pencil in one array: open brackets from the front (they sweep: kept dense), brackets that
      * became done in the previous round from the back (they only re-publish) */
     const bool listed = compact && round > 0;
-    const int nitems = nbx * g.npencil;
-    bool fresh = true;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int p = item / nbx, bx = item - p * nbx;
-        const int slot = bx * blockDim.x + threadIdx.x;
-        const int cnt_open = listed ? g.ocount[(rdb * g.npencil + p) * 2] : g.n;
-        const int cnt = listed ? cnt_open + g.ocount[(rdb * g.npencil + p) * 2 + 1] : g.n;
-        if ((int)(bx * blockDim.x) >= cnt) continue;     /* block-uniform */
+    const int cnt_open = listed ? g.ocount[(rdb * g.npencil + p) * 2] : g.n;
+    const int cnt = listed ? cnt_open + g.ocount[(rdb * g.npencil + p) * 2 + 1] : g.n;
+    if ((int)(blockIdx.x * blockDim.x) < cnt) {     /* block-uniform */
         const bool valid = slot < cnt;
         const int *list = g.olist + ((size_t)rdb * g.npencil + p) * g.ldw;
         BSP_ASSERT(cnt >= 0 && cnt <= g.n && cnt_open >= 0 && cnt_open <= cnt);
         const int e = !valid ? g.n : (!listed ? slot : (slot < cnt_open ? list[slot] : list[g.ldw - 1 - (slot - cnt_open)]));
         BSP_ASSERT(e >= 0 && e <= g.n);
-        bsp_stage_bars_begin(bars, fresh);
+        bsp_stage_bars_init(bars);
         BspRoundState st;
         st.want_defl = 0; st.want_count = 0; st.done = 1; st.was_done = 1; st.lo = st.hi = 0.0;
         if (valid) bsp_round_begin(g, p, e, round, st);
@@ -417,12 +389,12 @@ __host__ __device__ constexpr int bsp_rhs_ring(int B) { return B <= 6 ? BSP_RHS_
 /* thread -> (eigen index, factor column): identity at full width; in an optional (compacted) pass the slot-th
  * entry of the list the previous convergence check wrote.  Returns false for the whole block when it has nothing
  * to do (block-uniform). */
-__device__ __forceinline__ bool bsp_refine_map(const BspEigChunk &g, int p, int bx, int iter, int listed, int &e, bool &active)
+__device__ __forceinline__ bool bsp_refine_map(const BspEigChunk &g, int p, int iter, int listed, int &e, bool &active)
 {
-    const int slot = bx * blockDim.x + threadIdx.x;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (listed) {
         const int cnt = g.rcount[((iter - 1) & 1) * g.npencil + p];
-        if ((int)(bx * blockDim.x) >= cnt) return false;
+        if ((int)(blockIdx.x * blockDim.x) >= cnt) return false;
         active = slot < cnt;
         e = active ? g.rlist[((size_t)((iter - 1) & 1) * g.npencil + p) * g.ldw + slot] : 0;
         BSP_ASSERT(cnt <= g.n && e >= 0 && e < g.n);
@@ -434,50 +406,40 @@ __device__ __forceinline__ bool bsp_refine_map(const BspEigChunk &g, int p, int 
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_kernel(BspEigChunk g, int iter, int optional, int nbx)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_FACTOR, B)) bsp_factor_kernel(BspEigChunk g, int iter, int optional)
 {
     __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
     constexpr int RING = bsp_rhs_ring(B);
     __shared__ __align__(16) double ring[(RING + 1) * (B + 1) * BSP_EIG_THREADS];
     __shared__ __align__(8) uint64_t bars[2];
     if (optional && g.counters[BSP_C_REFINED]) return;
-    const int nitems = nbx * g.npencil;
-    bool fresh = true;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int p = item / nbx, bx = item - p * nbx;
-        const int ls = bx * blockDim.x + threadIdx.x;
-        int e;
-        bool active;
-        if (!bsp_refine_map(g, p, bx, iter, optional && g.rlist != nullptr, e, active)) continue;
-        bsp_stage_bars_begin(bars, fresh);
-        if (!__syncthreads_or(active)) continue;
-        constexpr int FS = 2 * B + 2;
-        BspRowsStaged<B, RING> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
-        src.rq = ring + threadIdx.x;
-        bsp_factor_forward_rows<B>(g, p, e, ls, iter, active, src);
-    }
+    const int p = blockIdx.y, ls = blockIdx.x * blockDim.x + threadIdx.x;
+    int e;
+    bool active;
+    if (!bsp_refine_map(g, p, iter, optional && g.rlist != nullptr, e, active)) return;
+    bsp_stage_bars_init(bars);
+    if (!__syncthreads_or(active)) return;
+    constexpr int FS = 2 * B + 2;
+    BspRowsStaged<B, RING> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    src.rq = ring + threadIdx.x;
+    bsp_factor_forward_rows<B>(g, p, e, ls, iter, active, src);
 }
 
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_back_kernel(BspEigChunk g, int iter, int corr_now, int corr_next, int optional, int nbx)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_back_kernel(BspEigChunk g, int iter, int corr_now, int corr_next, int optional)
 {
     __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
     __shared__ __align__(8) uint64_t bars[2];
     if (optional && g.counters[BSP_C_REFINED]) return;
-    const int nitems = nbx * g.npencil;
-    bool fresh = true;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int p = item / nbx, bx = item - p * nbx;
-        const int ls = bx * blockDim.x + threadIdx.x;
-        int e;
-        bool active;
-        if (!bsp_refine_map(g, p, bx, iter, optional && g.rlist != nullptr, e, active)) continue;
-        bsp_stage_bars_begin(bars, fresh);
-        if (!__syncthreads_or(active)) continue;
-        constexpr int FS = 2 * B + 2;
-        BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
-        bsp_back_substitute_rows<B>(g, p, e, ls, corr_now, corr_next, active, src);
-    }
+    const int p = blockIdx.y, ls = blockIdx.x * blockDim.x + threadIdx.x;
+    int e;
+    bool active;
+    if (!bsp_refine_map(g, p, iter, optional && g.rlist != nullptr, e, active)) return;
+    bsp_stage_bars_init(bars);
+    if (!__syncthreads_or(active)) return;
+    constexpr int FS = 2 * B + 2;
+    BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
+    bsp_back_substitute_rows<B>(g, p, e, ls, corr_now, corr_next, active, src);
 }
 
 /* ---- check-pointed solves (full-width iterations 0 and 1) ---------------------------------------------------- */
@@ -540,20 +502,23 @@ __global__ void __launch_bounds__(BSP_CKB_THREADS, BSP_CKB_MINB) bsp_back_ckpt_k
     bsp_back_ckpt_rows<B>(g, p, e, e, iter, corr_next, active, src, scr);
 }
 
-/* residual of the vectors in X against their own Rayleigh quotient (after the second solve) */
+/* residual of the vectors in X against their own Rayleigh quotient, in front of a compacted correction pass: the
+ * threads follow the list the last convergence check wrote (iteration `iter` reads the list of iter - 1) */
 template <int B>
-__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_resid_kernel(BspEigChunk g, int optional)
+__global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) bsp_resid_kernel(BspEigChunk g, int iter, int optional)
 {
     __shared__ __align__(128) double sm[BspTile<B>::SMEM_DOUBLES];
     __shared__ __align__(8) uint64_t bars[2];
     if (optional && g.counters[BSP_C_REFINED]) return;
-    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = bsp_refine_active(g, p, e);
+    const int p = blockIdx.y, ls = blockIdx.x * blockDim.x + threadIdx.x;
+    int e;
+    bool active;
+    if (!bsp_refine_map(g, p, iter, optional && g.rlist != nullptr, e, active)) return;
     bsp_stage_bars_init(bars);
     if (!__syncthreads_or(active)) return;
     constexpr int FS = 2 * B + 2;
     BspRowsStaged<B> src{sm, bars, g.fbH + (size_t)p * g.nrows * FS, g.fbS + (size_t)g.inst[p] * g.nrows * FS};
-    bsp_back_substitute_rows<B, true>(g, p, e, e, 0, 1, active, src);
+    bsp_back_substitute_rows<B, true>(g, p, e, ls, 0, 1, active, src);
 }
 
 __global__ void bsp_check_kernel(BspEigChunk g, int iter, int select)
