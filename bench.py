@@ -317,7 +317,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a rank that falls out of step must fail the run, not hold eight GPUs for the default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if world > 1:

@@ -5,6 +5,8 @@
 #ifndef BSP_API_EXTRA_CUH
 #define BSP_API_EXTRA_CUH
 
+#include "bsp_assembly_z.cuh"
+
 namespace {
 
 /* psi(ip, iv) = sum_j C(j,iv) B_j(r_ip)      WRITE_WF, Bsp_Atom.f90:118-146 */
@@ -446,6 +448,77 @@ int bspatom_trans_amp_hermitian(bspatom_handle h, int n, int kd, const double *z
     return 0;
 }
 
+
+/* ---- KIND_PI >= 3 branch of MATRIX_SVT: complex band matrices zAij from the tabulated angular integrals ------- */
+int bspatom_assemble_zaij(bspatom_handle h, const bsp_problem *p, int kind_pi, int nblk, int ncomp_in, const double *zIth,
+                          int ncomp_out, double *zA)
+{
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!p) return -2;
+    if (kind_pi < 3) return -3;
+    if (nblk < 1) return -4;
+    if (!zIth) return -6;
+    if (ncomp_out < 1 || ncomp_out > BSP_ZTERMS) return -7;
+    if (!zA) return -8;
+    bsp_problem q = *p;
+    q.l = 0; q.nvec = 0;
+    if ((rc = validate_problem(q))) return rc;
+    BspZArgs a;
+    memset(&a, 0, sizeof a);
+    a.nterm = ncomp_out;
+    int need_in = 1;
+    for (int c = 0; c < ncomp_out; ++c) {
+        BspZTerm &t = a.term[c];
+        if (kind_pi == 3 || kind_pi == 4) {       /* matrices.f90:117-121 */
+            t.src = c < 2 ? 0 : -1; t.div_r = (c == 0); t.deriv = (c == 1);
+        } else {                                  /* :127-136 */
+            t.src = (c < 2 || kind_pi >= 8) ? c : -1; t.div_r = 0; t.deriv = 0;
+        }
+        if (t.src >= 0) need_in = std::max(need_in, t.src + 1);
+    }
+    if (ncomp_in < need_in) return -5;
+    Group G;
+    G.k = q.k; G.B = q.k - 1; G.n = q.nfun; G.nkp = q.nkp; G.ka = q.ka; G.FS = 2 * G.B + 2;
+    G.npad = BSP_NPAD(G.n, G.B);
+    G.nrows = BSP_NROWS(G.npad, G.B);
+    std::vector<const bsp_problem *> insts = {&q};
+    G.ninst = 1;
+    if ((rc = upload_group_instances(h, G, insts))) { free_group(h, G); return rc; }
+    const int n = q.nfun, ld = 2 * q.k - 1;
+    const size_t n_in = (size_t)q.nkp * q.ka * nblk * ncomp_in, n_out = (size_t)ld * n * nblk * ncomp_out;
+    double *d_in = nullptr, *d_out = nullptr;
+    if ((rc = dev_alloc(h, &d_in, 2 * n_in)) || (rc = dev_alloc(h, &d_out, 2 * n_out))) {
+        if (d_in) dev_free(h, d_in, 2 * n_in);
+        free_group(h, G);
+        return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_in, zIth, sizeof(double) * 2 * n_in, cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * n_out, h->st);
+    a.n = n; a.nkp = q.nkp; a.ka = q.ka; a.nblk = nblk;
+    a.rt = G.d_rt; a.xgwg = G.d_xgwg;
+    a.zIth = (const double2 *)d_in; a.zA = (double2 *)d_out;
+    const dim3 grid((n + BSP_ZTR - 1) / BSP_ZTR, nblk);
+    const size_t smem = sizeof(double) * (size_t)(BSP_ZTR + q.k - 1) * q.ka * (2 * q.k + 2);
+    if (e == cudaSuccess) {
+        switch (q.k) {
+#define BSP_Z_CASE(K_) case K_: \
+            e = cudaFuncSetAttribute(bsp_assemble_zaij_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e == cudaSuccess) bsp_assemble_zaij_kernel<K_><<<grid, 128, smem, h->st>>>(a); break;
+            BSP_Z_CASE(3) BSP_Z_CASE(4) BSP_Z_CASE(5) BSP_Z_CASE(6) BSP_Z_CASE(7) BSP_Z_CASE(8) BSP_Z_CASE(9) BSP_Z_CASE(10)
+#undef BSP_Z_CASE
+        default: rc = BSPATOM_EUNSUPPORTED; break;
+        }
+        h->launches++;
+    }
+    if (e == cudaSuccess && !rc) e = cudaGetLastError();
+    if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(zA, d_out, sizeof(double) * 2 * n_out, cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = BSPATOM_ECUDA; }
+    dev_free(h, d_in, 2 * n_in); dev_free(h, d_out, 2 * n_out);
+    free_group(h, G);
+    return rc;
+}
 
 /* Device-side check of the batch that bspatom_batch_run left resident (nothing crosses PCIe but 4 doubles):
  *   out[0] = max over every eigenpair of every pencil of |H_l c - E S c|_inf / max(1, |E|)   (north star: < 1e-9)

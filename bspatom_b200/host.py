@@ -440,6 +440,51 @@ def _trans_amp_hermitian(self, zA_upper: np.ndarray, Cf: np.ndarray, Ci: np.ndar
 BspAtom.trans_amp_hermitian = _trans_amp_hermitian
 
 
+def _matrix_svt_z(self, kind_pi: int, zIth: np.ndarray, ncomp_out: Optional[int] = None, prob: Optional[Problem] = None) -> np.ndarray:
+    """KIND_PI >= 3 branch of MATRIX_SVT (matrices.f90:110-139, 164-175): the complex band matrices zAij from the
+    angular integrals zIth(nkp, ka, nlm, nm, ncomp) the host tabulated (ZINT_TH, Ang_Ints.f90:544-600).
+    Returns the general band (2k-1, nfun, nlm, nm, ncomp_out), AB[k-1+i-j, j] = zAij[i, j] (0-based), Fortran order."""
+    prob = prob or self.problem()
+    zIth = np.asfortranarray(zIth, dtype=np.complex128)
+    if zIth.ndim != 5:
+        raise BspAtomError("zIth must have the shape (nkp, ka, nlm, nm, ncomp)")
+    nkp, ka, nlm, nm, ncomp = zIth.shape
+    keep: list = []
+    cp = _to_c_problem(prob, 0, 0, keep)
+    if nkp != cp.nkp or ka != cp.ka:
+        raise BspAtomError("zIth is tabulated on (nkp, ka) = (%d, %d), the problem has (%d, %d)" % (nkp, ka, cp.nkp, cp.ka))
+    if ncomp_out is None:
+        ncomp_out = min(4, ncomp) if kind_pi >= 5 else (4 if kind_pi == 4 else 2)
+    zA = np.zeros((2 * prob.k - 1, prob.nfun, nlm, nm, ncomp_out), dtype=np.complex128, order="F")
+    rc = self.lib.bspatom_assemble_zaij(self._h, C.byref(cp), int(kind_pi), nlm * nm, ncomp, zIth.ctypes.data_as(C.c_void_p),
+                                        int(ncomp_out), zA.ctypes.data_as(C.c_void_p))
+    _lib.check(self.lib, self._h, rc, "bspatom_assemble_zaij")
+    return zA
+
+
+BspAtom.MATRIX_SVT_Z = _matrix_svt_z
+
+
+def _tormat_rvec(self, cinl: np.ndarray, R_upper: np.ndarray) -> np.ndarray:
+    """TORMAT's matrix elements of r (TorusFuns.f90:127-158): rvecij(ni, li, nj, lj) = cinl(:,ni,li)^T Xij cinl(:,nj,lj)
+    for ALL pairs in one band x dense product and one DMMA GEMM (the reference: (n1_max (lmax+1))^2 DSYMV + DDOT).
+    cinl: (nfun, n1_max, lmax+1); R_upper: upper band (k, nfun) of Xij = int B_i r B_j (MATRIX_SVT()["R"]); like
+    DSVMV('U') only the upper triangle of Xij is read."""
+    cinl = np.asfortranarray(cinl, dtype=np.float64)
+    n, n1, nl = cinl.shape
+    kd = R_upper.shape[0] - 1
+    A = np.zeros((2 * kd + 1, n), order="F")
+    A[: kd + 1, :] = R_upper                      # AB[kd+i-j, j] = X[i, j], i <= j
+    for d in range(1, kd + 1):                    # mirror: X[j+d, j] = X[j, j+d] = R_upper[kd-d, j+d]
+        A[kd + d, : n - d] = R_upper[kd - d, d:]
+    Cs = cinl.reshape(n, n1 * nl, order="F")
+    G = self.dipole(A, Cs, Cs)
+    return np.asfortranarray(G.reshape(n1, nl, n1, nl, order="F"))
+
+
+BspAtom.TORMAT_RVEC = _tormat_rvec
+
+
 def _dipole_chain(self, A_band: np.ndarray, C_blocks) -> np.ndarray:
     """D[l] = C[l+1]^T A C[l] for all neighbouring l in two launches (cfg5).  C_blocks: sequence of
     (n, nvec) arrays (e.g. BspAtom.cinl); returns (nl-1, nvec, nvec) with D[l] Fortran-ordered blocks."""

@@ -67,16 +67,24 @@ def gather_eigenpairs(E_local: np.ndarray, idx_local: Sequence[int], nitems: int
 def gather_eigenpairs_device(E_dev, C_dev=None, dst: int = 0):
     """The single collective of the path on DEVICE buffers: every rank contributes E_dev (nloc, nfun) and,
     optionally, C_dev (nloc, ncols * nfun: the selected eigenvector columns of its pencils, e.g. filled by
-    BspAtom.batch_download_ptrs straight from the solver's resident blocks) -- torch CUDA tensors with the same
-    shape on every rank; rank ``dst`` receives them over NCCL / NVLink (ncclSend/Recv under dist.gather) as
-    (world, nloc, ...) tensors that stay on its GPU for the writers.  Returns (E_all, C_all) on dst, (None, None)
-    elsewhere, plus the bytes this rank put on the wire."""
+    BspAtom.batch_download_ptrs straight from the solver's resident blocks) -- torch tensors on the rank's GPU
+    (CPU tensors under gloo); rank ``dst`` receives them over NCCL / NVLink (ncclSend/Recv under dist.gather) and
+    keeps them on its GPU for the writers.  nloc may differ between ranks (21 l values over 8 ranks, cfg4): the
+    row counts are exchanged first (one small all_gather) and the blocks are padded to the largest one on the wire,
+    so every rank issues the same collectives whatever its share.  Returns (E_all, C_all, sent_bytes): on dst lists
+    with one (nloc_r, ...) tensor per rank -- stacked into one (world, nloc, ...) tensor when all shares are equal --
+    and (None, None, sent_bytes) elsewhere."""
     import torch
     import torch.distributed as dist
 
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return E_dev.unsqueeze(0), (None if C_dev is None else C_dev.unsqueeze(0)), 0
     world, rank = dist.get_world_size(), dist.get_rank()
+    nloc = torch.tensor([int(E_dev.shape[0])], dtype=torch.int64, device=E_dev.device)
+    counts = [torch.zeros_like(nloc) for _ in range(world)]
+    dist.all_gather(counts, nloc)
+    counts = [int(c[0]) for c in counts]
+    nmax = max(counts)
     sent = 0
     outs = []
     for t in (E_dev, C_dev):
@@ -84,11 +92,19 @@ def gather_eigenpairs_device(E_dev, C_dev=None, dst: int = 0):
             outs.append(None)
             continue
         t = t.contiguous()
+        if t.shape[0] < nmax:      # ragged share: pad the block on the wire
+            pad = torch.zeros((nmax - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            t = torch.cat([t, pad], dim=0)
         recv = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
         dist.gather(t, recv, dst=dst)
         if rank != dst:
             sent += t.numel() * t.element_size()
-        outs.append(torch.stack(recv) if rank == dst else None)
+        if rank != dst:
+            outs.append(None)
+        elif min(counts) == nmax:
+            outs.append(torch.stack(recv))
+        else:
+            outs.append([recv[r][: counts[r]] for r in range(world)])
     return outs[0], outs[1], sent
 
 

@@ -182,6 +182,17 @@ int bspatom_dipole_chain_resident(bspatom_handle h, int i0, int nl, int nvec, in
 int bspatom_trans_amp_hermitian(bspatom_handle h, int n, int kd, const double *zA_upper, int nf, const double *Cf,
                                 int ni, const double *Ci, double *T);
 
+/* ---- KIND_PI >= 3 branch of MATRIX_SVT (matrices.f90:110-139, 164-175) --------- *
+ * zAij(ibra,jket,il,jl,c) = sum_ibet sum_igl fbra * W_c * (fket | dfket) * dr from the angular integrals the host
+ * tabulates on the radial quadrature grid (ZINT_TH, Ang_Ints.f90:544-600):
+ *   zIth : COMPLEX*16 zIth(nkp, ka, nblk, ncomp_in), nblk = nlm*nm blocks (il fastest), Fortran order
+ *   zA   : COMPLEX*16 general band AB(2k-1, nfun, nblk, ncomp_out), AB(k+i-j, j) = zAij(i,j), Fortran order
+ *   kind_pi = 3, 4 : c=1: W = zIth(..,1)/r with fket; c=2: W = zIth(..,1) with dfket; c=3,4 zero (as in the reference)
+ *   kind_pi >= 5   : c=1,2: W = zIth(..,c) with fket; kind_pi >= 8 also c=3,4
+ * Xij = int B_i r B_j (matrices.f90:174) is bspatom_assemble_band's R.  Only the knots / ka of *p are read.  */
+int bspatom_assemble_zaij(bspatom_handle h, const bsp_problem *p, int kind_pi, int nblk, int ncomp_in,
+                          const double *zIth, int ncomp_out, double *zA);
+
 /* ---- wavefunction synthesis: WRITE_WF (Bsp_Atom.f90:101-152) --------------- *
  * psi(ip, iv) = sum_j C(j,iv) B_j(r_ip), r_ip = ra + ip (rb-ra)/npts, ip=0..npts */
 int bspatom_wavefunction(bspatom_handle h, int k, int nfun, int nkp, const double *rt, double ra,

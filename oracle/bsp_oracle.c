@@ -419,6 +419,115 @@ int bsp_matrix_svt(int nfun, int k, int ka, int nkp, const double *rt,
 }
 
 /* ------------------------------------------------------------------------- *
+ * MATRIX_SVT, KIND_PI >= 3 branch        (matrices.f90:110-139, 164-175)
+ * zIth : COMPLEX*16 zIth(nkp, ka, nlm, nm, ncomp) (re,im interleaved), the
+ *        angular integrals on the radial quadrature grid (ZINT_TH, Ang_Ints.f90:544-600)
+ * zA   : COMPLEX*16 zAij(nfun, nfun, nlm, nm, ncomp_out), dense, zero outside the band
+ * Statement by statement: zsumc/zsumd (KIND_PI 3, 4: zsume/zsumf are never accumulated, so
+ * components 3, 4 stay zero, :164-173) and zsumc..zsumf for KIND_PI >= 5 / >= 8.
+ * Complex products are evaluated left to right, real * complex componentwise, like the
+ * Fortran expression fbra * zfAr * fket * dr.
+ * ------------------------------------------------------------------------- */
+int bsp_matrix_zaij(int nfun, int k, int ka, int nkp, const double *rt, const double *aind, const double *xg,
+                    const double *wg, int kind_pi, int nlm, int nm, int ncomp, const double *zIth, int ncomp_out,
+                    double *zA)
+{
+    const double eps = 2.220446049250313e-16;
+    double bsp[ORACLE_MAXK], dbsp[ORACLE_MAXK];
+    const size_t nn = (size_t)nfun * (size_t)nfun, nblk = (size_t)nlm * (size_t)nm;
+    memset(zA, 0, sizeof(double) * 2 * nn * nblk * (size_t)ncomp_out);
+    double *zs = (double *)malloc(sizeof(double) * 2 * nblk * 4);   /* zsumc, zsumd, zsume, zsumf (il, jl) */
+    int rc = 0;
+    for (int ibra = 1; ibra <= nfun && !rc; ++ibra) {           /* :68 */
+        int jlo = ibra - (k - 1) < 1 ? 1 : ibra - (k - 1);
+        int jhi = ibra + (k - 1) > nfun ? nfun : ibra + (k - 1);
+        for (int jket = jlo; jket <= jhi && !rc; ++jket) {      /* :69 */
+            int ibetmin = ibra > jket ? ibra : jket;            /* :71 */
+            int ibetmax = (ibra < jket ? ibra : jket) + k - 1;  /* :72 */
+            memset(zs, 0, sizeof(double) * 2 * nblk * 4);       /* :82-87 */
+            for (int ibet = ibetmin; ibet <= ibetmax && !rc; ++ibet) { /* :89 */
+                double f1 = (rt[ibet] + rt[ibet - 1]) / 2.0;
+                double f2 = (rt[ibet] - rt[ibet - 1]) / 2.0;
+                for (int igl = 0; igl < ka; ++igl) {            /* :94 */
+                    double r = f1 + xg[igl] * f2;
+                    double dr = f2 * wg[igl];
+                    int left;
+                    rc = bspall_impl(rt, nkp, k, nfun, aind, r, ibet + 1, &left, bsp, dbsp);
+                    if (rc) break;
+                    if (r == 0.0) r = eps;                      /* :102 */
+                    int ifun = ibra - (left - k), jfun = jket - (left - k);
+                    if (ifun < 1 || ifun > k || jfun < 1 || jfun > k) { rc = 3; break; }
+                    double fbra = bsp[ifun - 1], fket = bsp[jfun - 1], dfket = dbsp[jfun - 1];
+                    for (int il = 0; il < nlm; ++il) {          /* :111 */
+                        for (int jl = 0; jl < nm; ++jl) {       /* :112 */
+                            size_t b = (size_t)il + (size_t)nlm * (size_t)jl;
+#define ZITH(c, part) zIth[2 * ((size_t)(ibet - 1) + (size_t)nkp * ((size_t)igl + (size_t)ka * (b + nblk * (size_t)(c)))) + (part)]
+                            if (kind_pi == 3 || kind_pi == 4) {
+                                double are = ZITH(0, 0), aim = ZITH(0, 1);         /* zAlm, :118 */
+                                double fre = are / r, fim = aim / r;               /* zfAr = zAlm / r, :119 */
+                                zs[2 * (b + nblk * 0) + 0] += fbra * fre * fket * dr;   /* :120 */
+                                zs[2 * (b + nblk * 0) + 1] += fbra * fim * fket * dr;
+                                zs[2 * (b + nblk * 1) + 0] += fbra * are * dfket * dr;  /* :121 */
+                                zs[2 * (b + nblk * 1) + 1] += fbra * aim * dfket * dr;
+                            } else {
+                                int nc = kind_pi >= 8 ? 4 : 2;                     /* :127-136 */
+                                for (int c = 0; c < nc && c < ncomp; ++c) {
+                                    zs[2 * (b + nblk * c) + 0] += fbra * ZITH(c, 0) * fket * dr;
+                                    zs[2 * (b + nblk * c) + 1] += fbra * ZITH(c, 1) * fket * dr;
+                                }
+                            }
+#undef ZITH
+                        }
+                    }
+                }
+            }
+            size_t ij = (size_t)(ibra - 1) + (size_t)(jket - 1) * (size_t)nfun;
+            for (size_t b = 0; b < nblk; ++b)                   /* :164-173 */
+                for (int c = 0; c < ncomp_out && c < 4; ++c) {
+                    zA[2 * (ij + nn * (b + nblk * (size_t)c)) + 0] = zs[2 * (b + nblk * c) + 0];
+                    zA[2 * (ij + nn * (b + nblk * (size_t)c)) + 1] = zs[2 * (b + nblk * c) + 1];
+                }
+        }
+    }
+    free(zs);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------- *
+ * TORMAT, matrix elements of r           (TorusFuns.f90:127-158)
+ * rvecij(ni, li, nj, lj) = x^T Xij y with x = cinl(:, ni, li), y = cinl(:, nj, lj) through
+ * DSVMV('U', ...) = DSYMV (upper triangle of Xij) + DDOT (Modules.f90:427-452).
+ * cinl: (nfun, n1_max, 0:lmax) column-major; rvec: (n1_max, 0:lmax, n1_max, 0:lmax) column-major.
+ * ------------------------------------------------------------------------- */
+void bsp_tormat_rvec(int nfun, int n1_max, int lmax, const double *cinl, const double *Xij, double *rvec)
+{
+    double *v = (double *)malloc(sizeof(double) * (size_t)nfun);
+    const size_t nl = (size_t)(lmax + 1), nn1 = (size_t)n1_max;
+    for (size_t ni = 0; ni < nn1; ++ni)
+        for (size_t li = 0; li < nl; ++li)
+            for (size_t nj = 0; nj < nn1; ++nj)
+                for (size_t lj = 0; lj < nl; ++lj) {
+                    const double *x = cinl + (size_t)nfun * (ni + nn1 * li);
+                    const double *y = cinl + (size_t)nfun * (nj + nn1 * lj);
+                    /* v = Xij_sym(U) * y : DSYMV('U') reads A(i,j), i <= j, and mirrors it */
+                    for (int i = 0; i < nfun; ++i) v[i] = 0.0;
+                    for (int j = 0; j < nfun; ++j) {            /* reference BLAS column sweep */
+                        double t1 = y[j], t2 = 0.0;
+                        for (int i = 0; i < j; ++i) {
+                            double a = Xij[(size_t)i + (size_t)j * (size_t)nfun];
+                            v[i] += t1 * a;
+                            t2 += a * y[i];
+                        }
+                        v[j] += t1 * Xij[(size_t)j + (size_t)j * (size_t)nfun] + t2;
+                    }
+                    double f = 0.0;
+                    for (int i = 0; i < nfun; ++i) f += x[i] * v[i];   /* DDOT */
+                    rvec[ni + nn1 * (li + nl * (nj + nn1 * lj))] = f;
+                }
+    free(v);
+}
+
+/* ------------------------------------------------------------------------- *
  * H_l = T + U_l + V                       (matrices.f90:244)
  * ------------------------------------------------------------------------- */
 void bsp_hamiltonian(int nfun, const double *T, const double *Ul,

@@ -55,6 +55,9 @@ def lib():
             [C.c_int] * 4 + [_dp] * 4 + [C.c_int, C.c_int, _dp, _dp, C.c_int] + [_dp] * 7
         )
         L.bsp_matrix_svt.restype = C.c_int
+        L.bsp_matrix_zaij.argtypes = [C.c_int] * 4 + [_dp] * 4 + [C.c_int] * 4 + [_dp, C.c_int, _dp]
+        L.bsp_matrix_zaij.restype = C.c_int
+        L.bsp_tormat_rvec.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
         L.bsp_hamiltonian.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
         L.bsp_write_wf.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, _dp, C.c_int, _dp, _dp]
         L.bsp_write_wf.restype = C.c_int
@@ -197,6 +200,32 @@ def matrix_svt(b: Basis, lmax=0, kind_pot=0, par=None, bl=None, want_u=True, fas
     if rc:
         raise IndexError("reference would index bsp() out of bounds (rc=%d)" % rc)
     return dict(S=S, V=V, T=T, U=U, R=R, Ri=Ri, D=D)
+
+
+def matrix_zaij(b: Basis, kind_pi, zIth, ncomp_out):
+    """KIND_PI >= 3 branch of MATRIX_SVT (matrices.f90:110-139, 164-175).
+    zIth: complex array (nkp, ka, nlm, nm, ncomp), Fortran order; returns zAij (nfun, nfun, nlm, nm, ncomp_out), Fortran order."""
+    zIth = np.asfortranarray(zIth, dtype=np.complex128)
+    nkp, ka, nlm, nm, ncomp = zIth.shape
+    assert nkp == b.nkp and ka == b.ka
+    n = b.nfun
+    zA = np.zeros((n, n, nlm, nm, ncomp_out), dtype=np.complex128, order="F")
+    rc = lib().bsp_matrix_zaij(n, b.k, b.ka, b.nkp, _p(b.rt), _p(b.aind), _p(b.xg), _p(b.wg), int(kind_pi), nlm, nm, ncomp,
+                               zIth.ctypes.data_as(_dp), int(ncomp_out), zA.ctypes.data_as(_dp))
+    if rc:
+        raise FloatingPointError("bsp_matrix_zaij rc=%d" % rc)
+    return zA
+
+
+def tormat_rvec(cinl, Xij):
+    """TORMAT's matrix elements of r (TorusFuns.f90:127-158): rvecij(ni, li, nj, lj) = cinl(:,ni,li)^T Xij cinl(:,nj,lj), DSVMV('U').
+    cinl: (nfun, n1_max, lmax+1)."""
+    cinl = np.asfortranarray(cinl, dtype=np.float64)
+    Xij = np.asfortranarray(Xij, dtype=np.float64)
+    n, n1, nl = cinl.shape
+    out = np.zeros((n1, nl, n1, nl), order="F")
+    lib().bsp_tormat_rvec(n, n1, nl - 1, _p(cinl), _p(Xij), _p(out))
+    return out
 
 
 def hamiltonian(T, Ul, V):

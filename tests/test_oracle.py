@@ -206,3 +206,39 @@ def test_reference_enl_dat_if_built(oracle, tmp_path):
         w, _ = oracle.solve_system(m, l)
         # two LAPACK builds (MKL/reference LAPACK there, OpenBLAS here) agree within dsygv's backward error
         assert np.max(np.abs(vals[l] - w)) <= 64 * eps * np.abs(w).max() + 1e-13 * np.abs(w).max()
+
+
+def test_zaij_restatement_reduces_to_scalar_branch():
+    """the complex branch of the restatement (matrices.f90:110-139) against the pinned scalar branch: zIth = 1 gives
+    sumc / sumd of :141-142 (Rinv, D), zIth = r gives sumr of :144 -- bitwise, the arithmetic is the same"""
+    from oracle import oracle as O
+
+    b = O.make_basis(kind_grid=2, k=7, nfun=60, rb=500.0, rmax=40.0)
+    m = O.matrix_svt(b, lmax=0)
+    ones = np.ones((b.nkp, b.ka, 2, 1, 1), dtype=np.complex128, order="F")
+    z = O.matrix_zaij(b, 3, ones, 2)
+    assert np.array_equal(z[:, :, 1, 0, 0].real, m["Ri"]) and np.array_equal(z[:, :, 0, 0, 1].real, m["D"])
+    assert not np.any(z.imag)
+    rtab = np.zeros((b.nkp, b.ka, 1, 1, 2), dtype=np.complex128, order="F")
+    for ibet in range(b.nkp - 1):
+        rtab[ibet, :, 0, 0, 0] = (b.rt[ibet + 1] + b.rt[ibet]) / 2.0 + b.xg * ((b.rt[ibet + 1] - b.rt[ibet]) / 2.0)
+    rtab[:, :, 0, 0, 1] = 1j * rtab[:, :, 0, 0, 0]
+    zx = O.matrix_zaij(b, 5, rtab, 2)
+    assert np.array_equal(zx[:, :, 0, 0, 0].real, m["R"]) and np.array_equal(zx[:, :, 0, 0, 1].imag, m["R"])
+    # KIND_PI = 4 allocates four components and only fills two (matrices.f90:164-173)
+    z4 = O.matrix_zaij(b, 4, np.ones((b.nkp, b.ka, 1, 1, 3), dtype=np.complex128, order="F"), 4)
+    assert not np.any(z4[..., 2:]) and np.array_equal(z4[:, :, 0, 0, 0], z[:, :, 0, 0, 0])
+
+
+def test_tormat_restatement():
+    """DSVMV('U') loops (TorusFuns.f90:130-150, Modules.f90:427-452) against numpy on the mirrored upper triangle"""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(1)
+    n, n1, nl = 40, 5, 3
+    X = rng.standard_normal((n, n))
+    cinl = np.asfortranarray(rng.standard_normal((n, n1, nl)))
+    Xs = np.triu(X) + np.triu(X, 1).T
+    ref = np.einsum("ias,ij,jbt->asbt", cinl, Xs, cinl)
+    got = O.tormat_rvec(cinl, X)
+    assert np.max(np.abs(got - ref)) < 1e-12 * np.abs(ref).max()

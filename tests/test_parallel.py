@@ -124,3 +124,48 @@ def test_numa_binding_helper_is_best_effort():
     out = bind_host_memory_to_gpu("0000:ff:1f.0")          # no such device here
     assert out["node"] is None and out["mempolicy"] is False
     assert os.sched_getaffinity(0) == before
+
+
+def _worker_dev_ragged(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from bspatom_b200.parallel import gather_eigenpairs_device
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nloc = 3 - rank                      # 3 and 2 rows: the 21 l values of cfg4 over 8 ranks give 3,3,3,3,3,2,2,2
+    E = torch.arange(4 * nloc, dtype=torch.float64).view(nloc, 4) + 100 * rank
+    Cc = torch.arange(8 * nloc, dtype=torch.float64).view(nloc, 8) + 1000 * rank
+    Eg, Cg, sent = gather_eigenpairs_device(E, Cc, dst=0)
+    if rank == 0:
+        q.put(([e.numpy() for e in Eg], [c.numpy() for c in Cg]))
+    else:
+        assert Eg is None and Cg is None and sent == 8 * 3 * (4 + 8)     # padded to the largest share on the wire
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tensor_gather_ragged_shares_world2_gloo():
+    """unequal shares (an 8-GPU cfg4 run hung in NCCL on exactly this before the row counts were exchanged first)"""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_dev_ragged, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    Eg, Cg = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in range(2):
+        nloc = 3 - r
+        assert np.array_equal(Eg[r], np.arange(4.0 * nloc).reshape(nloc, 4) + 100 * r)
+        assert np.array_equal(Cg[r], np.arange(8.0 * nloc).reshape(nloc, 8) + 1000 * r)
