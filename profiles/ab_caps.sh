@@ -1,3 +1,4 @@
+# NOTE: the cap_* / stagger / carveout options exist only in commit 33a45dc (work-item launches); results: profiles/ab_caps_r2.txt, DESIGN.md section 12
 # A/B of the capped work-item launches (cap_* = block slots per SM) and the staggered chunk streams
 # usage: bash profiles/ab_caps.sh > gpurun_out/ab_caps.txt
 run() {

@@ -6,7 +6,11 @@ import json
 import shutil
 from collections import OrderedDict
 
+import os
+import sys
+
 SRC, DST = "gpurun_out", "profiles"
+RND = sys.argv[1] if len(sys.argv) > 1 else "r2"      # artefacts are named per round
 
 
 def val(rows, k):
@@ -18,10 +22,11 @@ def val(rows, k):
 
 
 out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from `ncu --set full --clock-control none` "
-                   "(profiles/ncu_final_cmd.sh, half-size step: 204 pencils per launch, N=1000, k=7); raw pages in "
-                   "profiles/prof_*_r1_raw.csv"}
+                   "(profiles/ncu_%s_cmd.sh, half-size step: 204 pencils per launch, N=1000, k=7: one FULL-WIDTH launch of "
+                   "each kernel -- back: first solve, factor: second solve, round: a round with the deflation sum); raw pages in "
+                   "profiles/prof_*_%s_raw.csv" % (RND if RND != "r1" else "final", RND)}
 for k in ("back", "factor", "round"):
-    rows = list(csv.reader(open("%s/prof_%s_r1_raw.csv" % (SRC, k))))
+    rows = list(csv.reader(open("%s/prof_%s_%s_raw.csv" % (SRC, k, RND))))
     r, w = val(rows, "dram__bytes_read.sum"), val(rows, "dram__bytes_write.sum")
     out["bsp_%s_kernel" % k] = {
         "dram_bytes": int(r + w), "dram_read": int(r), "dram_write": int(w), "pencils_per_launch": 204,
@@ -31,12 +36,13 @@ for k in ("back", "factor", "round"):
         "achieved_occupancy_pct": round(val(rows, "sm__warps_active.avg.pct_of_peak_sustained_active"), 1)}
     print(k, out["bsp_%s_kernel" % k])
     for ext in ("details.txt", "raw.csv"):
-        shutil.copy("%s/prof_%s_r1_%s" % (SRC, k, ext), DST)
-json.dump(out, open(DST + "/roofline_r1.json", "w"), indent=1)
-for f in ("bench_r1_n1.json", "bench_r1_n1_explin.json", "bench_r1_reference.json", "configs_r1.jsonl"):
-    shutil.copy("%s/%s" % (SRC, f), DST)
+        shutil.copy("%s/prof_%s_%s_%s" % (SRC, k, RND, ext), DST)
+json.dump(out, open(DST + "/roofline_%s.json" % RND, "w"), indent=1)
+for f in ("bench_%s_n1.json", "bench_%s_n1_explin.json", "bench_%s_reference.json", "configs_%s.jsonl", "tridiag_ab_%s.json"):
+    if os.path.exists("%s/%s" % (SRC, f % RND)):
+        shutil.copy("%s/%s" % (SRC, f % RND), DST)
 
-rows = list(csv.reader(open(SRC + "/launches_all.csv")))
+rows = list(csv.reader(open(SRC + "/launches_all_%s.csv" % RND)))
 start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 h = rows[start]
 ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
@@ -59,9 +65,9 @@ txt = ("one full-size step (408 pencils, 1 chunk stream), ncu --metrics gpu__tim
        + "round kernel launches in order (ms): " + ", ".join("%.3f" % ms for k, ms in last if "round" in k) + "\n"
        + "factor kernel launches in order (ms): " + ", ".join("%.3f" % ms for k, ms in last if "factor" in k) + "\n"
        + "back kernel launches in order (ms): " + ", ".join("%.3f" % ms for k, ms in last if "back" in k) + "\n")
-open(DST + "/launch_shares.txt", "w").write(txt)
+open(DST + "/launch_shares_%s.txt" % RND, "w").write(txt)
 print(txt)
-with open(DST + "/launches_r1.csv", "w") as f:
+with open(DST + "/launches_%s.csv" % RND, "w") as f:
     w = csv.writer(f)
     w.writerow(["launch", "kernel", "gpu__time_duration_ms"])
     for i, (k, ms) in enumerate(last):

