@@ -20,6 +20,7 @@ EXPORTS = [
     "bspatom_alloc_host", "bspatom_free_host",
     "bspatom_assemble_band", "bspatom_solve_batch", "bspatom_batch_upload", "bspatom_batch_run",
     "bspatom_batch_download", "bspatom_get_selection", "bspatom_batch_verify", "bspatom_dsygv_", "bspatom_dipole", "bspatom_dipole_chain", "bspatom_dipole_chain_resident",
+    "bspatom_create_multi", "bspatom_destroy_multi", "bspatom_last_error_multi", "bspatom_set_option_multi", "bspatom_solve_batch_multi",
     "bspatom_trans_amp_hermitian", "bspatom_assemble_zaij", "bspatom_wavefunction", "bspatom_wavefunction_resident", "bspatom_get_stats",
 ]
 
@@ -80,6 +81,12 @@ def load():
     L.bspatom_dipole_chain.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.bspatom_trans_amp_hermitian.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                               C.c_void_p]
+    L.bspatom_create_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, _ip]
+    L.bspatom_destroy_multi.argtypes = [C.c_void_p]
+    L.bspatom_last_error_multi.argtypes = [C.c_void_p]
+    L.bspatom_last_error_multi.restype = C.c_char_p
+    L.bspatom_set_option_multi.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.bspatom_solve_batch_multi.argtypes = [C.c_void_p, C.c_int, C.POINTER(BspProblem), C.c_void_p, C.c_void_p, _ip]
     L.bspatom_assemble_zaij.argtypes = [H, C.POINTER(BspProblem), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.bspatom_wavefunction.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

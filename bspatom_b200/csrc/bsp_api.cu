@@ -19,6 +19,7 @@
 #include <mutex>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bspatom.h"

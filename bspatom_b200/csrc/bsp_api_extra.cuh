@@ -449,6 +449,101 @@ int bspatom_trans_amp_hermitian(bspatom_handle h, int n, int kd, const double *z
 }
 
 
+/* ---- several GPUs from ONE host process (the Fortran driver is one process): SURVEY.md 8(b) ---------------------- *
+ * The problem list is cut into ndev contiguous ranges of equal weight (nfun^2 k per problem; a selection group is never
+ * split), one handle and one host thread per device; every device writes its range of the caller's E / C / info directly
+ * (contiguous slices: E is nfun_p doubles per problem, C nfun_p * nvec_p), so there is no exchange and no collective --
+ * the work list shards by (instance, l) exactly like the one-process-per-GPU path of bench.py. */
+struct bspatom_multi_s {
+    std::vector<bspatom_handle> h;
+    std::string err;
+};
+
+int bspatom_create_multi(bspatom_multi *m, int ndev, const int *dev_ids)
+{
+    if (!m) return -1;
+    *m = nullptr;
+    if (ndev < 1) return -2;
+    if (!dev_ids) return -3;
+    bspatom_multi x = new bspatom_multi_s();
+    for (int d = 0; d < ndev; ++d) {
+        bspatom_handle hd = nullptr;
+        const int rc = bspatom_create(&hd, dev_ids[d]);
+        if (rc) {
+            for (auto y : x->h) bspatom_destroy(y);
+            delete x;
+            return rc;
+        }
+        x->h.push_back(hd);
+    }
+    *m = x;
+    return 0;
+}
+
+int bspatom_destroy_multi(bspatom_multi m)
+{
+    if (!m) return -1;
+    for (auto y : m->h) bspatom_destroy(y);
+    delete m;
+    return 0;
+}
+
+const char *bspatom_last_error_multi(bspatom_multi m) { return m ? m->err.c_str() : "null handle"; }
+
+int bspatom_set_option_multi(bspatom_multi m, const char *name, double value)
+{
+    if (!m) return -1;
+    int rc = 0;
+    for (auto y : m->h) if (int r = bspatom_set_option(y, name, value)) rc = r;
+    return rc;
+}
+
+int bspatom_solve_batch_multi(bspatom_multi m, int nprob, const bsp_problem *probs, double *E, double *C, int *info)
+{
+    if (!m) return -1;
+    if (nprob < 1) return -2;
+    if (!probs) return -3;
+    if (!E) return -4;
+    const int ndev = (int)m->h.size();
+    std::vector<double> w(nprob);
+    double tot = 0.0;
+    for (int p = 0; p < nprob; ++p) { w[p] = (double)probs[p].nfun * probs[p].nfun * probs[p].k; tot += w[p]; }
+    std::vector<int> cut(ndev + 1, nprob);
+    cut[0] = 0;
+    {
+        double acc = 0.0;
+        int d = 1;
+        for (int p = 0; p < nprob && d < ndev; ++p) {
+            acc += w[p];
+            const bool in_group = p + 1 < nprob && probs[p].sel_mode && probs[p + 1].sel_mode && probs[p].sel_group >= 0 &&
+                                  probs[p].sel_group == probs[p + 1].sel_group;
+            if (acc >= tot * d / ndev && !in_group) cut[d++] = p + 1;
+        }
+    }
+    std::vector<long long> eoff(nprob + 1, 0), coff(nprob + 1, 0);
+    for (int p = 0; p < nprob; ++p) {
+        eoff[p + 1] = eoff[p] + probs[p].nfun;
+        coff[p + 1] = coff[p] + (long long)probs[p].nfun * std::max(0, probs[p].nvec);
+    }
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; ++d) {
+        const int p0 = cut[d], p1 = cut[d + 1];
+        if (p1 <= p0) continue;
+        th.emplace_back([&, d, p0, p1] {
+            rcs[d] = bspatom_solve_batch(m->h[d], p1 - p0, probs + p0, E + eoff[p0], C ? C + coff[p0] : nullptr,
+                                         info ? info + p0 : nullptr);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < ndev; ++d)
+        if (rcs[d]) {
+            m->err = "device " + std::to_string(d) + ": " + bspatom_last_error(m->h[d]);
+            return rcs[d];
+        }
+    return 0;
+}
+
 /* ---- KIND_PI >= 3 branch of MATRIX_SVT: complex band matrices zAij from the tabulated angular integrals ------- */
 int bspatom_assemble_zaij(bspatom_handle h, const bsp_problem *p, int kind_pi, int nblk, int ncomp_in, const double *zIth,
                           int ncomp_out, double *zA)

@@ -529,6 +529,52 @@ BspAtom.dipole_chain_resident = _dipole_chain_resident
 BspAtom.wavefunction_resident = _wavefunction_resident
 
 
+class BspAtomMulti:
+    """Several GPUs from one host process (bspatom_create_multi / bspatom_solve_batch_multi): what a single-process
+    Fortran driver binds to spread the (instance, l) list of SOLVE_SYSTEM over the GPUs of a box.
+    bench.py uses one process per GPU instead; both shard the same way and neither has a collective on the compute path."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.lib = _lib.load()
+        self._m = C.c_void_p()
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self.lib.bspatom_create_multi(C.byref(self._m), len(devices), ids)
+        _lib.check(self.lib, None, rc, "bspatom_create_multi")
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self.lib.bspatom_destroy_multi(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: float):
+        if self.lib.bspatom_set_option_multi(self._m, name.encode(), float(value)):
+            raise BspAtomError("bspatom_set_option_multi(%s) failed" % name)
+
+    def solve_batch(self, items: Iterable, nvec: Optional[int] = None, select: Optional["Selection"] = None):
+        """same contract as BspAtom.solve_batch: (list of E arrays, list of C blocks, info)"""
+        items = list(items)
+        arr, keep = build_problem_array(items, nvec, select)
+        nfs, nvs = arr.rec["nfun"].astype(np.int64), arr.rec["nvec"].astype(np.int64)
+        E, Cbuf = pinned_empty(int(nfs.sum())), pinned_empty(int((nfs * nvs).sum()))
+        info = np.zeros(len(items), dtype=np.int32)
+        rc = self.lib.bspatom_solve_batch_multi(self._m, len(items), arr, E.ctypes.data_as(C.c_void_p),
+                                                Cbuf.ctypes.data_as(C.c_void_p), info.ctypes.data_as(_lib._ip))
+        if rc:
+            raise BspAtomError("bspatom_solve_batch_multi failed: rc=%d %s" % (rc, self.lib.bspatom_last_error_multi(self._m).decode()))
+        eo = np.concatenate(([0], np.cumsum(nfs)))
+        co = np.concatenate(([0], np.cumsum(nfs * nvs)))
+        Es = [E[eo[i]:eo[i + 1]] for i in range(len(items))]
+        Cs = [Cbuf[co[i]:co[i + 1]].reshape((int(nfs[i]), int(nvs[i])), order="F") for i in range(len(items))]
+        return Es, Cs, info
+
+
 class BspAtomPipeline:
     """Throughput mode for sweeps: `depth` handles on one GPU alternate over a list of batches, each from its
     own host thread (ctypes releases the GIL).  Every batch does its own H2D, kernels and D2H through

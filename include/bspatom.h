@@ -106,6 +106,19 @@ void bspatom_free_host(void *p);
  * chunk streams when results go to pinned host buffers), "trace" (1: chunk / copy timeline on stderr) */
 int bspatom_set_option(bspatom_handle h, const char *name, double value);
 
+/* ---- several GPUs from one host process (the Fortran driver is ONE process) ------------------- *
+ * bspatom_create_multi opens one handle per listed device; bspatom_solve_batch_multi cuts the problem list into
+ * ndev contiguous ranges of equal weight (a selection group is never split) and runs them concurrently, one host
+ * thread per device, each writing its slice of the caller's E / C / info: the (instance, l) work list shards with no
+ * exchange between devices (the l-loop bodies of SOLVE_SYSTEM share only read-only Sij, Tij, Vij, matrices.f90:242-248).
+ * Same arguments, layout and error behaviour as bspatom_solve_batch.                                                */
+typedef struct bspatom_multi_s *bspatom_multi;
+int bspatom_create_multi(bspatom_multi *m, int ndev, const int *dev_ids);
+int bspatom_destroy_multi(bspatom_multi m);
+const char *bspatom_last_error_multi(bspatom_multi m);
+int bspatom_set_option_multi(bspatom_multi m, const char *name, double value);
+int bspatom_solve_batch_multi(bspatom_multi m, int nprob, const bsp_problem *probs, double *E, double *C, int *info);
+
 /* ---- assembly: replaces MATRIX_SVT (matrices.f90:1-200) ------------------ *
  * Outputs in LAPACK band storage (any may be NULL):
  *   S, H0 = T+V, Q = int B_i B_j/(2 r^2), T, V, R = int B_i r B_j,

@@ -197,3 +197,28 @@ def test_literal_chkphs_option(atom, oracle):
         assert np.array_equal(po.chkphs_ref(b, want), want)
         flips += int(np.sum(np.any(want != np.asarray(C0[l]), axis=0)))
     print("CHKPHS flipped %d of 120 default-convention vectors" % flips)
+
+
+def test_c_driver(tmp_path):
+    """tests/c_driver.c: plain C against include/bspatom.h + libbspatom.so, hydrogen levels through bspatom_solve_batch"""
+    import subprocess
+
+    from test_host import _build_c_driver
+
+    r = subprocess.run([_build_c_driver(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "c_driver: ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_solve_batch_multi_equals_single_handle(atom):
+    """bspatom_solve_batch_multi (several GPUs from one process): the list is cut into contiguous
+    ranges, one host thread per handle; here two handles on the same device -- results are bit-identical to one call
+    on one handle (sharding never changes a pencil's arithmetic)"""
+    a = host_basis(kind_grid=0, k=7, nfun=150, rb=75.0)
+    items = [(a.problem(), l) for l in range(7)]
+    E1, C1, i1 = atom.solve_batch(items, nvec=20)
+    multi = bsp.BspAtomMulti([0, 0])
+    E2, C2, i2 = multi.solve_batch(items, nvec=20)
+    multi.close()
+    assert not i1.any() and not i2.any()
+    for l in range(7):
+        assert np.array_equal(E1[l], E2[l]) and np.array_equal(C1[l], C2[l])

@@ -111,3 +111,29 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "bsp_oracle" not in txt, f
+
+
+def _build_c_driver(tmp_path):
+    import subprocess
+
+    exe = str(tmp_path / "c_driver")
+    libdir = os.path.join(ROOT, "bspatom_b200")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "c_driver.c"), "-L", libdir, "-lbspatom", "-Wl,-rpath," + libdir, "-lm"])
+    return exe
+
+
+def test_c_driver_compiles_and_fails_loudly_without_a_device(tmp_path):
+    """a plain C program binds the header and the library; without a GPU bspatom_create returns
+    BSPATOM_ENODEVICE and nothing is computed (no CPU fallback)"""
+    import subprocess
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_extra.py::test_c_driver")
+    from bspatom_b200 import build as _b
+
+    _b.build()
+    r = subprocess.run([_build_c_driver(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 77 and "no CUDA device" in r.stdout
