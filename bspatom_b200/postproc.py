@@ -228,6 +228,11 @@ def trans_amp_dipole(D: np.ndarray, E_fin: np.ndarray, n0_fin: int, n1_fin: int,
     """T_fi(ni) = An * c0 * <ci_fin(:,ni)| A |ci_ini>, ni = n0_fin..n1_fin (1-based, PhotoIon.f90:96-106), with the
     density-of-states normalisation An = sqrt(2 / (E_fin(ni+1) - E_fin(ni-1))).  D[ni-1] is the matrix element of
     final state ni (one column of bspatom_dipole's result).  Returns the array T_fi(n0_fin:n1_fin)."""
+    # the reference reads E_fin(ni-1) and E_fin(ni+1) out of bounds when there is no bound state in l_fin (n0_fin < 2)
+    # or Emax_fin was not set (n1_fin = nfun); numpy would wrap the index silently -- refuse instead
+    if n0_fin < 2 or n1_fin > len(E_fin) - 1 or n1_fin < n0_fin:
+        raise ValueError("trans_amp_dipole needs 2 <= n0_fin <= n1_fin <= nfun - 1 (density-of-states stencil E_fin(ni-1), "
+                         "E_fin(ni+1), PhotoIon.f90:97): got n0_fin=%d n1_fin=%d nfun=%d" % (n0_fin, n1_fin, len(E_fin)))
     ni = np.arange(n0_fin, n1_fin + 1)                 # 1-based
     An = np.sqrt(2.0 / (E_fin[ni] - E_fin[ni - 2]))    # E_fin(ni+1) - E_fin(ni-1)
     return An * c0 * np.asarray(D, dtype=np.float64)[ni - 1]

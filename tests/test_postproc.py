@@ -211,3 +211,16 @@ def test_cubspl_matches_the_statement_by_statement_restatement():
     yq = np.array([0.0, 1.0, 0.0, 1.0, 0.0])
     v = cubspl(xq, yq, np.array([0.5]))[0]
     assert abs(v - cubspl_ref(xq, yq, [0.5])[0]) < 1e-15
+
+
+def test_trans_amp_dipole_refuses_out_of_range_stencil():
+    """n0_fin < 2 or n1_fin = nfun: the reference reads E_fin out of bounds (PhotoIon.f90:97); numpy would wrap silently"""
+    from bspatom_b200 import postproc
+
+    E = np.linspace(-0.5, 3.0, 30)
+    D = np.ones(30)
+    with pytest.raises(ValueError):
+        postproc.trans_amp_dipole(D, E, 0, 10, 1.0)
+    with pytest.raises(ValueError):
+        postproc.trans_amp_dipole(D, E, 3, 30, 1.0)
+    assert postproc.trans_amp_dipole(D, E, 2, 29, 1.0).shape == (28,)
