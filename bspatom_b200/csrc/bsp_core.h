@@ -1414,11 +1414,12 @@ BSP_HD void bsp_back_ckpt_rows(const BspEigChunk &g, int p, int e, int ls, int i
  * N = 1000 pencils (CPU replay): vec_tol = 1e-12 selects 10-17 % and |C^T S C - I| stays below 1e-11.
  * Unconverged eigen indices are appended to the compaction list the next pass runs on (order varies from run
  * to run; the result of an eigen index does not depend on its slot). */
-BSP_HD void bsp_check_converged(const BspEigChunk &g, int p, int e, int iter, int select)
+/* the test itself: true when eigen index e stays in the iteration (marks it converged otherwise) */
+BSP_HD bool bsp_check_keep(const BspEigChunk &g, int p, int e, int select)
 {
-    if (e >= g.n) return;
+    if (e >= g.n) return false;
     const size_t id = (size_t)p * g.ldw + e;
-    if (g.status[id] & BSP_ST_CONVERGED) return;
+    if (g.status[id] & BSP_ST_CONVERGED) return false;
     const double rho = g.rho[id];
     const double r = g.res[id], a = fmax(1.0, fabs(rho));
     bool ok = (r <= g.conv_tol * a);
@@ -1434,21 +1435,25 @@ BSP_HD void bsp_check_converged(const BspEigChunk &g, int p, int e, int iter, in
         if (!(gp > 0.0)) gp = 0.0;
         ok = (g.res2[id] <= g.vec_tol * gp);
     }
-    if (ok) {
-        g.status[id] |= BSP_ST_CONVERGED;
-    } else {
+    if (ok) g.status[id] |= BSP_ST_CONVERGED;
+    return !ok;
+}
+
+/* host replay form: test + append to the compaction list (the kernel appends warp by warp, bsp_check_kernel) */
+BSP_HD void bsp_check_converged(const BspEigChunk &g, int p, int e, int iter, int select)
+{
+    if (!bsp_check_keep(g, p, e, select)) return;
 #if defined(__CUDA_ARCH__)
-        atomicAdd(g.counters + BSP_C_UNCONV, 1);
-        if (g.rlist) {
-            const int slot = atomicAdd(g.rcount + (iter & 1) * g.npencil + p, 1);
-            BSP_ASSERT(slot >= 0 && slot < g.n);
-            g.rlist[((size_t)(iter & 1) * g.npencil + p) * g.ldw + slot] = e;
-        }
-#else
-        g.counters[BSP_C_UNCONV] += 1;
-        if (g.rlist) g.rlist[((size_t)(iter & 1) * g.npencil + p) * g.ldw + g.rcount[(iter & 1) * g.npencil + p]++] = e;
-#endif
+    atomicAdd(g.counters + BSP_C_UNCONV, 1);
+    if (g.rlist) {
+        const int slot = atomicAdd(g.rcount + (iter & 1) * g.npencil + p, 1);
+        BSP_ASSERT(slot >= 0 && slot < g.n);
+        g.rlist[((size_t)(iter & 1) * g.npencil + p) * g.ldw + slot] = e;
     }
+#else
+    g.counters[BSP_C_UNCONV] += 1;
+    if (g.rlist) g.rlist[((size_t)(iter & 1) * g.npencil + p) * g.ldw + g.rcount[(iter & 1) * g.npencil + p]++] = e;
+#endif
 }
 
 /* a compacted pass of iteration `iter` maps thread `slot` of pencil p to the eigen index the check of

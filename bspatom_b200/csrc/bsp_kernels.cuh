@@ -524,7 +524,26 @@ __global__ void __launch_bounds__(BSP_EIG_THREADS, bsp_minb(BSP_MINB_BACK, B)) b
 __global__ void bsp_check_kernel(BspEigChunk g, int iter, int select)
 {
     if (g.counters[BSP_C_REFINED]) return;
-    bsp_check_converged(g, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, iter, select);
+    const int p = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool keep = bsp_check_keep(g, p, e, select);
+    /* a warp appends its eigen indices as one ascending run (one atomic per warp): the compacted passes that
+     * follow then read X / R columns of neighbouring lanes from the same 32-byte sectors -- the selected pairs are
+     * the ones with close neighbours and come in runs of consecutive indices */
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (mask) {
+        const int lane = threadIdx.x & 31, cnt = __popc(mask);
+        int base = 0;
+        if (lane == 0) {
+            atomicAdd(g.counters + BSP_C_UNCONV, cnt);
+            if (g.rlist) base = atomicAdd(g.rcount + (iter & 1) * g.npencil + p, cnt);
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep && g.rlist) {
+            const int slot = base + __popc(mask & ((1u << lane) - 1u));
+            BSP_ASSERT(slot >= 0 && slot < g.n);
+            g.rlist[((size_t)(iter & 1) * g.npencil + p) * g.ldw + slot] = e;
+        }
+    }
     if (bsp_last_block(g.counters + BSP_C_ARRIVE)) bsp_check_ctl(g, iter);
 }
 
