@@ -404,6 +404,40 @@ class BspAtom(BspInputs):
         _lib.check(self.lib, self._h, rc, "bspatom_wavefunction")
         return r, psi
 
+    # ---- WRITEWF (WriteWF.f90:1-68): many wavefunctions of one l on the r-grid -----------------------
+    def WRITEWF(self, n0: int, n1: int, l0: int, npts: int = 10000, literal: bool = True, path: Optional[str] = None):
+        """The states WRITEWF writes to WFs.dat: n = 1 first, then n = n0 .. n1 (1-based) of cinl(:, :, l0), one column
+        each, evaluated on r = ra + i (rb - ra)/npts in ONE launch of the wavefunction kernel.
+        literal = True keeps the reference's coefficient indexing j = left - nbc1 + jfun (WriteWF.f90:38,51), which is
+        one function higher than WRITE_WF's j = left - k + jfun when nbc1 = k - 1: the same
+        kernel on the coefficient vectors shifted by k - nbc1; literal = False follows WRITE_WF.
+        path: also write the file, FORMAT(100G20.10) (records longer than 100 items wrap like Fortran's format reversion)."""
+        if self.cinl is None:
+            raise BspAtomError("WRITEWF before SOLVE_SYSTEM")
+        Cl = np.asarray(self.cinl[l0])
+        cols = [0] + list(range(n0 - 1, n1))
+        if max(cols) >= Cl.shape[1] or n0 < 1:
+            raise ValueError("WRITEWF: states %d..%d outside the %d eigenvectors kept for l = %d" % (n0, n1, Cl.shape[1], l0))
+        Csel = np.zeros((self.nfun, len(cols)), order="F")
+        shift = (self.k - self.nbc1) if literal else 0
+        Csel[: self.nfun - shift, :] = Cl[shift:, cols]
+        r, fr = self.WRITE_WF(Csel, npts=npts)
+        if shift == 1:
+            # in the first knot interval the literal mapping also reaches j = 1 where WRITE_WF's j = 0 is skipped: it pairs
+            # c(1) with bsp(1), the B-spline that READ_INPUTS dropped for the boundary condition, ((t1 - r)/(t1 - ra))^(k-1)
+            t1 = float(self.rt[self.nbc1])
+            first = r < t1
+            fr[first, :] += np.outer(((t1 - r[first]) / (t1 - self.ra)) ** (self.k - 1), Cl[0, cols])
+        elif shift > 1:
+            raise BspAtomError("WRITEWF(literal=True): nbc1 = %d < k - 1 is not a configuration READ_INPUTS produces" % self.nbc1)
+        if path is not None:
+            with open(path, "w") as f:
+                for i in range(npts + 1):
+                    vals = [r[i]] + [fr[i, j] for j in range(fr.shape[1])]
+                    for a in range(0, len(vals), 100):
+                        f.write("".join(postproc.fortran_g(v, 20, 10) for v in vals[a:a + 100]) + "\n")
+        return r, fr
+
     # ---- TRANS_AMP contraction (PhotoIon.f90:90-105) ------------------------------------
     def dipole(self, A_band: np.ndarray, Cf: np.ndarray, Ci: np.ndarray) -> np.ndarray:
         """D = Cf^T A Ci with A in general band storage (2kd+1, n)."""

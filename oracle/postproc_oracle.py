@@ -288,3 +288,35 @@ def chkphs_ref(b, cinl_l):
         if fr[0] < 0.0 and fr[1] < 0.0 and fr[2] < 0.0:       # :447
             out[:, n] = -out[:, n]
     return out
+
+
+def writewf(b, cinl_l0, n0, n1, nbc1, npts):
+    """WRITEWF (WriteWF.f90:23-61), statement by statement: fr(is), is = 0 .. n1-n0+1, for r = ra + i dr, with the
+    reference's own index mapping jmin = left - nbc1 + 1, jfun = j - (left - nbc1).  cinl_l0: (nfun, nstates) of one l
+    (1-based state n = column n-1).  Plain loops through the oracle's interv / bsplvb: small npts only."""
+    import numpy as np
+
+    from . import oracle as O
+
+    k, nfun, nkp = b.k, b.nfun, b.nkp
+    dr = (b.rb - b.ra) / float(npts)
+    out = np.zeros((npts + 1, n1 - n0 + 2))
+    rr = np.zeros(npts + 1)
+    for i in range(npts + 1):
+        r = b.ra + float(i) * dr
+        left, _ = O.interv(b.rt, r)
+        bsp = O.bsplvb(b.rt, k, r, left)
+        jmin = left - nbc1 + 1
+        jmax = min(jmin + k - 1, nfun)
+        n = 0
+        for is_ in range(0, n1 - n0 + 2):
+            n = 1 if is_ == 0 else n + 1
+            sumf = 0.0
+            for j in range(jmin, jmax + 1):
+                jfun = j - (left - nbc1)
+                sumf = sumf + cinl_l0[j - 1, n - 1] * bsp[jfun - 1]
+            out[i, is_] = sumf
+            if is_ == 0:
+                n = n0 - 1
+        rr[i] = r
+    return rr, out

@@ -222,3 +222,31 @@ def test_solve_batch_multi_equals_single_handle(atom):
     assert not i1.any() and not i2.any()
     for l in range(7):
         assert np.array_equal(E1[l], E2[l]) and np.array_equal(C1[l], C2[l])
+
+
+def test_writewf_literal_and_corrected(oracle, tmp_path):
+    """WRITEWF (WriteWF.f90:1-68): state 1 and states n0..n1 of one l in one launch; literal index mapping
+    (left - nbc1, the reference's own) against the statement-by-statement restatement, corrected mapping against
+    WRITE_WF's; file in FORMAT(100G20.10)"""
+    from oracle import postproc_oracle as PO
+
+    atom = bsp.BspAtom(device=0)
+    inp = bsp.BspInputs.from_values(kind_grid=2, k=7, nfun=100, rb=500.0, rmax=60.0, lmax=1)
+    atom.adopt(inp)
+    atom.SOLVE_SYSTEM()
+    b = oracle.shipped_basis()
+    n0, n1, l0, npts = 3, 9, 1, 150
+    Cl = np.asarray(atom.cinl[l0])
+    r, fr = atom.WRITEWF(n0, n1, l0, npts=npts, literal=True, path=str(tmp_path / "WFs.dat"))
+    rr, ref = PO.writewf(b, Cl, n0, n1, atom.nbc1, npts)
+    assert fr.shape == ref.shape == (npts + 1, n1 - n0 + 2)
+    assert np.allclose(r, rr, rtol=0, atol=1e-13)
+    assert np.max(np.abs(fr - ref)) <= 1e-13 * max(1.0, np.abs(ref).max())
+    # corrected mapping = WRITE_WF of the same columns
+    _, fr2 = atom.WRITEWF(n0, n1, l0, npts=npts, literal=False)
+    for j, n in enumerate([1] + list(range(n0, n1 + 1))):
+        _, psi = oracle.write_wf(b, Cl[:, n - 1], npts=npts)
+        assert np.max(np.abs(fr2[:, j] - psi)) <= 1e-13 * max(1.0, np.abs(psi).max())
+    lines = open(tmp_path / "WFs.dat").read().splitlines()
+    assert len(lines) == npts + 1 and len(lines[0]) == 20 * (n1 - n0 + 3)
+    atom.close()

@@ -224,3 +224,25 @@ def test_trans_amp_dipole_refuses_out_of_range_stencil():
     with pytest.raises(ValueError):
         postproc.trans_amp_dipole(D, E, 3, 30, 1.0)
     assert postproc.trans_amp_dipole(D, E, 2, 29, 1.0).shape == (28,)
+
+
+def test_writewf_restatement_against_write_wf():
+    """WRITEWF's literal index mapping (WriteWF.f90:38,51: left - nbc1) = WRITE_WF's (Bsp_Atom.f90:133,138: left - k) on
+    coefficients shifted by k - nbc1, plus c(1) times the dropped first B-spline in the first knot interval"""
+    from oracle import oracle as O
+    from oracle import postproc_oracle as PO
+
+    b = O.make_basis(kind_grid=0, k=5, nfun=40, rb=20.0)
+    m = O.matrix_svt(b, lmax=0)
+    w, v = O.solve_system(m, 0)
+    nbc1 = int(np.sum(b.rt == b.rt[0]))
+    assert nbc1 == b.k - 1
+    rr, out = PO.writewf(b, v, 2, 4, nbc1, 97)
+    t1 = b.rt[nbc1]
+    for j, n in enumerate([1, 2, 3, 4]):
+        c = np.zeros(b.nfun)
+        c[: b.nfun - 1] = v[1:, n - 1]
+        _, psi = O.write_wf(b, c, npts=97)
+        first = rr < t1
+        psi[first] += ((t1 - rr[first]) / (t1 - b.ra)) ** (b.k - 1) * v[0, n - 1]
+        assert first.sum() >= 2 and np.max(np.abs(out[:, j] - psi)) < 1e-14
