@@ -431,6 +431,8 @@ class BspAtom(BspInputs):
         elif shift > 1:
             raise BspAtomError("WRITEWF(literal=True): nbc1 = %d < k - 1 is not a configuration READ_INPUTS produces" % self.nbc1)
         if path is not None:
+            from . import postproc
+
             with open(path, "w") as f:
                 for i in range(npts + 1):
                     vals = [r[i]] + [fr[i, j] for j in range(fr.shape[1])]
