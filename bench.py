@@ -81,6 +81,22 @@ def workload(cfg: str, bsp, rank: int, world: int, zrep: int, grid: str):
     raise SystemExit("unknown config " + cfg)
 
 
+def shard_sizes(cfg: str, world: int, zrep: int):
+    if cfg in ("cfg2", "cfg5"):
+        return [51 * zrep] * world
+    total = 4096 if cfg == "cfg3" else 21
+    return [len(range(r, total, world)) for r in range(world)]
+
+
+def config_dict(cfg: str, grid: str, world: int, zrep: int):
+    """the `config` object of the bench line: the same for this arm and the reference arm (the driver compares them)"""
+    return {"workload": label(cfg, grid), "solves_per_step_per_gpu": shard_sizes(cfg, world, zrep),
+            "charges_per_gpu": zrep if cfg == "cfg2" else None,
+            "l2": "no flush: each chunk's factor workspace (56 KB per eigenpair, GBs per chunk) is far larger than the 126 MB L2",
+            "parallelism": "shard the (instance, l) list over %d rank(s), no collective on the compute path; one "
+                           "NCCL gather of eigenpairs from device buffers in the end-to-end legs" % world}
+
+
 class ClockSampler(threading.Thread):
     """samples SM clock / throttle reasons while the timed region runs (NVML, 100 ms)."""
 
@@ -237,7 +253,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True,
         "scaling": "weak" if cfg in ("cfg2", "cfg5") else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": label("cfg2" if cfg == "cfg5" else cfg, args.grid), "sample": "per step: " + desc},
+        # the same object as this repo's own arm prints for this N (the sample of the workload a CPU step covers is
+        # described in cpu_baseline.sample)
+        "config": config_dict("cfg2" if cfg == "cfg5" else cfg, args.grid, max(1, args.gpus), args.zrep),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
                          "sample": desc + "; no Fortran compiler in the image or on the box (profiles/box_probe_r2.json): "
                                           "the reference itself cannot be built, this is its algorithm restated"},
@@ -638,11 +656,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / steps, "higher_is_better": True,
             "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": label(args.config, args.grid), "solves_per_step_per_gpu": wl["shard"],
-                       "charges_per_gpu": args.zrep if args.config == "cfg2" else None,
-                       "l2": "no flush: each chunk's factor workspace (56 KB per eigenpair, GBs per chunk) is far larger than the 126 MB L2",
-                       "parallelism": "shard the (instance, l) list over %d rank(s), no collective on the compute path; one "
-                                      "NCCL gather of eigenpairs from device buffers in the end-to-end legs" % world},
+            "config": config_dict(args.config, args.grid, world, args.zrep),
             "clocks": sampler.summary(), "host_numa": numa, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "step_roofline": step_roof, "cpu_baseline": cpu_baseline, "accuracy": accuracy,
             "kernel_ms_per_step_single_stream": {n_: float(m_) / steps for n_, m_ in zip(names, k1ms)},

@@ -392,7 +392,10 @@ struct GpuExec {
     dim3 grid() const { return dim3((g.n + BSP_EIG_THREADS - 1) / BSP_EIG_THREADS, g.npencil); }
     /* compacted passes: a pencil lists 10-17 % of its eigenpairs (64-thread blocks were measured: factor +0.25 ms,
      * no gain overall) */
-    static constexpr int LISTED_THREADS = 128;
+#ifndef BSP_LISTED_THREADS
+#define BSP_LISTED_THREADS 128
+#endif
+    static constexpr int LISTED_THREADS = BSP_LISTED_THREADS;
     dim3 grid_listed() const { return dim3((g.n + LISTED_THREADS - 1) / LISTED_THREADS, g.npencil); }
     void note() {
         h->launches++;
