@@ -285,12 +285,18 @@ class BspAtom(BspInputs):
         return out
 
     # ---- SOLVE_SYSTEM core (matrices.f90:242-265) --------------------------------------
-    def SOLVE_SYSTEM(self, nvec: Optional[int] = None):
+    def SOLVE_SYSTEM(self, nvec: Optional[int] = None, device_select: Optional[bool] = None):
         """Loop l = 0..lmax of the reference, as ONE batched call.  Fills Enl, cinl, info.
-        Raises like the reference STOPs (matrices.f90:250-254) when info != 0."""
+        Raises like the reference STOPs (matrices.f90:250-254) when info != 0.
+        device_select (default: on for KIND_PI >= 3 with a given Emax_fin): the reference keeps ctemp(:, 1:ntemp, l)
+        only (matrices.f90:296-334); the same rule then runs on the device right after the eigenvalue stage, and only
+        those columns are refined and copied (cinl blocks keep the shape (nfun, nvec); columns >= ntemp(l) are unset)."""
         prob = self.problem()
         ls = list(range(self.lmax + 1))
-        E, Cs, info = self.solve_batch([(prob, l) for l in ls], nvec=nvec)
+        if device_select is None:
+            device_select = self.KIND_PI >= 3 and self.Emax_fin != -1.0
+        select = Selection.from_kind_pi(self.Emax_fin, self.KIND_PI) if device_select else None
+        E, Cs, info = self.solve_batch([(prob, l) for l in ls], nvec=nvec, select=select)
         self.info = info
         bad = [(l, i) for l, i in zip(ls, info) if i != 0]
         if bad:

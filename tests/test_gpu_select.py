@@ -119,3 +119,53 @@ def test_resident_dipole_chain_and_wavefunction(atom, oracle):
         assert np.max(np.abs(D_sel[l] - ref[l])) < 1e-12 * np.abs(ref[l]).max()
     with pytest.raises(bsp.BspAtomError):
         atom.dipole_chain_resident(Rb, 0, 4, int(nsel.min()) + 1 if nsel.min() < 200 else 201)
+
+
+def test_solve_system_outputs_with_device_selection(oracle, tmp_path):
+    """SURVEY.md 8(f) row f-2 end to end on the GPU path: SOLVE_SYSTEM (KIND_PI = 3, Emax_fin given) with the state
+    selection on the device, then Enl.dat / Eigenvec_All.dat -- against (a) the same with every eigenvector computed and
+    the selection on the host and (b) the oracle's dsygv eigenpairs pushed through the restated bookkeeping
+    (matrices.f90:269-378)."""
+    from oracle import postproc_oracle as PO
+
+    def run(device_select, sub):
+        atom = bsp.BspAtom(device=0)
+        inp = bsp.BspInputs.from_values(kind_grid=2, k=7, nfun=100, rb=500.0, rmax=60.0, lmax=2)
+        atom.adopt(inp)
+        atom.KIND_PI, atom.l_ini, atom.l_fin, atom.Emax_fin = 3, 0, 1, 0.4
+        atom.SOLVE_SYSTEM(device_select=device_select)
+        d = tmp_path / sub
+        d.mkdir()
+        atom.write_outputs(str(d))
+        out = (atom.Enl.copy(), atom.sel, atom.selection().copy(), open(d / "Enl.dat").read().splitlines(),
+               open(d / "Eigenvec_All.dat").read().splitlines())
+        atom.close()
+        return out
+
+    Enl_d, sel_d, ns_d, enl_d, vec_d = run(True, "dev")
+    Enl_h, sel_h, ns_h, enl_h, vec_h = run(False, "host")
+    nfun = Enl_d.shape[0]
+    # the device computed exactly the ntemp(l) columns the reference keeps; the host run computed all
+    assert list(ns_d) == list(sel_d.ntemp) and list(ns_h) == [nfun] * 3
+    assert list(sel_d.ntemp) == list(sel_h.ntemp) and sel_d.n1_max == sel_h.n1_max and np.array_equal(sel_d.n01, sel_h.n01)
+    assert max(sel_d.ntemp) < nfun                      # the selection does cut work on this input
+    # eigenvalues: identical where a vector was computed (Rayleigh quotients), closed brackets elsewhere
+    tol = np.maximum(1e-12 * np.abs(Enl_h), 1e-10)
+    assert np.all(np.abs(Enl_d - Enl_h) <= tol)
+    # files: same structure, same numbers to the printed digits for the kept states
+    assert len(enl_d) == len(enl_h) == 1 + 3 * nfun and vec_d[0] == vec_h[0] and len(vec_d) == len(vec_h)
+    for a, b in zip(vec_d[1:], vec_h[1:]):
+        if len(a) < 30:
+            assert a == b
+        else:
+            va = np.array([float(a[5 + 20 * i: 25 + 20 * i]) for i in range(nfun)])
+            vb = np.array([float(b[5 + 20 * i: 25 + 20 * i]) for i in range(nfun)])
+            assert np.max(np.abs(va - vb)) <= 1e-9 * max(1.0, np.abs(vb).max())
+    # against the oracle: dsygv spectra through the restated bookkeeping
+    bo = oracle.shipped_basis()
+    m = oracle.matrix_svt(bo, lmax=2)
+    Eo = np.stack([oracle.solve_system(m, l)[0] for l in range(3)], axis=1)
+    ref = PO.solve_system_bookkeeping(Eo, 3, 0, 1, 0.4)
+    assert list(ref["ntemp"]) == list(sel_d.ntemp) and ref["n1_max"] == sel_d.n1_max
+    tol = np.maximum(np.maximum(1e-12 * np.abs(Eo), 1e-10), 64 * np.finfo(float).eps * np.abs(Eo).max())
+    assert np.all(np.abs(Enl_d - Eo) <= tol)
