@@ -61,7 +61,9 @@ inline void bsp_enqueue_chunk(Exec &ex, const BspSchedule &sch)
         if (lean) ex.resid(1);
         ex.factor(t, optional);
         ex.back(t, t >= 2, (check_follows || lean) ? -1 : (t + 1 >= 2), optional);
-        if (t + 1 >= sch.min_iters) ex.check(t, check_follows ? 1 : 0);
+        /* check: 1 = residual / gap test that selects the correction pass; 2 = the looser one after a correction (not
+         * after the last enqueued pass: what is still listed there counts as unconverged and the chunk is redone) */
+        if (t + 1 >= sch.min_iters) ex.check(t, check_follows ? 1 : ((select && t + 1 < sch.max_iters) ? 2 : 0));
     }
 }
 
