@@ -1,5 +1,5 @@
 # after the "another correction pass" rule: GPU tests, cfg3 / cfg2 / cfg4 bench lines (orthonormality over every pencil, time per step)
-python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -2
+python -m pytest tests/test_gpu_solve.py tests/test_gpu_debug.py -m gpu -q --timeout 900 2>&1 | tail -2
 python bench.py --steps 3 --warmup 3 --config cfg3 --no-cpu-baseline > gpurun_out/bench_r2_cfg3_n1.json 2> gpurun_out/bench_r2_cfg3_n1.err; echo cfg3 rc=$?
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b_quick.json 2> gpurun_out/b_quick.err; echo cfg2 rc=$?
 python bench.py --steps 3 --warmup 3 --config cfg4 --no-cpu-baseline --no-e2e > gpurun_out/b_cfg4.json 2> gpurun_out/b_cfg4.err; echo cfg4 rc=$?
