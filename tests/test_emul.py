@@ -178,3 +178,26 @@ def test_schedule_budget(emul, oracle, kw, lmax, max_rounds):
         E, Cm, st = solve(emul, H, m["S"], b.k - 1)
         assert st[0] <= max_rounds, (l, st[0])
         assert st[1] <= 3 and st[2] == 0 and st[3] == 0 and st[5] == 0, (l, list(st))
+
+
+def test_near_threshold_level_gets_a_second_correction(emul, oracle):
+    """cfg3 problem 1097 (Tietz Z = 13, t = 0.955, l = 1, N = 500): the highest bound level (E = -4.8e-4) kept components
+    of its neighbours at 1e-9 after ONE correction pass (large pivot growth of the un-pivoted factor near threshold):
+    |C^T S C - I| was 1.7e-9 on the GPU and in this replay, bit for bit.  With the check after a correction pass looking at
+    ||r||_2 / gap as well, that vector takes one more pass (4 iterations instead of 3) and the defect is below 1e-10."""
+    from cases import cfg3_problems
+
+    _, items = cfg3_problems(1098)
+    p, l = items[1097]
+    assert p.pot_kind == 11 and l == 1
+    b = oracle.make_basis(kind_grid=0, k=7, nfun=500, rb=500.0)
+    par = np.zeros(8)
+    par[:2] = p.pot_par[:2]
+    m = oracle.matrix_svt(b, lmax=l, kind_pot=p.pot_kind, par=par)
+    H = oracle.hamiltonian(m["T"], m["U"][:, :, l], m["V"])
+    E, Cm, st = solve(emul, H, m["S"], 6)
+    assert st[1] == 4                                   # iterations
+    G = Cm.T @ m["S"] @ Cm - np.eye(500)
+    assert np.abs(G).max() < 1e-10
+    res = np.abs(H @ Cm - (m["S"] @ Cm) * E).max(0) / np.maximum(1.0, np.abs(E))
+    assert res.max() < 1e-12
