@@ -135,7 +135,12 @@ int bspatom_assemble_band(bspatom_handle h, const bsp_problem *p, double *S, dou
  *     nfun_p x nvec_p, column j = eigenvector j, C^T S C = I  (Hij on exit of DSYGV).
  *     Sign: the first coefficient with |c_i| >= 1e-6 max|c| is positive.
  * info[p]: 0 ok; nfun+i: S not positive definite at pivot i; 1..nfun: that
- *     many eigenpairs missed the residual tolerance.                         */
+ *     many eigenpairs missed the residual tolerance, left their bracket, or form a
+ *     numerically degenerate pair (|E_i - E_{i+1}| <= 256 eps |E|): every vector comes
+ *     from its own inverse iteration and nothing re-orthogonalises within such a pair
+ *     (LAPACK's dstein would) -- radial Sturm-Liouville spectra are simple, so the
+ *     reference's pencils never get there; an arbitrary pencil through bspatom_dsygv_
+ *     can, and is told so through info instead of silently non-orthogonal vectors.  */
 int bspatom_solve_batch(bspatom_handle h, int nprob, const bsp_problem *probs, double *E, double *C,
                         int *info);
 
