@@ -6,6 +6,7 @@
  * exit 0: ok;  77: no CUDA device (bspatom_create -> BSPATOM_ENODEVICE: the path has no CPU fallback);  1: failure.
  */
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,6 +15,11 @@
 
 int main(void)
 {
+    /* layout of struct bsp_problem as this C compiler sees it: the Python (ctypes) and Fortran (BIND(C)) mirrors must agree */
+    printf("c_driver: sizeof(bsp_problem) = %zu, offsets rt %zu pot_par %zu v_tab %zu l %zu ul_extra %zu nvec %zu sel_mode %zu sel_ecut_a %zu sel_ecut_b %zu\n",
+           sizeof(bsp_problem), offsetof(bsp_problem, rt), offsetof(bsp_problem, pot_par), offsetof(bsp_problem, v_tab),
+           offsetof(bsp_problem, l), offsetof(bsp_problem, ul_extra), offsetof(bsp_problem, nvec), offsetof(bsp_problem, sel_mode),
+           offsetof(bsp_problem, sel_ecut_a), offsetof(bsp_problem, sel_ecut_b));
     bspatom_handle h = NULL;
     int rc = bspatom_create(&h, 0);
     if (rc == BSPATOM_ENODEVICE) { printf("c_driver: no CUDA device (rc=%d), nothing computed\n", rc); return 77; }

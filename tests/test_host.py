@@ -137,3 +137,9 @@ def test_c_driver_compiles_and_fails_loudly_without_a_device(tmp_path):
     _b.build()
     r = subprocess.run([_build_c_driver(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 77 and "no CUDA device" in r.stdout
+    # struct bsp_problem: the C compiler's layout = the ctypes mirror (= the BIND(C) type of INTEGRATION.md)
+    P = _lib.BspProblem
+    want = "sizeof(bsp_problem) = %d, offsets rt %d pot_par %d v_tab %d l %d ul_extra %d nvec %d sel_mode %d sel_ecut_a %d sel_ecut_b %d" % (
+        ctypes.sizeof(P), P.rt.offset, P.pot_par.offset, P.v_tab.offset, P.l.offset, P.ul_extra.offset, P.nvec.offset,
+        P.sel_mode.offset, P.sel_ecut_a.offset, P.sel_ecut_b.offset)
+    assert want in r.stdout, r.stdout
