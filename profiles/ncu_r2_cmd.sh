@@ -5,6 +5,7 @@ set -x
 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_gpu_r2.log 2>&1; tail -3 gpurun_out/pytest_gpu_r2.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r2.log 2>&1; tail -2 gpurun_out/smoke_r2.log
 # north star stages (ii)+(iii) as a stand-alone A/B: band -> tridiagonal bulge chasing and one tridiagonal Sturm round, 408 matrices
+[ -x profiles/micro/tridiag_ab ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o profiles/micro/tridiag_ab profiles/micro/tridiag_ab.cu
 timeout 300 ./profiles/micro/tridiag_ab 1000 6 408 3 gpurun_out/tri.bin > gpurun_out/tridiag_ab_r2.json 2> gpurun_out/tridiag_ab_r2.err; cat gpurun_out/tridiag_ab_r2.json
 timeout 300 python profiles/micro/tridiag_ab_check.py gpurun_out/tri.bin > gpurun_out/tridiag_ab_check_r2.json 2>&1; cat gpurun_out/tridiag_ab_check_r2.json; rm -f gpurun_out/tri.bin
 python bench.py --steps 8 --warmup 3 > gpurun_out/bench_r2_n1.json 2> gpurun_out/bench_r2_n1.err; tail -2 gpurun_out/bench_r2_n1.err
