@@ -242,3 +242,51 @@ def test_tormat_restatement():
     ref = np.einsum("ias,ij,jbt->asbt", cinl, Xs, cinl)
     got = O.tormat_rvec(cinl, X)
     assert np.max(np.abs(got - ref)) < 1e-12 * np.abs(ref).max()
+
+
+def test_matrix_svt_against_scipy_bsplines():
+    """Independent pin of the restated MATRIX_SVT (matrices.f90:68-183): the same integrals from third-party code --
+    scipy.interpolate.BSpline for the basis functions and their derivatives (B_j lives on the knots rt(j..j+k)),
+    numpy's Gauss-Legendre nodes -- with the reference's own quadrature rule (ka points per knot interval; ka = k+3 = 10
+    is even here, so gauleg's odd-ka quirk does not enter).  S, T, r and B_i B_j' are polynomial and exact at ka points;
+    V = -Z/r and the centrifugal term are not: they are compared at the SAME ka-point rule, which is what the reference
+    computes."""
+    from scipy.interpolate import BSpline
+
+    from oracle import oracle as O
+
+    for kw in (dict(kind_grid=0, k=7, nfun=40, rb=20.0), dict(kind_grid=2, k=7, nfun=60, rb=500.0, rmax=40.0)):
+        b = O.make_basis(**kw)
+        k, n = b.k, b.nfun
+        assert b.ka % 2 == 0
+        m = O.matrix_svt(b, lmax=2)
+        xg, wg = np.polynomial.legendre.leggauss(b.ka)
+        assert np.allclose(np.sort(b.xg), xg, rtol=0, atol=1e-15)
+        funs = [BSpline.basis_element(b.rt[j:j + k + 1], extrapolate=False) for j in range(n)]
+        ders = [f.derivative() for f in funs]
+        mats = {nm: np.zeros((n, n)) for nm in ("S", "T", "V", "R", "Ri", "D", "U1", "U2")}
+        for ibet in range(b.nkp - 1):
+            ta, tb = b.rt[ibet], b.rt[ibet + 1]
+            if not tb > ta:
+                continue
+            r = (tb + ta) / 2 + xg * (tb - ta) / 2
+            dr = wg * (tb - ta) / 2
+            js = [j for j in range(n) if b.rt[j] <= ta and tb <= b.rt[j + k]]
+            F = {j: np.nan_to_num(funs[j](r)) for j in js}
+            dF = {j: np.nan_to_num(ders[j](r)) for j in js}
+            for i in js:
+                for j in js:
+                    mats["S"][i, j] += np.sum(F[i] * F[j] * dr)
+                    mats["T"][i, j] += np.sum(dF[i] * 0.5 * dF[j] * dr)
+                    mats["V"][i, j] += np.sum(F[i] * (-1.0 / r) * F[j] * dr)
+                    mats["R"][i, j] += np.sum(F[i] * r * F[j] * dr)
+                    mats["Ri"][i, j] += np.sum(F[i] / r * F[j] * dr)
+                    mats["D"][i, j] += np.sum(F[i] * dF[j] * dr)
+                    mats["U1"][i, j] += np.sum(F[i] * (2.0 / (2.0 * r * r)) * F[j] * dr)
+                    mats["U2"][i, j] += np.sum(F[i] * (6.0 / (2.0 * r * r)) * F[j] * dr)
+        ref = dict(S=m["S"], T=m["T"], V=m["V"], R=m["R"], Ri=m["Ri"], D=m["D"], U1=m["U"][:, :, 1], U2=m["U"][:, :, 2])
+        for nm, got in mats.items():
+            scale = np.abs(ref[nm]).max(axis=1, keepdims=True)
+            err = np.max(np.abs(got - ref[nm]) / scale)
+            assert err < 1e-13, (kw, nm, err)        # measured: 5e-15 .. 3e-14
+        assert not np.any(m["U"][:, :, 0])
