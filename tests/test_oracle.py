@@ -290,3 +290,63 @@ def test_matrix_svt_against_scipy_bsplines():
             err = np.max(np.abs(got - ref[nm]) / scale)
             assert err < 1e-13, (kw, nm, err)        # measured: 5e-15 .. 3e-14
         assert not np.any(m["U"][:, :, 0])
+
+
+def test_write_wf_and_zaij_against_scipy_bsplines():
+    """WRITE_WF (Bsp_Atom.f90:118-146) and the KIND_PI >= 3 branch of MATRIX_SVT (matrices.f90:110-139) restatements
+    against scipy.interpolate.BSpline: psi(r) = sum_j c_j B_j(r), and zAij = sum fbra W (fket | dfket) dr with a complex
+    table W on the quadrature grid."""
+    from scipy.interpolate import BSpline
+
+    from oracle import oracle as O
+
+    b = O.make_basis(kind_grid=0, k=6, nfun=30, rb=15.0)
+    k, n = b.k, b.nfun
+    rng = np.random.default_rng(4)
+    c = rng.standard_normal(n)
+    r, psi = O.write_wf(b, c, npts=333)
+    ref = sum(c[j] * np.nan_to_num(BSpline.basis_element(b.rt[j:j + k + 1], extrapolate=False)(r)) for j in range(n))
+    inner = (r > b.rt[0]) & (r < b.rt[-1])
+    assert np.max(np.abs(psi[inner] - ref[inner])) < 1e-13 * np.abs(ref).max()
+    # complex table: smooth in r, different per block / component
+    nlm, nm, ncomp = 2, 1, 2
+    xg, wg = np.polynomial.legendre.leggauss(b.ka)
+    if not np.allclose(np.sort(b.xg), xg, atol=1e-15):
+        pytest.skip("odd ka: gauleg's middle-weight quirk, not numpy's rule")
+    order = np.argsort(b.xg)                      # the reference's node order is gauleg's, not ascending
+    z = np.zeros((b.nkp, b.ka, nlm, nm, ncomp), dtype=np.complex128, order="F")
+    rr = np.zeros((b.nkp, b.ka))
+    for ibet in range(b.nkp - 1):
+        rr[ibet] = (b.rt[ibet + 1] + b.rt[ibet]) / 2 + b.xg * (b.rt[ibet + 1] - b.rt[ibet]) / 2
+        for il in range(nlm):
+            for cc in range(ncomp):
+                z[ibet, :, il, 0, cc] = np.exp(1j * (0.3 + 0.2 * il) * rr[ibet]) * (1.0 + 0.5 * cc) / (1.0 + rr[ibet])
+    zA3 = O.matrix_zaij(b, 3, z, 2)
+    zA5 = O.matrix_zaij(b, 5, z, 2)
+    funs = [BSpline.basis_element(b.rt[j:j + k + 1], extrapolate=False) for j in range(n)]
+    ders = [f.derivative() for f in funs]
+    ref3 = np.zeros((n, n, nlm, 2), dtype=np.complex128)
+    ref5 = np.zeros((n, n, nlm, 2), dtype=np.complex128)
+    for ibet in range(b.nkp - 1):
+        ta, tb = b.rt[ibet], b.rt[ibet + 1]
+        if not tb > ta:
+            continue
+        rq = rr[ibet]
+        dr = b.wg * (tb - ta) / 2
+        js = [j for j in range(n) if b.rt[j] <= ta and tb <= b.rt[j + k]]
+        F = {j: np.nan_to_num(funs[j](rq)) for j in js}
+        dF = {j: np.nan_to_num(ders[j](rq)) for j in js}
+        for i in js:
+            for j in js:
+                for il in range(nlm):
+                    w1, w2 = z[ibet, :, il, 0, 0], z[ibet, :, il, 0, 1]
+                    ref3[i, j, il, 0] += np.sum(F[i] * (w1 / rq) * F[j] * dr)
+                    ref3[i, j, il, 1] += np.sum(F[i] * w1 * dF[j] * dr)
+                    ref5[i, j, il, 0] += np.sum(F[i] * w1 * F[j] * dr)
+                    ref5[i, j, il, 1] += np.sum(F[i] * w2 * F[j] * dr)
+    for got, ref_ in ((zA3[:, :, :, 0, :], ref3), (zA5[:, :, :, 0, :], ref5)):
+        for il in range(nlm):
+            for cc in range(2):
+                scale = np.abs(ref_[:, :, il, cc]).max(axis=1, keepdims=True)
+                assert np.max(np.abs(got[:, :, il, cc] - ref_[:, :, il, cc]) / scale) < 1e-13
+    del order
